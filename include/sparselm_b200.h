@@ -1,0 +1,180 @@
+/*
+ * sparselm_b200 -- C ABI of the B200 solver engine for sparse-lm's convex estimators.
+ *
+ * This is the drop-in boundary for the reference's solve seam
+ *     CVXRegressor._solve(X, y, solver_options)      src/sparselm/model/_base.py:512-519
+ * (overrides: model/_lasso.py:486-502, model/_adaptive_lasso.py:206-232, 515-524)
+ * and for the (candidate x fold) fan-out that drives it
+ *     GridSearchCV.fit / evaluate_candidates          src/sparselm/model_selection.py:291-359
+ * The reference is pure Python; a maintainer binds this library with ctypes
+ * (see INTEGRATION.md).  All pointers named *_dev are device pointers owned by the
+ * caller (the Python host allocates them as torch tensors); the engine never
+ * frees caller memory.  Every call is ordered on the given CUDA stream
+ * (a cudaStream_t passed as void*).  Return value 0 = success; otherwise an
+ * error code and slm_last_error() describes it.  No C++ exception crosses
+ * this boundary.
+ *
+ * Layouts.  The design matrix lives on the device as the *augmented* row-major
+ * matrix Xa[n][lda] = [ X | y | 1 | 0-pad ], lda = slm_padded_cols(p).  One
+ * symmetric Gram of Xa (pa x pa, pa == lda) therefore carries X^T X, X^T y,
+ * y^T y, the column sums and n.  Batched solver state is feature-major:
+ * Z[f][j][k], fold f, feature j, grid column k (k contiguous, row stride ldz,
+ * ldz % 8 == 0), so one fold's coefficient batch is the row-major B operand of
+ * the tensor-core Gram apply.
+ */
+#ifndef SPARSELM_B200_H
+#define SPARSELM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLM_MAX_FOLDS 16
+
+typedef struct slm_ctx slm_ctx;
+
+/* ---- lifecycle ----------------------------------------------------------- */
+int slm_version(void);
+int slm_create(int device, slm_ctx** out);
+void slm_destroy(slm_ctx* ctx);
+const char* slm_last_error(const slm_ctx* ctx);
+int slm_sm_count(const slm_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t slm_launch_count(const slm_ctx* ctx);
+/* average device time in ms of the `which` kernel family since the last reset,
+ * measured with CUDA events on the launching stream when timing is enabled.
+ * which: 0 = gram build, 1 = gram apply, 2 = prox, 3 = gap, 4 = score */
+int slm_timing_enable(slm_ctx* ctx, int on);
+int slm_timing_read(slm_ctx* ctx, int which, double* total_ms, int64_t* launches, double* flops);
+int slm_timing_reset(slm_ctx* ctx);
+
+/* pa = lda = round_up(p + 2, 8) */
+int64_t slm_padded_cols(int64_t p);
+
+/* ---- K1: design packing and Gram build ----------------------------------- */
+/* replaces: X, y arrival in CVXRegressor.fit / _preprocess_data (_base.py:173-227).
+ * Xa[r][0:p] = sqrt(sw_r) * X[perm? no: r][col_perm[j]], Xa[r][p] = sqrt(sw_r) y_r,
+ * Xa[r][p+1] = sqrt(sw_r), rest 0.  col_perm_dev (int32[p]) may be NULL (identity);
+ * row_perm_dev (int64[n]) may be NULL; sw_dev may be NULL. */
+int slm_pack_design(slm_ctx* ctx, const double* X_dev, int64_t ldx, const double* y_dev,
+                    const double* sw_dev, const int32_t* col_perm_dev,
+                    const int64_t* row_perm_dev, int64_t n, int64_t p, double* Xa_dev,
+                    int64_t lda, void* stream);
+
+/* Gblk[f] = Xa[rows_f]^T Xa[rows_f], rows_f = [row_ptr[f], row_ptr[f+1]); FP64 DMMA
+ * SYRK (upper tiles + mirror).  replaces: the data term cp.sum_squares(X @ beta - y)
+ * (_lasso.py:120) being re-canonicalised for every fit.  row_ptr is a HOST array. */
+int slm_gram_blocks(slm_ctx* ctx, const double* Xa_dev, int64_t lda, const int64_t* row_ptr,
+                    int n_blocks, double* Gblk_dev, void* stream);
+
+/* in place: Gtot = sum_f Gblk[f]; Gblk[f] <- Gtot - Gblk[f]  (training Gram of fold f
+ * when the blocks are the CV test folds, model_selection.py:304-323). */
+int slm_gram_complement(slm_ctx* ctx, double* Gblk_dev, int n_blocks, int64_t pa,
+                        double* Gtot_dev, void* stream);
+
+/* in-place centering of one augmented Gram using its ones row/column
+ * (fit_intercept=True, _base.py:216-222): G <- G - s s^T / n on the [0,p] block. */
+int slm_gram_center(slm_ctx* ctx, double* G_dev, int64_t pa, int64_t p, void* stream);
+
+/* G_ext[a][b] = G[idx[a]][idx[b]] for a,b < pe; rows/cols pe, pe+1 (y, ones) follow.
+ * replaces X_ext = X[:, beta_indices] (_lasso.py:461). pae = slm_padded_cols(pe). */
+int slm_gram_gather(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
+                    const int32_t* idx_dev, int64_t pe, double* Gext_dev, int64_t pae,
+                    void* stream);
+
+/* lambda_max(G[0:p,0:p]) for n_grams Grams (stride g_stride doubles) by batched block
+ * power iteration on the tensor-core apply; result (HOST array lam[n_grams]) is the
+ * largest Rayleigh quotient seen (a lower bound; callers add a margin).
+ * work_dev: >= slm_lipschitz_workspace(p, n_grams) bytes. */
+size_t slm_lipschitz_workspace(int64_t p, int n_grams);
+int slm_lipschitz(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p,
+                  int n_grams, int iters, void* work_dev, double* lam_host, void* stream);
+
+/* ---- K5-K7: the batched accelerated proximal-gradient solve --------------- */
+typedef struct slm_batch {
+    /* problem data */
+    int32_t n_folds;     /* number of Grams in this batch (<= SLM_MAX_FOLDS)          */
+    int32_t n_groups;    /* number of penalty groups (groups contiguous in feature order) */
+    int64_t p;           /* features                                                   */
+    int64_t pa;          /* leading dimension of every Gram                            */
+    int64_t ldz;         /* row stride of all [p][ldz] / [G][ldz] arrays (mult. of 8)  */
+    const double* G_dev; /* Gram f at G_dev + f*g_stride; c_f is its row p, yty = [p][p] */
+    int64_t g_stride;
+    const int32_t* gptr_dev; /* int32[n_groups+1]; NULL => every feature its own group */
+    int32_t K[SLM_MAX_FOLDS];        /* grid columns of fold f (<= ldz)               */
+    double n_obs[SLM_MAX_FOLDS];     /* n of the data term 1/(2n)                      */
+    double lipschitz[SLM_MAX_FOLDS]; /* L >= lambda_max(G_f)/n_f                       */
+    /* penalty weights, all [F][rows][ldz] device arrays with fold stride rows*ldz    */
+    const double* lam1_dev; /* [F][ldz] l1 weight per column, used when W1_dev == NULL */
+    const double* W1_dev;   /* [F][p][ldz] per-coefficient l1 weights or NULL          */
+    const double* W2_dev;   /* [F][n_groups][ldz] group-l2 weights or NULL (=0)        */
+    const double* D2_dev;   /* [F][n_groups][ldz] ridge weights or NULL (=0)           */
+    /* state: B in = start point, out = solution                                       */
+    double* B_dev;          /* [F][p][ldz]                                             */
+    const int32_t* skip_dev; /* [F][ldz] or NULL: columns with skip != 0 are left untouched
+                              * (adaptive chains whose weights already converged)       */
+    void* work_dev;         /* >= slm_solve_workspace(...) bytes                        */
+    size_t work_bytes;
+    /* control */
+    double tol;        /* stop when gap <= tol * max(|primal|, floor_rel * yty/(2n))    */
+    double floor_rel;
+    int32_t max_iter;
+    int32_t check_every;
+    /* per-column results, [F][ldz] device arrays (may be NULL) */
+    double* gap_dev;
+    double* primal_dev;
+    int32_t* n_iter_dev;
+    int32_t* status_dev; /* 0 converged, 1 max_iter reached, 2 non-finite */
+    /* host outputs */
+    int32_t iters_run;     /* outer iterations executed */
+    int32_t n_unconverged; /* columns that hit max_iter */
+} slm_batch;
+
+size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups);
+
+/* replaces cp.Problem.solve for every (fold, grid column) at once (_base.py:516). */
+int slm_solve_batch(slm_ctx* ctx, slm_batch* batch, void* stream);
+
+/* ---- K8: adaptive reweighting (_adaptive_lasso.py:196-204, 364-374, 712-726) -----
+ * W1[j][k] = a1[k] * alpha[k] / (|B[j][k]| + eps)            (if W1_dev != NULL)
+ * W2[g][k] = a2[k] * gw[g] * alpha[k] / (||B_g[:,k]|| + eps)  (if W2_dev != NULL)
+ * dnorm[k] = || [W2;W1]_new - [W2;W1]_old ||_2  (convergence test :189-194, :698-710) */
+int slm_adaptive_update(slm_ctx* ctx, const double* B_dev, int64_t p, int64_t ldz, int32_t K,
+                        int32_t n_groups, const int32_t* gptr_dev, const double* gw_dev,
+                        const double* a1_dev, const double* a2_dev, const double* alpha_dev,
+                        double eps, double* W1_dev, double* W2_dev, double* dnorm_dev,
+                        void* stream);
+
+/* ---- K9: overlap fold-back (_lasso.py:492-501) ----------------------------------
+ * coef[j][k] = sum_{t in [inv_ptr[j], inv_ptr[j+1])} Bext[inv_idx[t]][k]
+ * (CSR inverse of beta_indices, summed in ascending order: deterministic). */
+int slm_fold_back(slm_ctx* ctx, const double* Bext_dev, const int32_t* inv_ptr_dev,
+                  const int32_t* inv_idx_dev, int64_t p, int64_t ldz, int32_t K,
+                  double* coef_dev, void* stream);
+
+/* ---- K10: CV scoring (sklearn scorer inside _fit_and_score, model_selection.py:305)
+ * rows [r0, r1) of Xa are the test fold; B [p][ldz]; intercept[k] may be NULL.
+ * out_dev[0][k] = sum (y - yhat)^2, out_dev[1][k] = sum |y - yhat|  (ldz stride).
+ * yhat_dev: scratch [(r1-r0) + 256][ldz] (predictions, then partial sums). */
+int slm_cv_score(slm_ctx* ctx, const double* Xa_dev, int64_t lda, int64_t p, int64_t r0,
+                 int64_t r1, const double* B_dev, int64_t ldz, int32_t K,
+                 const double* intercept_dev, double* yhat_dev, double* out_dev, void* stream);
+
+/* intercept[k] = ybar - mu^T B[:,k] from the (uncentred) training Gram's ones row
+ * (LinearModel._set_intercept, _base.py:202). */
+int slm_intercepts(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
+                   const double* B_dev, int64_t ldz, int32_t K, double* intercept_dev,
+                   void* stream);
+
+/* plain batched tensor-core apply GZ_f = G_f Z_f (exposed for tests / roofline runs) */
+int slm_gram_apply(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p,
+                   int n_folds, const int32_t* K, const double* Z_dev, int64_t ldz,
+                   double* GZ_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPARSELM_B200_H */

@@ -60,7 +60,7 @@ def build(force: bool = False) -> str:
     ):
         return _LIB_PATH
     os.makedirs(os.path.dirname(_LIB_PATH), exist_ok=True)
-    cmd = ["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", _LIB_PATH, src, "-lm"]
+    cmd = ["gcc", "-O3", "-fopenmp", "-shared", "-fPIC", "-o", _LIB_PATH, src, "-lm"]
     subprocess.run(cmd, check=True)
     return _LIB_PATH
 

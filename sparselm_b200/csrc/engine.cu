@@ -1,0 +1,976 @@
+// sparselm_b200 engine: CUDA kernels (sm_100a) + C ABI (include/sparselm_b200.h).
+//
+// Kernel inventory:
+//   K1  gram build      gemm_f64_kernel<..., SYM>      (gemm_f64.cuh)   FP64 tensor
+//   K2  centering       gram_center_kernel                             HBM
+//   K3  overlap gather  gram_gather_kernel                             HBM
+//   K4  lipschitz       gemm apply (N=8) + power_norm_kernel           HBM (N=8)
+//   K5  gram apply      gemm_f64_kernel<...>                           FP64 tensor
+//   K6  prox epilogue   prox_kernel  (momentum, soft-threshold, group shrink, ridge)
+//   K7  gap + mask      gap_kernel   (duality gap, per-column convergence flag)
+//   K8  reweighting     adaptive_kernel
+//   K9  fold back       fold_back_kernel
+//   K10 scoring         gemm_f64_kernel<A_MMAJOR> + score_kernel
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sparselm_b200.h"
+#include "gemm_f64.cuh"
+#include "solver_kernels.cuh"
+
+using namespace slm;
+
+// ------------------------------------------------------------------------- //
+// context
+// ------------------------------------------------------------------------- //
+enum { FAM_GRAM = 0, FAM_APPLY = 1, FAM_PROX = 2, FAM_GAP = 3, FAM_SCORE = 4, FAM_COUNT = 5 };
+
+struct Family {
+    std::vector<cudaEvent_t> ev;  // begin/end pairs not yet accumulated
+    std::vector<cudaEvent_t> pool;
+    double ms = 0.0;
+    double flops = 0.0;
+    int64_t n = 0;
+};
+
+struct slm_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    int64_t launches = 0;
+    bool timing = false;
+    Family fam[FAM_COUNT];
+    int* d_counter = nullptr;
+    int* h_counter = nullptr;
+    int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
+    int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
+};
+
+static int fail(slm_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CUDA_OK(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(ctx, 100 + (int)e__,                                               \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+#define LAUNCH_OK(name)                                                                    \
+    do {                                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(ctx, 100 + (int)e__, std::string(name) + ": " + cudaGetErrorString(e__)); \
+        ctx->launches++;                                                                   \
+    } while (0)
+
+struct FamTimer {  // RAII event pair around a launch when timing is on
+    slm_ctx* ctx;
+    int fam;
+    cudaStream_t s;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    FamTimer(slm_ctx* c, int f, cudaStream_t st, double flops) : ctx(c), fam(f), s(st) {
+        Family& F = ctx->fam[fam];
+        F.flops += flops;
+        F.n += 1;
+        if (!ctx->timing) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!F.pool.empty()) {
+                e = F.pool.back();
+                F.pool.pop_back();
+            } else {
+                cudaEventCreate(&e);
+            }
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, s);
+    }
+    ~FamTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, s);
+        ctx->fam[fam].ev.push_back(e0);
+        ctx->fam[fam].ev.push_back(e1);
+    }
+};
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------- //
+// GEMM dispatch
+// ------------------------------------------------------------------------- //
+constexpr int kBK = 16;
+constexpr int kStages = 4;
+
+struct Shape {
+    int bm, bn;
+    int minb;   // CTAs per SM the kernel is built for
+    double eff; // measured fraction of the per-SM DMMA peak this warp layout reaches
+};
+
+static void fill_units(GemmBatch& b, const Shape& sh, bool sym, int sms) {
+    long long u = 0;
+    int max_kt = 1;
+    for (int i = 0; i < b.n_problems; ++i) {
+        GemmProblem& pr = b.pr[i];
+        pr.tiles_m = (pr.M + sh.bm - 1) / sh.bm;
+        pr.tiles_n = (pr.N + sh.bn - 1) / sh.bn;
+        pr.kt = std::max(1, (pr.Kd + kBK - 1) / kBK);
+        if (pr.N <= 0 || pr.M <= 0 || pr.Kd <= 0) pr.tiles_m = pr.tiles_n = 0;
+        pr.n_tiles = sym ? pr.tiles_n * (pr.tiles_n + 1) / 2 : pr.tiles_m * pr.tiles_n;
+        pr.unit_begin = (int)u;
+        u += (long long)pr.n_tiles * pr.kt;
+        if (pr.n_tiles > 0) max_kt = std::max(max_kt, pr.kt);
+    }
+    b.total_units = (int)u;
+    // range length >= slabs per tile => at most two contributions per tile
+    long long n_cta = std::min<long long>((long long)sms * sh.minb, std::max<long long>(1, u / max_kt));
+    b.units_per_cta = (int)((u + n_cta - 1) / n_cta);
+    if (b.units_per_cta < max_kt) b.units_per_cta = max_kt;
+}
+
+template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB>
+static cudaError_t launch_gemm_t(const GemmBatch& b, cudaStream_t s) {
+    using Cfg = GemmCfg<WM, WN, MI, NI, kBK, kStages, AM>;
+    auto kern = gemm_f64_kernel<WM, WN, MI, NI, kBK, kStages, AM, SYM, MINB>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (b.total_units <= 0) return cudaSuccess;
+    int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
+    kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b);
+    return cudaGetLastError();
+}
+
+// K-major (apply) menu; index = shape id
+static const Shape kApplyShapes[] = {
+    {128, 128, 1, 0.84}, {128, 104, 1, 0.79}, {128, 104, 1, 0.85}, {128, 56, 2, 0.85}, {128, 128, 1, 0.85},
+    {128, 64, 2, 0.85},  {64, 104, 2, 0.85},  {128, 32, 2, 0.80},  {128, 16, 2, 0.70}, {128, 8, 2, 0.60},
+};
+constexpr int kNumApplyShapes = sizeof(kApplyShapes) / sizeof(Shape);
+
+static cudaError_t launch_apply_shape(int id, const GemmBatch& b, cudaStream_t s) {
+    switch (id) {
+        case 0: return launch_gemm_t<2, 4, 8, 4, false, false, 1>(b, s);
+        case 1: return launch_gemm_t<8, 1, 2, 13, false, false, 1>(b, s);
+        case 2: return launch_gemm_t<16, 1, 1, 13, false, false, 1>(b, s);
+        case 3: return launch_gemm_t<8, 1, 2, 7, false, false, 2>(b, s);
+        case 4: return launch_gemm_t<4, 4, 4, 4, false, false, 1>(b, s);
+        case 5: return launch_gemm_t<4, 2, 4, 4, false, false, 2>(b, s);
+        case 6: return launch_gemm_t<8, 1, 1, 13, false, false, 2>(b, s);
+        case 7: return launch_gemm_t<8, 1, 2, 4, false, false, 2>(b, s);
+        case 8: return launch_gemm_t<8, 1, 2, 2, false, false, 2>(b, s);
+        case 9: return launch_gemm_t<8, 1, 2, 1, false, false, 2>(b, s);
+    }
+    return cudaErrorInvalidValue;
+}
+// M-major (scoring) menu
+static const Shape kScoreShapes[] = {{128, 128, 1, 0.84}, {128, 64, 2, 0.85}, {128, 32, 2, 0.8}, {128, 16, 2, 0.7}, {128, 8, 2, 0.6}};
+constexpr int kNumScoreShapes = sizeof(kScoreShapes) / sizeof(Shape);
+static cudaError_t launch_score_shape(int id, const GemmBatch& b, cudaStream_t s) {
+    switch (id) {
+        case 0: return launch_gemm_t<2, 4, 8, 4, true, false, 1>(b, s);
+        case 1: return launch_gemm_t<4, 2, 4, 4, true, false, 2>(b, s);
+        case 2: return launch_gemm_t<8, 1, 2, 4, true, false, 2>(b, s);
+        case 3: return launch_gemm_t<8, 1, 2, 2, true, false, 2>(b, s);
+        case 4: return launch_gemm_t<8, 1, 2, 1, true, false, 2>(b, s);
+    }
+    return cudaErrorInvalidValue;
+}
+// symmetric (Gram build) menu
+static const Shape kSyrkShapes[] = {{128, 128, 1, 0.84}, {128, 128, 1, 0.85}};
+static cudaError_t launch_syrk_shape(int id, const GemmBatch& b, cudaStream_t s) {
+    switch (id) {
+        case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1>(b, s);
+        case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1>(b, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+struct ProblemDims {
+    int M, N;
+};
+// cost model: the kernel is DMMA-bound and stream-K balances the SMs, so time is
+// (padded tile work) / (efficiency of the warp layout).
+static int pick_shape(const Shape* shapes, int n_shapes, const ProblemDims* pd, int np, int sms) {
+    (void)sms;
+    int best = 0;
+    double best_cost = 1e300;
+    for (int s = 0; s < n_shapes; ++s) {
+        double work = 0.0;
+        for (int i = 0; i < np; ++i) {
+            if (pd[i].N <= 0) continue;
+            work += (double)((pd[i].M + shapes[s].bm - 1) / shapes[s].bm) *
+                    ((pd[i].N + shapes[s].bn - 1) / shapes[s].bn) * shapes[s].bm * shapes[s].bn;
+        }
+        double cost = work / shapes[s].eff;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = s;
+        }
+    }
+    return best;
+}
+
+// batched apply: GZ_f = G_f Z_f for f < F, with N_f = round_up(K_f, 8)
+static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int F,
+                         const int32_t* K, const double* Z, int64_t ldz, double* GZ, cudaStream_t s,
+                         double algo_flops = -1.0) {
+    for (int f0 = 0; f0 < F; f0 += kMaxGemmProblems) {
+        int nf = std::min(F - f0, (int)kMaxGemmProblems);
+        GemmBatch b;
+        memset(&b, 0, sizeof(b));
+        ProblemDims pd[kMaxGemmProblems];
+        double flops = 0.0;
+        b.n_problems = nf;
+        for (int i = 0; i < nf; ++i) {
+            int f = f0 + i;
+            GemmProblem& pr = b.pr[i];
+            pr.P = G + (int64_t)f * g_stride;
+            pr.Q = Z + (int64_t)f * p * ldz;
+            pr.C = GZ + (int64_t)f * p * ldz;
+            pr.ldp = pa;
+            pr.ldq = ldz;
+            pr.ldc = ldz;
+            pr.M = (int)p;
+            pr.N = (int)std::min<int64_t>(round_up(K[f], 8), ldz);
+            pr.Kd = (int)p;
+            pd[i] = {pr.M, pr.N};
+            flops += 2.0 * (double)p * (double)p * (double)K[f];
+        }
+        int sid = pick_shape(kApplyShapes, kNumApplyShapes, pd, nf, ctx->sm_count);
+        if (ctx->force_apply_shape >= 0 && ctx->force_apply_shape < kNumApplyShapes) sid = ctx->force_apply_shape;
+        fill_units(b, kApplyShapes[sid], false, ctx->sm_count);
+        FamTimer tm(ctx, FAM_APPLY, s, algo_flops >= 0 ? algo_flops : flops);
+        // partial tiles are accumulated with atomics: the output starts from zero
+        cudaMemsetAsync(GZ + (int64_t)f0 * p * ldz, 0, sizeof(double) * (size_t)nf * p * ldz, s);
+        cudaError_t e = launch_apply_shape(sid, b, s);
+        if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("gram apply: ") + cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------- //
+// small kernels: packing, complement, centering, gather
+// ------------------------------------------------------------------------- //
+__global__ void pack_design_kernel(const double* __restrict__ X, long long ldx,
+                                   const double* __restrict__ y, const double* __restrict__ sw,
+                                   const int* __restrict__ col_perm,
+                                   const long long* __restrict__ row_perm, long long n, int p,
+                                   double* __restrict__ Xa, long long lda) {
+    long long r = blockIdx.y;
+    long long src_r = row_perm ? row_perm[r] : r;
+    double s = sw ? sqrt(sw[src_r]) : 1.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < lda; j += gridDim.x * blockDim.x) {
+        double v;
+        if (j < p) {
+            int sj = col_perm ? col_perm[j] : j;
+            v = s * X[src_r * ldx + sj];
+        } else if (j == p) {
+            v = s * y[src_r];
+        } else if (j == p + 1) {
+            v = s;
+        } else {
+            v = 0.0;
+        }
+        Xa[r * lda + j] = v;
+    }
+}
+
+__global__ void gram_complement_kernel(double* __restrict__ Gblk, int nb, long long stride,
+                                       double* __restrict__ Gtot) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= stride) return;
+    double vals[SLM_MAX_FOLDS];
+    double tot = 0.0;
+    for (int f = 0; f < nb; ++f) {
+        vals[f] = Gblk[(long long)f * stride + i];
+        tot += vals[f];
+    }
+    Gtot[i] = tot;
+    for (int f = 0; f < nb; ++f) {
+        // sum of the other blocks in a fixed order (no subtraction => no cancellation)
+        double acc = 0.0;
+        for (int g = 0; g < nb; ++g)
+            if (g != f) acc += vals[g];
+        Gblk[(long long)f * stride + i] = acc;
+    }
+}
+
+__global__ void gram_center_kernel(double* __restrict__ G, long long pa, int p) {
+    // rows/cols 0..p (features and y); ones row p+1 kept intact
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j > p || i > p) return;
+    const double* ones = G + (long long)(p + 1) * pa;
+    double n = ones[p + 1];
+    G[(long long)i * pa + j] -= ones[i] * ones[j] / n;
+}
+
+__global__ void gram_gather_kernel(const double* __restrict__ G, long long pa, int p,
+                                   const int* __restrict__ idx, int pe, double* __restrict__ Ge,
+                                   long long pae) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int a = blockIdx.y;
+    if (b >= pae) return;
+    double v = 0.0;
+    if (a < pe + 2 && b < pe + 2) {
+        int ia = a < pe ? idx[a] : p + (a - pe);
+        int ib = b < pe ? idx[b] : p + (b - pe);
+        v = G[(long long)ia * pa + ib];
+    }
+    Ge[(long long)a * pae + b] = v;
+}
+
+// ------------------------------------------------------------------------- //
+// solver kernels
+// ------------------------------------------------------------------------- //
+constexpr int CT = 4;          // grid columns per block (adaptive kernel)
+constexpr int PT = 256;        // threads per block
+constexpr int NGL = PT / CT;   // group lanes per block
+
+template <typename T>
+__device__ __forceinline__ T block_col_reduce_sum(T v, T (*red)[CT], int gl, int c) {
+    red[gl][c] = v;
+    __syncthreads();
+#pragma unroll
+    for (int s = NGL / 2; s > 0; s >>= 1) {
+        if (gl < s) red[gl][c] += red[gl + s][c];
+        __syncthreads();
+    }
+    T r = red[0][c];
+    __syncthreads();
+    return r;
+}
+
+__global__ void init_cols_kernel(double* theta, double* tmom, int* flag, int* status, int* n_iter,
+                                 const int* skip, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    theta[i] = theta[n + i] = 0.0;  // both parities
+    tmom[i] = tmom[n + i] = 1.0;
+    if (skip && skip[i]) {
+        flag[i] = 3;  // frozen from the start; results of the earlier solve are kept
+        return;
+    }
+    flag[i] = 0;
+    if (status) status[i] = -1;
+    if (n_iter) n_iter[i] = 0;
+}
+
+// K4 helper: V <- W/||W|| per column, tracks the largest Rayleigh quotient.
+__global__ void __launch_bounds__(256) power_norm_kernel(double* __restrict__ V, const double* __restrict__ W,
+                                                         int p, double* __restrict__ lam, int init) {
+    const int f = blockIdx.x;
+    const int c = threadIdx.x & 7, r = threadIdx.x >> 3;  // 8 columns x 32 row lanes
+    double* Vf = V + (long long)f * p * 8;
+    const double* Wf = W + (long long)f * p * 8;
+    __shared__ double red[3][32][8];
+    if (init) {
+        for (int j = r; j < p; j += 32) {
+            unsigned h = (unsigned)(j * 8 + c) * 2654435761u + 12345u * (unsigned)(f + 1);
+            h ^= h >> 15;
+            h *= 2246822519u;
+            h ^= h >> 13;
+            Vf[(long long)j * 8 + c] = ((double)(h & 0xffffff) / 8388608.0) - 1.0;
+        }
+        if (threadIdx.x == 0) lam[f] = 0.0;
+        return;
+    }
+    double vw = 0.0, ww = 0.0, vv = 0.0;
+    for (int j = r; j < p; j += 32) {
+        double v = Vf[(long long)j * 8 + c], w = Wf[(long long)j * 8 + c];
+        vw += v * w;
+        ww += w * w;
+        vv += v * v;
+    }
+    red[0][r][c] = vw;
+    red[1][r][c] = ww;
+    red[2][r][c] = vv;
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (r < s) {
+            red[0][r][c] += red[0][r + s][c];
+            red[1][r][c] += red[1][r + s][c];
+            red[2][r][c] += red[2][r + s][c];
+        }
+        __syncthreads();
+    }
+    vw = red[0][0][c];
+    ww = red[1][0][c];
+    vv = red[2][0][c];
+    if (threadIdx.x == 0) {
+        double best = lam[f];
+        for (int cc = 0; cc < 8; ++cc) {
+            double q = red[2][0][cc] > 0.0 ? red[0][0][cc] / red[2][0][cc] : 0.0;
+            best = fmax(best, q);
+        }
+        lam[f] = best;
+    }
+    const double inv = ww > 0.0 ? rsqrt(ww) : 0.0;
+    for (int j = r; j < p; j += 32) Vf[(long long)j * 8 + c] = Wf[(long long)j * 8 + c] * inv;
+}
+
+// K8: adaptive reweighting.
+__global__ void __launch_bounds__(PT) adaptive_kernel(const double* __restrict__ B, int p, long long ldz, int K,
+                                                      int Gn, const int* __restrict__ gptr,
+                                                      const double* __restrict__ gw,
+                                                      const double* __restrict__ a1,
+                                                      const double* __restrict__ a2,
+                                                      const double* __restrict__ alpha, double eps,
+                                                      double* __restrict__ W1, double* __restrict__ W2,
+                                                      double* __restrict__ dnorm) {
+    const int k0 = blockIdx.x * CT;
+    const int c = threadIdx.x % CT, gl = threadIdx.x / CT;
+    const int k = k0 + c;
+    const bool colok = k < K;
+    __shared__ double red[NGL][CT];
+    double acc = 0.0;
+    if (colok) {
+        const double al = alpha[k];
+        const double s1 = a1 ? a1[k] : 0.0;
+        const double s2 = a2 ? a2[k] : 0.0;
+        for (int g = gl; g < Gn; g += NGL) {
+            const int ja = gptr ? gptr[g] : g;
+            const int jb = gptr ? gptr[g + 1] : g + 1;
+            double ss = 0.0;
+            for (int j = ja; j < jb; ++j) {
+                const double b = B[(long long)j * ldz + k];
+                ss += b * b;
+                if (W1) {
+                    const double wn = s1 * (al / (fabs(b) + eps));
+                    const double d = wn - W1[(long long)j * ldz + k];
+                    acc += d * d;
+                    W1[(long long)j * ldz + k] = wn;
+                }
+            }
+            if (W2) {
+                const double wn = (s2 * (gw ? gw[g] : 1.0)) * (al / (sqrt(ss) + eps));
+                const double d = wn - W2[(long long)g * ldz + k];
+                acc += d * d;
+                W2[(long long)g * ldz + k] = wn;
+            }
+        }
+    }
+    acc = block_col_reduce_sum<double>(acc, red, gl, c);
+    if (colok && gl == 0 && dnorm) dnorm[k] = sqrt(acc);
+}
+
+// K9
+__global__ void fold_back_kernel(const double* __restrict__ Be, const int* __restrict__ inv_ptr,
+                                 const int* __restrict__ inv_idx, int p, long long ldz, int K,
+                                 double* __restrict__ coef) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (k >= K || j >= p) return;
+    double acc = 0.0;
+    for (int t = inv_ptr[j]; t < inv_ptr[j + 1]; ++t) acc += Be[(long long)inv_idx[t] * ldz + k];
+    coef[(long long)j * ldz + k] = acc;
+}
+
+// K10: residual reductions, two deterministic stages.
+constexpr int SCORE_RB = 128;  // row blocks
+__global__ void __launch_bounds__(256) score_partial_kernel(const double* __restrict__ Xa, long long lda, int p,
+                                                            long long r0, long long m,
+                                                            const double* __restrict__ yhat, long long ldz,
+                                                            int K, const double* __restrict__ icpt,
+                                                            double* __restrict__ part) {
+    // block = 8 columns x 32 row lanes; grid = (ceil(K/8), SCORE_RB)
+    const int c = threadIdx.x & 7, r = threadIdx.x >> 3;
+    const int k = blockIdx.x * 8 + c;
+    __shared__ double red[2][32][8];
+    double sse = 0.0, sae = 0.0;
+    if (k < K) {
+        const double b0 = icpt ? icpt[k] : 0.0;
+        for (long long i = (long long)blockIdx.y * 32 + r; i < m; i += (long long)SCORE_RB * 32) {
+            const double* row = Xa + (r0 + i) * lda;
+            const double d = row[p] - yhat[i * ldz + k] - b0 * row[p + 1];
+            sse += d * d;
+            sae += fabs(d);
+        }
+    }
+    red[0][r][c] = sse;
+    red[1][r][c] = sae;
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (r < s) {
+            red[0][r][c] += red[0][r + s][c];
+            red[1][r][c] += red[1][r + s][c];
+        }
+        __syncthreads();
+    }
+    if (r == 0 && k < K) {
+        part[((long long)blockIdx.y * 2 + 0) * ldz + k] = red[0][0][c];
+        part[((long long)blockIdx.y * 2 + 1) * ldz + k] = red[1][0][c];
+    }
+}
+__global__ void score_final_kernel(const double* __restrict__ part, long long ldz, int K,
+                                   double* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double sse = 0.0, sae = 0.0;
+    for (int b = 0; b < SCORE_RB; ++b) {
+        sse += part[((long long)b * 2 + 0) * ldz + k];
+        sae += part[((long long)b * 2 + 1) * ldz + k];
+    }
+    out[k] = sse;
+    out[ldz + k] = sae;
+}
+
+__global__ void __launch_bounds__(256) intercept_kernel(const double* __restrict__ G, long long pa, int p,
+                                                        const double* __restrict__ B, long long ldz, int K,
+                                                        double* __restrict__ icpt) {
+    const int c = threadIdx.x & 7, r = threadIdx.x >> 3;
+    const int k = blockIdx.x * 8 + c;
+    __shared__ double red[32][8];
+    const double* ones = G + (long long)(p + 1) * pa;
+    double acc = 0.0;
+    if (k < K)
+        for (int j = r; j < p; j += 32) acc += ones[j] * B[(long long)j * ldz + k];
+    red[r][c] = acc;
+    __syncthreads();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (r < s) red[r][c] += red[r + s][c];
+        __syncthreads();
+    }
+    if (r == 0 && k < K) {
+        const double n = ones[p + 1];
+        icpt[k] = (ones[p] - red[0][c]) / n;
+    }
+}
+
+// ------------------------------------------------------------------------- //
+// C ABI
+// ------------------------------------------------------------------------- //
+extern "C" {
+
+int slm_version(void) { return 1; }
+
+int64_t slm_padded_cols(int64_t p) { return round_up(p + 2, 8); }
+
+int slm_create(int device, slm_ctx** out) {
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return 2;  // no CUDA device: fail loudly, no fallback
+    if (device < 0 || device >= ndev) return 3;
+    if (cudaSetDevice(device) != cudaSuccess) return 4;
+    slm_ctx* ctx = new slm_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return 5;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("SLM_FORCE_APPLY_SHAPE")) ctx->force_apply_shape = atoi(e);
+    if (const char* e = getenv("SLM_FORCE_SYRK_SHAPE")) ctx->force_syrk_shape = atoi(e);
+    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counter, sizeof(int)) != cudaSuccess) {
+        delete ctx;
+        return 6;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void slm_destroy(slm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& F : ctx->fam) {
+        for (auto e : F.ev) cudaEventDestroy(e);
+        for (auto e : F.pool) cudaEventDestroy(e);
+    }
+    if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
+    delete ctx;
+}
+
+const char* slm_last_error(const slm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int slm_sm_count(const slm_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int64_t slm_launch_count(const slm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int slm_timing_enable(slm_ctx* ctx, int on) {
+    if (!ctx) return 1;
+    ctx->timing = on != 0;
+    return 0;
+}
+static void timing_collect(slm_ctx* ctx) {
+    for (auto& F : ctx->fam) {
+        for (size_t i = 0; i + 1 < F.ev.size(); i += 2) {
+            float ms = 0.f;
+            cudaEventSynchronize(F.ev[i + 1]);
+            if (cudaEventElapsedTime(&ms, F.ev[i], F.ev[i + 1]) == cudaSuccess) F.ms += ms;
+            F.pool.push_back(F.ev[i]);
+            F.pool.push_back(F.ev[i + 1]);
+        }
+        F.ev.clear();
+    }
+}
+int slm_timing_read(slm_ctx* ctx, int which, double* total_ms, int64_t* launches, double* flops) {
+    if (!ctx || which < 0 || which >= FAM_COUNT) return 1;
+    timing_collect(ctx);
+    if (total_ms) *total_ms = ctx->fam[which].ms;
+    if (launches) *launches = ctx->fam[which].n;
+    if (flops) *flops = ctx->fam[which].flops;
+    return 0;
+}
+int slm_timing_reset(slm_ctx* ctx) {
+    if (!ctx) return 1;
+    timing_collect(ctx);
+    for (auto& F : ctx->fam) {
+        F.ms = 0.0;
+        F.flops = 0.0;
+        F.n = 0;
+    }
+    return 0;
+}
+
+int slm_pack_design(slm_ctx* ctx, const double* X, int64_t ldx, const double* y, const double* sw,
+                    const int32_t* col_perm, const int64_t* row_perm, int64_t n, int64_t p, double* Xa,
+                    int64_t lda, void* stream) {
+    if (!ctx || !X || !y || !Xa) return fail(ctx, 1, "slm_pack_design: null argument");
+    if (lda < p + 2 || (lda & 1)) return fail(ctx, 1, "slm_pack_design: lda must be even and >= p+2");
+    if (n <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int bx = (int)std::min<int64_t>((lda + 255) / 256, 64);
+    for (int64_t r0 = 0; r0 < n; r0 += 65535) {  // gridDim.y limit
+        int64_t nr = std::min<int64_t>(65535, n - r0);
+        dim3 grid(bx, (unsigned)nr);
+        // row r of this chunk is global row r0 + r
+        pack_design_kernel<<<grid, 256, 0, s>>>(X + (row_perm ? 0 : r0 * ldx), ldx, y + (row_perm ? 0 : r0),
+                                                sw ? sw + (row_perm ? 0 : r0) : nullptr, col_perm,
+                                                row_perm ? (const long long*)(row_perm + r0) : nullptr, nr,
+                                                (int)p, Xa + r0 * lda, lda);
+        LAUNCH_OK("pack_design_kernel");
+    }
+    return 0;
+}
+
+int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* row_ptr, int n_blocks,
+                    double* Gblk, void* stream) {
+    if (!ctx || !Xa || !row_ptr || !Gblk) return fail(ctx, 1, "slm_gram_blocks: null argument");
+    if (lda % 8) return fail(ctx, 1, "slm_gram_blocks: lda must be a multiple of 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    int sid = ctx->force_syrk_shape >= 0 && ctx->force_syrk_shape < 2 ? ctx->force_syrk_shape : 0;
+    const Shape sh = kSyrkShapes[sid];
+    for (int f0 = 0; f0 < n_blocks; f0 += kMaxGemmProblems) {
+        int nf = std::min(n_blocks - f0, (int)kMaxGemmProblems);
+        GemmBatch b;
+        memset(&b, 0, sizeof(b));
+        b.n_problems = nf;
+        double flops = 0.0;
+        for (int i = 0; i < nf; ++i) {
+            int f = f0 + i;
+            GemmProblem& pr = b.pr[i];
+            int64_t r0 = row_ptr[f], r1 = row_ptr[f + 1];
+            pr.P = pr.Q = Xa + r0 * lda;
+            pr.C = Gblk + (int64_t)f * lda * lda;
+            pr.ldp = pr.ldq = pr.ldc = lda;
+            pr.M = pr.N = (int)lda;
+            pr.Kd = (int)(r1 - r0);
+            flops += (double)(r1 - r0) * (double)lda * (double)(lda + 1);  // SYRK count
+        }
+        fill_units(b, sh, true, ctx->sm_count);
+        FamTimer tm(ctx, FAM_GRAM, s, flops);
+        cudaMemsetAsync(Gblk + (int64_t)f0 * lda * lda, 0, sizeof(double) * (size_t)nf * lda * lda, s);
+        cudaError_t e = launch_syrk_shape(sid, b, s);
+        if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("gram build: ") + cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    return 0;
+}
+
+int slm_gram_complement(slm_ctx* ctx, double* Gblk, int n_blocks, int64_t pa, double* Gtot, void* stream) {
+    if (!ctx || !Gblk || !Gtot) return fail(ctx, 1, "slm_gram_complement: null argument");
+    if (n_blocks > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_gram_complement: too many blocks");
+    long long stride = (long long)pa * pa;
+    gram_complement_kernel<<<(unsigned)((stride + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Gblk, n_blocks,
+                                                                                            stride, Gtot);
+    LAUNCH_OK("gram_complement_kernel");
+    return 0;
+}
+
+int slm_gram_center(slm_ctx* ctx, double* G, int64_t pa, int64_t p, void* stream) {
+    if (!ctx || !G) return fail(ctx, 1, "slm_gram_center: null argument");
+    // NOTE: every thread reads the (unmodified) ones row; rows 0..p are updated
+    dim3 grid((unsigned)((p + 1 + 255) / 256), (unsigned)(p + 1));
+    gram_center_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, pa, (int)p);
+    LAUNCH_OK("gram_center_kernel");
+    return 0;
+}
+
+int slm_gram_gather(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const int32_t* idx, int64_t pe,
+                    double* Ge, int64_t pae, void* stream) {
+    if (!ctx || !G || !idx || !Ge) return fail(ctx, 1, "slm_gram_gather: null argument");
+    if (pae < pe + 2) return fail(ctx, 1, "slm_gram_gather: pae too small");
+    dim3 grid((unsigned)((pae + 255) / 256), (unsigned)pae);
+    gram_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, pa, (int)p, idx, (int)pe, Ge, pae);
+    LAUNCH_OK("gram_gather_kernel");
+    return 0;
+}
+
+int slm_gram_apply(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_folds,
+                   const int32_t* K, const double* Z, int64_t ldz, double* GZ, void* stream) {
+    if (!ctx || !G || !K || !Z || !GZ) return fail(ctx, 1, "slm_gram_apply: null argument");
+    if (ldz % 8 || pa % 2) return fail(ctx, 1, "slm_gram_apply: ldz must be a multiple of 8, pa even");
+    return apply_batched(ctx, G, g_stride, pa, p, n_folds, K, Z, ldz, GZ, (cudaStream_t)stream);
+}
+
+size_t slm_lipschitz_workspace(int64_t p, int n_grams) {
+    return (size_t)(2 * (int64_t)n_grams * p * 8 + n_grams) * sizeof(double);
+}
+
+int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_grams,
+                  int iters, void* work, double* lam_host, void* stream) {
+    if (!ctx || !G || !work || !lam_host) return fail(ctx, 1, "slm_lipschitz: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* V = (double*)work;
+    double* W = V + (int64_t)n_grams * p * 8;
+    double* lam = W + (int64_t)n_grams * p * 8;
+    std::vector<int32_t> K(n_grams, 8);
+    power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 1);
+    LAUNCH_OK("power_norm_kernel(init)");
+    for (int it = 0; it < iters; ++it) {
+        int rc = apply_batched(ctx, G, g_stride, pa, p, n_grams, K.data(), V, 8, W, s, 0.0);
+        if (rc) return rc;
+        power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 0);
+        LAUNCH_OK("power_norm_kernel");
+    }
+    CUDA_OK(cudaMemcpyAsync(lam_host, lam, sizeof(double) * n_grams, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups) {
+    (void)n_groups;
+    size_t state = (size_t)n_folds * (size_t)p * (size_t)ldz * sizeof(double);
+    size_t cols = (size_t)n_folds * (size_t)ldz;
+    size_t part = cols * (size_t)kMaxChunks * NQ * sizeof(double);
+    return 4 * state + cols * (4 * sizeof(double) + sizeof(int)) + part + 256;
+}
+
+int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
+    if (!ctx || !bt) return fail(ctx, 1, "slm_solve_batch: null argument");
+    if (bt->n_folds < 1 || bt->n_folds > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_solve_batch: n_folds out of range");
+    if (bt->ldz % 8) return fail(ctx, 1, "slm_solve_batch: ldz must be a multiple of 8");
+    if (!bt->G_dev || !bt->B_dev || !bt->work_dev) return fail(ctx, 1, "slm_solve_batch: null device pointer");
+    const int F = bt->n_folds;
+    const int64_t p = bt->p, ldz = bt->ldz;
+    if (bt->work_bytes < slm_solve_workspace(p, ldz, F, bt->n_groups))
+        return fail(ctx, 1, "slm_solve_batch: workspace too small");
+    const int Gn = bt->gptr_dev ? bt->n_groups : (int)p;
+    cudaStream_t s = (cudaStream_t)stream;
+
+    const size_t state = (size_t)F * p * ldz;
+    const size_t cols = (size_t)F * ldz;
+    double* Z = (double*)bt->work_dev;
+    double* GZ = Z + state;
+    double* GB = GZ + state;
+    double* T = GB + state;
+    double* theta = T + state;       // [2][cols]
+    double* tmom = theta + 2 * cols;  // [2][cols]
+    double* part = tmom + 2 * cols;   // [F][n_chunks][NQ][ldz]
+    int* flag = (int*)(part + cols * (size_t)kMaxChunks * NQ);
+
+    SolveDev sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.F = F;
+    sp.p = (int)p;
+    sp.Gn = Gn;
+    sp.ldz = ldz;
+    sp.pa = bt->pa;
+    sp.g_stride = bt->g_stride;
+    sp.G = bt->G_dev;
+    sp.gptr = bt->gptr_dev;
+    sp.lam1 = bt->lam1_dev;
+    sp.W1 = bt->W1_dev;
+    sp.W2 = bt->W2_dev;
+    sp.D2 = bt->D2_dev;
+    sp.B = bt->B_dev;
+    sp.Z = Z;
+    sp.GZ = GZ;
+    sp.GB = GB;
+    sp.T = T;
+    sp.theta[0] = theta;
+    sp.theta[1] = theta + cols;
+    sp.tmom[0] = tmom;
+    sp.tmom[1] = tmom + cols;
+    sp.part = part;
+    sp.flag = flag;
+    sp.gpt = std::max(1, (Gn + SG * kMaxChunks - 1) / (SG * kMaxChunks));
+    sp.n_chunks = (Gn + SG * sp.gpt - 1) / (SG * sp.gpt);
+    sp.gap = bt->gap_dev;
+    sp.primal = bt->primal_dev;
+    sp.n_iter = bt->n_iter_dev;
+    sp.status = bt->status_dev;
+    sp.counter = ctx->d_counter;
+    sp.tol = bt->tol;
+    sp.floor_rel = bt->floor_rel;
+    int Kmax = 0;
+    long long Ktot = 0;
+    for (int f = 0; f < F; ++f) {
+        if (bt->K[f] < 0 || bt->K[f] > ldz) return fail(ctx, 1, "slm_solve_batch: K[f] out of range");
+        if (!(bt->lipschitz[f] > 0.0) || !(bt->n_obs[f] > 0.0))
+            return fail(ctx, 1, "slm_solve_batch: lipschitz and n_obs must be positive");
+        sp.K[f] = bt->K[f];
+        sp.n_obs[f] = bt->n_obs[f];
+        sp.step[f] = 1.0 / bt->lipschitz[f];
+        Kmax = std::max(Kmax, bt->K[f]);
+        Ktot += bt->K[f];
+    }
+    bt->iters_run = 0;
+    bt->n_unconverged = 0;
+    if (Kmax == 0) return 0;
+
+    init_cols_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(theta, tmom, flag, sp.status, sp.n_iter,
+                                                                    bt->skip_dev, (long long)cols);
+    LAUNCH_OK("init_cols_kernel");
+    CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    CUDA_OK(cudaMemsetAsync(GB, 0, state * sizeof(double), s));
+
+    const dim3 cgrid((unsigned)((Kmax + SC - 1) / SC), (unsigned)sp.n_chunks, (unsigned)F);
+    const dim3 mgrid((unsigned)((Kmax + SC - 1) / SC), (unsigned)((p + MOM_ROWS - 1) / MOM_ROWS), (unsigned)F);
+    const dim3 fgrid((unsigned)((Kmax + 127) / 128), (unsigned)F);
+    const int check_every = std::max(1, bt->check_every);
+    long long n_active = Ktot;
+    int it = 0;
+    for (it = 0; it < bt->max_iter; ++it) {
+        const int par = it & 1;
+        double algo = 2.0 * (double)p * (double)p * (double)n_active;
+        int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, bt->K, Z, ldz, GZ, s, algo);
+        if (rc) return rc;
+        if (it % check_every == 0) {
+            CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), s));
+            {
+                FamTimer tm(ctx, FAM_GAP, s, 0.0);
+                gap_partial_kernel<<<cgrid, ST, 0, s>>>(sp, par, 0);
+                gap_final_kernel<<<fgrid, 128, 0, s>>>(sp, it, 0);
+            }
+            LAUNCH_OK("gap kernels");
+            ctx->launches++;
+            CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaStreamSynchronize(s));
+            n_active = *ctx->h_counter;
+            if (n_active == 0) break;
+        }
+        {
+            FamTimer tm(ctx, FAM_PROX, s, 0.0);
+            prox_main_kernel<<<cgrid, ST, 0, s>>>(sp, par);
+            prox_momentum_kernel<<<mgrid, ST, 0, s>>>(sp, par);
+        }
+        LAUNCH_OK("prox kernels");
+        ctx->launches++;
+    }
+    bt->iters_run = it;
+
+    // final certificate from an exact G*B
+    CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    {
+        int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, bt->K, Z, ldz, GZ, s, 0.0);
+        if (rc) return rc;
+    }
+    CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), s));
+    {
+        FamTimer tm(ctx, FAM_GAP, s, 0.0);
+        gap_partial_kernel<<<cgrid, ST, 0, s>>>(sp, 0, 1);
+        gap_final_kernel<<<fgrid, 128, 0, s>>>(sp, it, 1);
+    }
+    LAUNCH_OK("gap kernels(final)");
+    ctx->launches++;
+    CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    bt->n_unconverged = *ctx->h_counter;
+    return 0;
+}
+
+int slm_adaptive_update(slm_ctx* ctx, const double* B, int64_t p, int64_t ldz, int32_t K, int32_t n_groups,
+                        const int32_t* gptr, const double* gw, const double* a1, const double* a2,
+                        const double* alpha, double eps, double* W1, double* W2, double* dnorm,
+                        void* stream) {
+    if (!ctx || !B || !alpha) return fail(ctx, 1, "slm_adaptive_update: null argument");
+    if (K <= 0) return 0;
+    const int Gn = gptr ? n_groups : (int)p;
+    adaptive_kernel<<<(unsigned)((K + CT - 1) / CT), PT, 0, (cudaStream_t)stream>>>(
+        B, (int)p, ldz, K, Gn, gptr, gw, a1, a2, alpha, eps, W1, W2, dnorm);
+    LAUNCH_OK("adaptive_kernel");
+    return 0;
+}
+
+int slm_fold_back(slm_ctx* ctx, const double* Be, const int32_t* inv_ptr, const int32_t* inv_idx, int64_t p,
+                  int64_t ldz, int32_t K, double* coef, void* stream) {
+    if (!ctx || !Be || !inv_ptr || !inv_idx || !coef) return fail(ctx, 1, "slm_fold_back: null argument");
+    if (K <= 0 || p <= 0) return 0;
+    dim3 grid((unsigned)((K + 127) / 128), (unsigned)p);
+    fold_back_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Be, inv_ptr, inv_idx, (int)p, ldz, K, coef);
+    LAUNCH_OK("fold_back_kernel");
+    return 0;
+}
+
+int slm_cv_score(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int64_t r0, int64_t r1,
+                 const double* B, int64_t ldz, int32_t K, const double* icpt, double* yhat, double* out,
+                 void* stream) {
+    if (!ctx || !Xa || !B || !yhat || !out) return fail(ctx, 1, "slm_cv_score: null argument");
+    if (ldz % 8) return fail(ctx, 1, "slm_cv_score: ldz must be a multiple of 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t m = r1 - r0;
+    if (m <= 0 || K <= 0) return 0;
+    GemmBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n_problems = 1;
+    GemmProblem& pr = b.pr[0];
+    pr.P = Xa + r0 * lda;
+    pr.Q = B;
+    pr.C = yhat;
+    pr.ldp = lda;
+    pr.ldq = ldz;
+    pr.ldc = ldz;
+    pr.M = (int)m;
+    pr.N = (int)std::min<int64_t>(round_up(K, 8), ldz);
+    pr.Kd = (int)p;
+    ProblemDims pd = {pr.M, pr.N};
+    int sid = pick_shape(kScoreShapes, kNumScoreShapes, &pd, 1, ctx->sm_count);
+    fill_units(b, kScoreShapes[sid], false, ctx->sm_count);
+    {
+        FamTimer tm(ctx, FAM_SCORE, s, 2.0 * (double)m * (double)p * (double)K);
+        cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)m * ldz, s);
+        cudaError_t e = launch_score_shape(sid, b, s);
+        if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("score gemm: ") + cudaGetErrorString(e));
+        ctx->launches++;
+    }
+    double* part = yhat + m * ldz;
+    dim3 grid((unsigned)((K + 7) / 8), SCORE_RB);
+    score_partial_kernel<<<grid, 256, 0, s>>>(Xa, lda, (int)p, r0, m, yhat, ldz, K, icpt, part);
+    LAUNCH_OK("score_partial_kernel");
+    score_final_kernel<<<(unsigned)((K + 127) / 128), 128, 0, s>>>(part, ldz, K, out);
+    LAUNCH_OK("score_final_kernel");
+    return 0;
+}
+
+int slm_intercepts(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const double* B, int64_t ldz,
+                   int32_t K, double* icpt, void* stream) {
+    if (!ctx || !G || !B || !icpt) return fail(ctx, 1, "slm_intercepts: null argument");
+    if (K <= 0) return 0;
+    intercept_kernel<<<(unsigned)((K + 7) / 8), 256, 0, (cudaStream_t)stream>>>(G, pa, (int)p, B, ldz, K, icpt);
+    LAUNCH_OK("intercept_kernel");
+    return 0;
+}
+
+}  // extern "C"

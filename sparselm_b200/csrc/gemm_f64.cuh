@@ -1,0 +1,255 @@
+// FP64 tensor-core GEMM core for sm_100a (DMMA via mma.sync.m8n8k4.f64).
+//
+// FP64 has no tcgen05/UMMA kind on Blackwell, so the tensor path for doubles is
+// warp-level mma.sync (SASS: DMMA.8x8x4) fed from shared memory; operands are
+// staged global->shared with a multi-stage cp.async (LDGSTS) pipeline.
+//
+// One kernel serves every dense contraction of the hot path:
+//   * Gram build   G_f = Xa_f^T Xa_f          (A K-major, symmetric: upper tiles + mirror)
+//   * Gram apply   GZ_f = G_f Z_f             (A K-major through G's symmetry)
+//   * CV scoring   Yhat_f = Xte_f B_f         (A M-major)
+// i.e. C[M x N] = A[M x Kd] * B[Kd x N] with B row-major [Kd][ldq] and A given
+// either as its transpose (row-major [Kd][ldp], "K-major") or row-major [M][ldp].
+//
+// Scheduling is stream-K: the (tile, k-slab) work units of all problems of a
+// batch are laid out on one line and cut into equal contiguous ranges, one per
+// persistent CTA (grid = SMs x CTAs/SM), so that the 148 SMs finish together
+// whatever the tile count.  A CTA whose range covers a whole tile stores it; a
+// partial tile is accumulated with red.global.add.f64 into the (pre-zeroed)
+// output.  The host keeps range length >= slabs per tile, so a tile has at most
+// two contributions and the sum is order independent (bit-reproducible).
+//
+// Shared-memory tiles are padded by 4 doubles per row: for the m8n8k4 fragment
+// pattern (k = lane%4, x = lane/4) a row stride == 4 or 12 (mod 16) doubles makes
+// every half-warp hit 16 distinct 8-byte banks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace slm {
+
+constexpr int kMaxGemmProblems = 16;
+
+struct GemmProblem {
+    const double* P;  // A operand (see A_MMAJOR)
+    const double* Q;  // B operand, row-major [Kd][ldq]
+    double* C;        // row-major [M][ldc]
+    long long ldp, ldq, ldc;
+    int M, N, Kd;
+    int tiles_m, tiles_n;
+    int n_tiles;     // tiles of this problem (upper triangle only when SYM)
+    int kt;          // k-slabs per tile
+    int unit_begin;  // first linear work unit (tile * kt + slab) of this problem
+};
+
+struct GemmBatch {
+    int n_problems;
+    int total_units;
+    int units_per_cta;
+    GemmProblem pr[kMaxGemmProblems];
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int bytes = valid ? 16 : 0;  // src-size 0 => 16 bytes of zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool A_MMAJOR>
+struct GemmCfg {
+    static constexpr int BM = WARPS_M * MI * 8;
+    static constexpr int BN = WARPS_N * NI * 8;
+    static constexpr int NT = WARPS_M * WARPS_N * 32;
+    static constexpr int A_LD = A_MMAJOR ? (BK + 4) : (BM + 4);
+    static constexpr int A_ROWS = A_MMAJOR ? BM : BK;
+    static constexpr int B_LD = BN + 4;
+    static constexpr int A_STAGE = A_ROWS * A_LD;  // doubles
+    static constexpr int B_STAGE = BK * B_LD;
+    static constexpr size_t SMEM = (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+};
+
+// SYM: problem is C = A^T A with P == Q; only tiles with tn >= tm exist and each
+// is also written transposed.
+template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool A_MMAJOR, bool SYM, int MINB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
+    gemm_f64_kernel(const __grid_constant__ GemmBatch batch) {
+    using Cfg = GemmCfg<WARPS_M, WARPS_N, MI, NI, BK, STAGES, A_MMAJOR>;
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, NT = Cfg::NT;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;
+    double* Bs = smem + (size_t)STAGES * Cfg::A_STAGE;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+    const int lk = lane & 3, lx = lane >> 2;
+
+    int u = blockIdx.x * batch.units_per_cta;
+    const int u_end = min(batch.total_units, u + batch.units_per_cta);
+
+#pragma unroll 1
+    while (u < u_end) {
+        // ---- locate (problem, tile, slab range) of this segment ------------------
+        int pi = 0;
+#pragma unroll 1
+        for (int i = 1; i < batch.n_problems; ++i)
+            if (u >= batch.pr[i].unit_begin) pi = i;
+        const GemmProblem& pr = batch.pr[pi];
+        const int KT = pr.kt;
+        const int local = u - pr.unit_begin;
+        int tl = local / KT;
+        const int kt0 = local - tl * KT;
+        const int kt1 = min(KT, kt0 + (u_end - u));
+        u += kt1 - kt0;
+        int tm, tn;
+        if (SYM) {
+            tm = 0;
+            int rowlen = pr.tiles_n;
+#pragma unroll 1
+            while (tl >= rowlen) {
+                tl -= rowlen;
+                ++tm;
+                --rowlen;
+            }
+            tn = tm + tl;
+        } else {
+            tm = tl / pr.tiles_n;
+            tn = tl - tm * pr.tiles_n;
+        }
+        const int m0 = tm * BM, n0 = tn * BN;
+        const int M = pr.M, N = pr.N, Kd = pr.Kd;
+        const long long ldp = pr.ldp, ldq = pr.ldq, ldc = pr.ldc;
+        const double* __restrict__ P = pr.P;
+        const double* __restrict__ Q = pr.Q;
+
+        double acc[MI][NI][2];
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        auto load_stage = [&](int kt, int stage) {
+            const int k0 = kt * BK;
+            double* as = As + (size_t)stage * Cfg::A_STAGE;
+            double* bs = Bs + (size_t)stage * Cfg::B_STAGE;
+            if (!A_MMAJOR) {
+                constexpr int CPR = BM / 2;  // 16-byte chunks per row
+                for (int c = tid; c < BK * CPR; c += NT) {
+                    int r = c / CPR, x = (c - r * CPR) * 2;
+                    long long col = (long long)m0 + x;
+                    bool ok = (k0 + r < Kd) && (col + 2 <= ldp);
+                    const double* src = ok ? (P + (long long)(k0 + r) * ldp + col) : P;
+                    cp_async16(as + r * Cfg::A_LD + x, src, ok);
+                }
+            } else {
+                constexpr int CPR = BK / 2;
+                for (int c = tid; c < BM * CPR; c += NT) {
+                    int r = c / CPR, x = (c - r * CPR) * 2;
+                    // columns >= Kd (inside the row allocation) may be loaded: the matching
+                    // rows of the B tile are zero-filled, and Xa's padding is finite
+                    bool ok = (m0 + r < M) && (k0 + x + 2 <= ldp);
+                    const double* src = ok ? (P + (long long)(m0 + r) * ldp + k0 + x) : P;
+                    cp_async16(as + r * Cfg::A_LD + x, src, ok);
+                }
+            }
+            {
+                constexpr int CPR = BN / 2;
+                for (int c = tid; c < BK * CPR; c += NT) {
+                    int r = c / CPR, x = (c - r * CPR) * 2;
+                    long long col = (long long)n0 + x;
+                    bool ok = (k0 + r < Kd) && (col + 2 <= ldq);
+                    const double* src = ok ? (Q + (long long)(k0 + r) * ldq + col) : Q;
+                    cp_async16(bs + r * Cfg::B_LD + x, src, ok);
+                }
+            }
+        };
+
+        // ---- prologue ------------------------------------------------------------
+        const int nkt = kt1 - kt0;
+#pragma unroll
+        for (int s = 0; s < STAGES - 1; ++s) {
+            if (s < nkt) load_stage(kt0 + s, s);
+            cp_async_commit();
+        }
+
+        // ---- main loop -----------------------------------------------------------
+#pragma unroll 1
+        for (int it = 0; it < nkt; ++it) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads();
+            {
+                int nk = it + STAGES - 1;
+                if (nk < nkt) load_stage(kt0 + nk, nk % STAGES);
+                cp_async_commit();
+            }
+            const double* as = As + (size_t)(it % STAGES) * Cfg::A_STAGE;
+            const double* bs = Bs + (size_t)(it % STAGES) * Cfg::B_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; ++kk) {
+                double a[MI], b[NI];
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    int m = (wm * MI + i) * 8 + lx;
+                    a[i] = A_MMAJOR ? as[m * Cfg::A_LD + kk * 4 + lk] : as[(kk * 4 + lk) * Cfg::A_LD + m];
+                }
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    int n = (wn * NI + j) * 8 + lx;
+                    b[j] = bs[(kk * 4 + lk) * Cfg::B_LD + n];
+                }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();  // smem is reused by the next segment
+
+        // ---- epilogue --------------------------------------------------------------
+        double* __restrict__ C = pr.C;
+        const bool whole = (kt0 == 0) && (kt1 == KT);
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int row = m0 + (wm * MI + i) * 8 + lx;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+                int col = n0 + (wn * NI + j) * 8 + lk * 2;
+                if (row < M && col < N) {  // N is even: col+1 < N too
+                    const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    double* dst = C + (long long)row * ldc + col;
+                    if (whole) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+                    } else {
+                        atomicAdd(dst, v0);
+                        atomicAdd(dst + 1, v1);
+                    }
+                    if (SYM && tm != tn) {
+                        double* d0 = C + (long long)col * ldc + row;
+                        double* d1 = C + (long long)(col + 1) * ldc + row;
+                        if (whole) {
+                            *d0 = v0;
+                            *d1 = v1;
+                        } else {
+                            atomicAdd(d0, v0);
+                            atomicAdd(d1, v1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace slm

@@ -1,0 +1,406 @@
+// Solver-side kernels of the batched accelerated proximal-gradient method:
+//   K6  prox_main_kernel + prox_momentum_kernel   (fused epilogue of one iteration)
+//   K7  gap_partial_kernel + gap_final_kernel     (duality gap + convergence mask)
+// All HBM/L2-bound.  State is feature-major [F][p][ldz] (grid columns contiguous),
+// groups are contiguous feature ranges gptr[g]..gptr[g+1].
+//
+// Thread mapping: a block owns SC=8 adjacent grid columns (one 64-byte row
+// segment) and SG=32 "group lanes"; lane gl handles whole groups, so group norms
+// need no cross-thread traffic and every reduction has a fixed order
+// (bit-reproducible run to run).  Per-column reductions that span blocks go
+// through a small partials buffer part[f][chunk][q][ldz] and are finished by the
+// consumer kernel in chunk order.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/sparselm_b200.h"
+
+namespace slm {
+
+constexpr int SC = 8;              // grid columns per block
+constexpr int SG = 32;             // group lanes per block
+constexpr int ST = SC * SG;        // threads per block
+constexpr int kMaxChunks = 64;     // group chunks per column (partials per column)
+constexpr int NQ = 5;              // partial quantities per (chunk, column)
+constexpr int MOM_ROWS = 256;      // rows per block in the momentum kernel
+
+struct SolveDev {
+    int F, p, Gn;
+    int gpt;       // groups per thread in the chunked kernels
+    int n_chunks;  // ceil(Gn / (SG*gpt)) <= kMaxChunks
+    long long ldz, pa, g_stride;
+    const double* G;
+    const int* gptr;
+    const double *lam1, *W1, *W2, *D2;
+    double *B, *Z, *GZ, *GB, *T;
+    double* theta[2];
+    double* tmom[2];
+    double* part;  // [F][n_chunks][NQ][ldz]
+    int* flag;     // 0 active, 1 converged/frozen, 3 skipped by the caller
+    double *gap, *primal;
+    int *n_iter, *status;
+    int* counter;
+    double tol, floor_rel;
+    int K[SLM_MAX_FOLDS];
+    double n_obs[SLM_MAX_FOLDS];
+    double step[SLM_MAX_FOLDS];
+};
+
+__device__ __forceinline__ double softt(double v, double t) {
+    return v > t ? v - t : (v < -t ? v + t : 0.0);
+}
+
+// reduce over the SG group lanes for each of the SC columns; result valid for all threads
+__device__ __forceinline__ double lanes_sum(double v, double (*red)[SC], int gl, int c) {
+    red[gl][c] = v;
+    __syncthreads();
+#pragma unroll
+    for (int s = SG / 2; s > 0; s >>= 1) {
+        if (gl < s) red[gl][c] += red[gl + s][c];
+        __syncthreads();
+    }
+    double r = red[0][c];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double lanes_max(double v, double (*red)[SC], int gl, int c) {
+    red[gl][c] = v;
+    __syncthreads();
+#pragma unroll
+    for (int s = SG / 2; s > 0; s >>= 1) {
+        if (gl < s) red[gl][c] = fmax(red[gl][c], red[gl + s][c]);
+        __syncthreads();
+    }
+    double r = red[0][c];
+    __syncthreads();
+    return r;
+}
+
+// ---- K6a: GB recurrence, gradient step, soft-threshold, group shrink, ridge -----
+// writes T = beta_{k+1} and the per-chunk restart dot  sum (z - b+)(b+ - b)
+__global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ SolveDev sp, int par) {
+    const int f = blockIdx.z, chunk = blockIdx.y;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, gl = threadIdx.x / SC;
+    const int k = k0 + c;
+    __shared__ double red[SG][SC];
+    const long long colbase = (long long)f * sp.ldz + k;
+    const bool active = (k < Kf) && sp.flag[colbase] == 0;
+    if (__syncthreads_and(!active)) return;
+
+    const double theta = active ? sp.theta[par][colbase] : 0.0;
+    const double inv1pt = 1.0 / (1.0 + theta);
+    const double* __restrict__ cvec = sp.G + (long long)f * sp.g_stride + (long long)sp.p * sp.pa;
+    const double n = sp.n_obs[f], step = sp.step[f];
+    const double son = step / n;
+    const long long ldz = sp.ldz;
+    const long long sbase = (long long)f * sp.p * ldz + k;
+    const long long gbase = (long long)f * sp.Gn * ldz + k;
+    const double lam1 = (active && sp.lam1) ? sp.lam1[colbase] : 0.0;
+
+    double dot = 0.0;
+    if (active) {
+        for (int i = 0; i < sp.gpt; ++i) {
+            const int g = (chunk * sp.gpt + i) * SG + gl;
+            if (g >= sp.Gn) break;
+            const int ja = sp.gptr ? sp.gptr[g] : g;
+            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+            double ss = 0.0;
+            for (int j = ja; j < jb; ++j) {
+                const long long e = sbase + (long long)j * ldz;
+                const double gz = sp.GZ[e];
+                sp.GB[e] = (gz + theta * sp.GB[e]) * inv1pt;
+                const double v = sp.Z[e] - son * (gz - cvec[j]);
+                const double w1 = sp.W1 ? sp.W1[e] : lam1;
+                const double u = softt(v, step * w1);
+                sp.T[e] = u;  // stash; scaled below
+                ss += u * u;
+            }
+            const double nrm = sqrt(ss);
+            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+            double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
+            scale = scale / (1.0 + step * d2);
+            for (int j = ja; j < jb; ++j) {
+                const long long e = sbase + (long long)j * ldz;
+                const double bn = scale * sp.T[e];
+                sp.T[e] = bn;
+                dot += (sp.Z[e] - bn) * (bn - sp.B[e]);
+            }
+        }
+    }
+    dot = lanes_sum(dot, red, gl, c);
+    if (active && gl == 0)
+        sp.part[(((long long)f * sp.n_chunks + chunk) * NQ + 0) * ldz + k] = dot;
+}
+
+// ---- K6b: restart test, momentum, state rotation (elementwise, coalesced) --------
+__global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant__ SolveDev sp, int par) {
+    const int f = blockIdx.z;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, r = threadIdx.x / SC;
+    const int k = k0 + c;
+    __shared__ double red[SG][SC];
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const bool active = (k < Kf) && sp.flag[colbase] == 0;
+    if (__syncthreads_and(!active)) return;
+
+    double acc = 0.0;
+    if (active)
+        for (int ch = r; ch < sp.n_chunks; ch += SG)
+            acc += sp.part[(((long long)f * sp.n_chunks + ch) * NQ + 0) * ldz + k];
+    const double dsum = lanes_sum(acc, red, r, c);
+    if (!active) return;
+    const double tm = sp.tmom[par][colbase];
+    double tn = 0.5 * (1.0 + sqrt(1.0 + 4.0 * tm * tm));
+    double th = (tm - 1.0) / tn;
+    if (dsum > 0.0) {  // gradient-scheme adaptive restart (O'Donoghue & Candes)
+        th = 0.0;
+        tn = 1.0;
+    }
+    const long long sbase = (long long)f * sp.p * ldz + k;
+    const int j0 = blockIdx.y * MOM_ROWS;
+    const int j1 = min(j0 + MOM_ROWS, sp.p);
+    for (int j = j0 + r; j < j1; j += SG) {
+        const long long e = sbase + (long long)j * ldz;
+        const double bn = sp.T[e];
+        const double b = sp.B[e];
+        sp.Z[e] = bn + th * (bn - b);
+        sp.B[e] = bn;
+    }
+    if (blockIdx.y == 0 && r == 0) {
+        sp.theta[par ^ 1][colbase] = th;
+        sp.tmom[par ^ 1][colbase] = tn;
+    }
+}
+
+// dual norm of one group: smallest nu with || S(|g|, nu*w1) ||_2 <= nu*w2, by a
+// monotone Newton iteration from a lower bound (psi is convex and decreasing),
+// finished on the feasible side.  gfun(j) returns |g_j|, wfun(j) returns w1_j.
+template <typename GF, typename WF>
+__device__ __forceinline__ double group_dual_newton(int ja, int jb, double w2, double lo, double hi, GF gfun,
+                                                    WF wfun) {
+    double nu = lo;
+    for (int it = 0; it < 50; ++it) {
+        double s2 = 0.0, sw = 0.0;
+        for (int j = ja; j < jb; ++j) {
+            const double w = wfun(j);
+            const double u = gfun(j) - nu * w;
+            if (u > 0.0) {
+                s2 += u * u;
+                sw += w * u;
+            }
+        }
+        const double s = sqrt(s2);
+        const double psi = s - nu * w2;
+        if (!(psi > 0.0)) break;
+        const double dpsi = -sw / s - w2;
+        const double nn = nu - psi / dpsi;
+        if (!(nn > nu)) break;
+        nu = nn;
+    }
+    // finish on the feasible side
+    double bump = 4e-16;
+    for (int t = 0; t < 12; ++t) {
+        const double cand = nu * (1.0 + bump);
+        double s2 = 0.0;
+        for (int j = ja; j < jb; ++j) {
+            const double u = gfun(j) - cand * wfun(j);
+            if (u > 0.0) s2 += u * u;
+        }
+        if (sqrt(s2) <= cand * w2) return fmin(cand, hi);
+        bump *= 8.0;
+    }
+    return hi;
+}
+
+// ---- K7a: per-chunk pieces of the duality gap of B_k ------------------------------
+// G B_k comes from the momentum recurrence (GZ, GB_{k-1}, theta) or, in final mode
+// (Z == B), from GZ directly.
+__global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__ SolveDev sp, int par,
+                                                         int final_mode) {
+    const int f = blockIdx.z, chunk = blockIdx.y;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, gl = threadIdx.x / SC;
+    const int k = k0 + c;
+    __shared__ double red[SG][SC];
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const int flag = (k < Kf) ? sp.flag[colbase] : 3;
+    const bool active = flag != 3 && (final_mode || flag == 0);
+    if (__syncthreads_and(!active)) return;
+
+    const double theta = (active && !final_mode) ? sp.theta[par][colbase] : 0.0;
+    const double inv1pt = 1.0 / (1.0 + theta);
+    const double* __restrict__ cvec = sp.G + (long long)f * sp.g_stride + (long long)sp.p * sp.pa;
+    const double n = sp.n_obs[f];
+    const double inv_n = 1.0 / n;
+    const long long sbase = (long long)f * sp.p * ldz + k;
+    const long long gbase = (long long)f * sp.Gn * ldz + k;
+    const double lam1 = (active && sp.lam1) ? sp.lam1[colbase] : 0.0;
+
+    auto gb_at = [&](long long e) {
+        const double gz = sp.GZ[e];
+        return final_mode ? gz : (gz + theta * sp.GB[e]) * inv1pt;
+    };
+
+    double cb = 0.0, bgb = 0.0, pen = 0.0, ridge = 0.0, lbmax = 0.0;
+    if (active) {
+        for (int i = 0; i < sp.gpt; ++i) {
+            const int g = (chunk * sp.gpt + i) * SG + gl;
+            if (g >= sp.Gn) break;
+            const int ja = sp.gptr ? sp.gptr[g] : g;
+            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+            double ss = 0.0, gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
+            bool anyinf = false;
+            for (int j = ja; j < jb; ++j) {
+                const long long e = sbase + (long long)j * ldz;
+                const double gb = gb_at(e);
+                const double b = sp.B[e];
+                const double cj = cvec[j];
+                const double w1 = sp.W1 ? sp.W1[e] : lam1;
+                cb += cj * b;
+                bgb += b * gb;
+                pen += w1 * fabs(b);
+                ss += b * b;
+                const double gj = fabs((cj - gb) * inv_n - d2 * b);
+                gg2 += gj * gj;
+                ww2 += w1 * w1;
+                if (gj > 0.0) {
+                    if (w1 > 0.0)
+                        ratio = fmax(ratio, gj / w1);
+                    else
+                        anyinf = true;
+                }
+            }
+            pen += w2 * sqrt(ss);
+            ridge += d2 * ss;
+            // lower bound of this group's dual norm (exact when a closed form exists)
+            double lb;
+            const double gn = sqrt(gg2);
+            if (gg2 == 0.0)
+                lb = 0.0;
+            else if (w2 <= 0.0)
+                lb = anyinf ? INFINITY : ratio;
+            else if (ww2 == 0.0)
+                lb = gn / w2;
+            else
+                lb = gn / (w2 + sqrt(ww2));
+            lbmax = fmax(lbmax, lb);
+        }
+    }
+    // block-wide threshold: only groups whose upper bound exceeds it can hold the max
+    const double thr = lanes_max(lbmax, red, gl, c);
+    double omega = lbmax;
+    if (active) {
+        for (int i = 0; i < sp.gpt; ++i) {
+            const int g = (chunk * sp.gpt + i) * SG + gl;
+            if (g >= sp.Gn) break;
+            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+            if (w2 <= 0.0) continue;  // closed form already in lbmax
+            const int ja = sp.gptr ? sp.gptr[g] : g;
+            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+            auto gfun = [&](int j) {
+                const long long e = sbase + (long long)j * ldz;
+                return fabs((cvec[j] - gb_at(e)) * inv_n - d2 * sp.B[e]);
+            };
+            auto wfun = [&](int j) { return sp.W1 ? sp.W1[sbase + (long long)j * ldz] : lam1; };
+            double gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
+            bool anyinf = false;
+            for (int j = ja; j < jb; ++j) {
+                const double gj = gfun(j), w1 = wfun(j);
+                gg2 += gj * gj;
+                ww2 += w1 * w1;
+                if (gj > 0.0) {
+                    if (w1 > 0.0)
+                        ratio = fmax(ratio, gj / w1);
+                    else
+                        anyinf = true;
+                }
+            }
+            if (gg2 == 0.0 || ww2 == 0.0) continue;  // closed form
+            const double gn = sqrt(gg2);
+            double hi = gn / w2;
+            if (!anyinf && ratio < hi) hi = ratio;
+            if (!(hi > thr)) continue;
+            const double lo = gn / (w2 + sqrt(ww2));
+            omega = fmax(omega, group_dual_newton(ja, jb, w2, lo, hi, gfun, wfun));
+        }
+    }
+    cb = lanes_sum(cb, red, gl, c);
+    bgb = lanes_sum(bgb, red, gl, c);
+    pen = lanes_sum(pen, red, gl, c);
+    ridge = lanes_sum(ridge, red, gl, c);
+    omega = lanes_max(omega, red, gl, c);
+    if (active && gl == 0) {
+        double* dst = sp.part + (((long long)f * sp.n_chunks + chunk) * NQ) * ldz + k;
+        dst[0 * ldz] = cb;
+        dst[1 * ldz] = bgb;
+        dst[2 * ldz] = pen;
+        dst[3 * ldz] = ridge;
+        dst[4 * ldz] = omega;
+    }
+}
+
+// ---- K7b: finish the gap per column, set convergence flags --------------------------
+__global__ void gap_final_kernel(const __grid_constant__ SolveDev sp, int it, int final_mode) {
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sp.K[f]) return;
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const int flag = sp.flag[colbase];
+    const bool active = flag != 3 && (final_mode || flag == 0);
+    if (!active) return;
+    double cb = 0.0, bgb = 0.0, pen = 0.0, ridge = 0.0, omega = 0.0;
+    for (int ch = 0; ch < sp.n_chunks; ++ch) {
+        const double* src = sp.part + (((long long)f * sp.n_chunks + ch) * NQ) * ldz + k;
+        cb += src[0 * ldz];
+        bgb += src[1 * ldz];
+        pen += src[2 * ldz];
+        ridge += src[3 * ldz];
+        omega = fmax(omega, src[4 * ldz]);
+    }
+    const double* Gf = sp.G + (long long)f * sp.g_stride;
+    const double n = sp.n_obs[f];
+    const double yty = Gf[(long long)sp.p * sp.pa + sp.p];
+    const double rr = yty - 2.0 * cb + bgb;
+    const double rr_aug = rr + n * ridge;
+    const double yr = yty - cb;
+    const double P = rr_aug / (2.0 * n) + pen;
+    double s = omega > 1.0 ? 1.0 / omega : 1.0;
+    if (!(omega < INFINITY)) s = 0.0;
+    const double D = (2.0 * s * yr - s * s * rr_aug) / (2.0 * n);
+    const double gap = P - D;
+    const double scale = fmax(fabs(P), sp.floor_rel * yty / (2.0 * n));
+    const bool finite = isfinite(P) && isfinite(gap);
+    const bool conv = finite && gap <= sp.tol * scale;
+    if (sp.gap) sp.gap[colbase] = gap;
+    if (sp.primal) sp.primal[colbase] = P;
+    if (!final_mode) {
+        if (conv || !finite) {
+            sp.flag[colbase] = 1;
+            if (sp.n_iter) sp.n_iter[colbase] = it;
+            if (sp.status) sp.status[colbase] = finite ? 0 : 2;
+        } else {
+            atomicAdd(sp.counter, 1);
+        }
+    } else if (flag == 0) {  // not flagged inside the loop: judge the final point
+        if (sp.n_iter) sp.n_iter[colbase] = it;
+        if (sp.status) sp.status[colbase] = !finite ? 2 : (conv ? 0 : 1);
+        if (!conv) atomicAdd(sp.counter, 1);
+    }
+}
+
+}  // namespace slm

@@ -1,0 +1,502 @@
+"""Host driver of the CUDA engine: owns device memory (torch tensors), streams and
+the call sequence into the C ABI (include/sparselm_b200.h).
+
+PyTorch is plumbing here (allocation, H2D/D2H, streams, torch.distributed);
+every arithmetic step of the hot path is a kernel of libsparselm_b200.so.  There
+is no CPU fallback: constructing an Engine without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["Engine", "PenaltyGrid", "FoldData", "EngineError", "get_engine"]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+@dataclass
+class PenaltyGrid:
+    """K penalised problems sharing one design (columns of the batch).
+
+    penalty_k(b) = sum_j w1_jk |b_j| + sum_g W2[g,k] ||b_g|| + 1/2 sum_g D2[g,k] ||b_g||^2
+    in *solver feature order* (groups contiguous: gptr[g]..gptr[g+1]).
+    """
+
+    p: int
+    lam1: np.ndarray                      # (K,) l1 weight per column (w1_jk = lam1_k)
+    gptr: np.ndarray | None = None        # int32 (G+1,), None => singleton groups
+    W2: np.ndarray | None = None          # (G, K)
+    D2: np.ndarray | None = None          # (G, K)
+    # adaptive re-weighting (None => single pass)
+    adaptive: dict | None = None
+    # keys: a1 (K,)|None, a2 (K,)|None, alpha (K,), gw (G,)|None, eps, tol, max_iter,
+    #       update_function (callable|None)
+
+    @property
+    def K(self):
+        return int(len(self.lam1))
+
+    @property
+    def n_groups(self):
+        return self.p if self.gptr is None else int(len(self.gptr) - 1)
+
+
+@dataclass
+class FoldData:
+    """Device-resident problem data of one CV search (or one plain fit)."""
+
+    n: int
+    p: int
+    pa: int
+    Xa: object                 # torch [n, pa] augmented design, rows sorted by fold
+    row_ptr: np.ndarray        # int64 (F+1,) test-fold row ranges in Xa
+    G_train: object            # torch [F, pa, pa] training Grams (centred if fit_intercept)
+    G_full: object             # torch [pa, pa] Gram of all rows (centred if fit_intercept)
+    n_train: np.ndarray        # (F,)
+    L_train: np.ndarray        # (F,) Lipschitz constants lambda_max(G)/n with margin
+    L_full: float
+    fit_intercept: bool
+    row_perm: np.ndarray | None = None
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def n_folds(self):
+        return len(self.n_train)
+
+
+class Engine:
+    LIPSCHITZ_ITERS = 32
+    LIPSCHITZ_MARGIN = 1.05
+
+    def __init__(self, device: int | None = None):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise EngineError(
+                "sparselm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback"
+            )
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        h = ctypes.c_void_p()
+        rc = self.lib.slm_create(self.device_index, ctypes.byref(h))
+        if rc != 0:
+            raise EngineError(f"slm_create failed with code {rc}")
+        self.h = h
+        self.sm_count = self.lib.slm_sm_count(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.slm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- helpers ---------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc != 0:
+            msg = self.lib.slm_last_error(self.h)
+            raise EngineError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    @property
+    def stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+    def to_device(self, a, dtype=None):
+        """numpy / torch (cpu, pinned or cuda) -> contiguous cuda tensor."""
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def launch_count(self):
+        return int(self.lib.slm_launch_count(self.h))
+
+    def timing_enable(self, on=True):
+        self.lib.slm_timing_enable(self.h, 1 if on else 0)
+
+    def timing_reset(self):
+        self.lib.slm_timing_reset(self.h)
+
+    def timing_read(self):
+        names = ["gram_build", "gram_apply", "prox", "gap", "score"]
+        out = {}
+        for i, nm in enumerate(names):
+            ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+            self.lib.slm_timing_read(self.h, i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl))
+            out[nm] = {"ms": ms.value, "launches": n.value, "flops": fl.value}
+        return out
+
+    # ---- K1: pack + Gram ---------------------------------------------------
+    def padded_cols(self, p):
+        return int(self.lib.slm_padded_cols(p))
+
+    def pack(self, X, y, sample_weight=None, col_perm=None, row_perm=None):
+        torch = self.torch
+        Xd = self.to_device(X, torch.float64)
+        yd = self.to_device(y, torch.float64).reshape(-1)
+        n, p = Xd.shape
+        pa = self.padded_cols(p)
+        Xa = torch.empty((n, pa), dtype=torch.float64, device=self.device)
+        sw = None if sample_weight is None else self.to_device(sample_weight, torch.float64)
+        cp = None if col_perm is None else self.to_device(np.asarray(col_perm, dtype=np.int32))
+        rp = None if row_perm is None else self.to_device(np.asarray(row_perm, dtype=np.int64))
+        self._ck(self.lib.slm_pack_design(self.h, self._ptr(Xd), Xd.stride(0), self._ptr(yd), self._ptr(sw),
+                                          self._ptr(cp), self._ptr(rp), n, p, self._ptr(Xa), pa, self.stream),
+                 "slm_pack_design")
+        return Xa
+
+    def gram_blocks(self, Xa, row_ptr, extra=0):
+        """[F(+extra), pa, pa]: block f = Xa[rows_f]^T Xa[rows_f]; `extra` spare slots."""
+        torch = self.torch
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        F = len(row_ptr) - 1
+        pa = Xa.shape[1]
+        G = torch.empty((F + extra, pa, pa), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
+                                          row_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F,
+                                          self._ptr(G), self.stream), "slm_gram_blocks")
+        return G
+
+    def gram_complement(self, Gblk, F=None, out=None):
+        """In place: blocks -> complements (training Grams); returns the total."""
+        torch = self.torch
+        pa = Gblk.shape[-1]
+        F = Gblk.shape[0] if F is None else F
+        Gtot = torch.empty((pa, pa), dtype=torch.float64, device=self.device) if out is None else out
+        self._ck(self.lib.slm_gram_complement(self.h, self._ptr(Gblk), F, pa, self._ptr(Gtot), self.stream),
+                 "slm_gram_complement")
+        return Gtot
+
+    def gram_center(self, G, p):
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        for f in range(Gs.shape[0]):
+            self._ck(self.lib.slm_gram_center(self.h, self._ptr(Gs[f]), pa, p, self.stream), "slm_gram_center")
+
+    def gram_gather(self, G, p, idx_dev, pe):
+        torch = self.torch
+        pa = G.shape[-1]
+        pae = self.padded_cols(pe)
+        Gs = G.reshape(-1, pa, pa)
+        out = torch.empty((Gs.shape[0], pae, pae), dtype=torch.float64, device=self.device)
+        for f in range(Gs.shape[0]):
+            self._ck(self.lib.slm_gram_gather(self.h, self._ptr(Gs[f]), pa, p, self._ptr(idx_dev), pe,
+                                              self._ptr(out[f]), pae, self.stream), "slm_gram_gather")
+        return out
+
+    def lipschitz(self, G, p, iters=None):
+        """lambda_max of each Gram's leading p x p block (lower bound, no margin)."""
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        out = np.zeros(F)
+        iters = self.LIPSCHITZ_ITERS if iters is None else iters
+        for f0 in range(0, F, _lib.SLM_MAX_FOLDS):
+            nf = min(F - f0, _lib.SLM_MAX_FOLDS)
+            nbytes = self.lib.slm_lipschitz_workspace(p, nf)
+            work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            lam = (ctypes.c_double * nf)()
+            self._ck(self.lib.slm_lipschitz(self.h, self._ptr(Gs[f0]), pa * pa, pa, p, nf, iters,
+                                            self._ptr(work), lam, self.stream), "slm_lipschitz")
+            out[f0:f0 + nf] = np.frombuffer(lam, dtype=np.float64, count=nf)
+        return out
+
+    def gram_apply(self, G, p, K, Z):
+        """GZ_f = G_f Z_f (tests / roofline)."""
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        ldz = Z.shape[-1]
+        GZ = torch.zeros_like(Z)
+        Karr = (ctypes.c_int32 * F)(*[int(k) for k in K])
+        self._ck(self.lib.slm_gram_apply(self.h, self._ptr(Gs), pa * pa, pa, p, F, Karr, self._ptr(Z), ldz,
+                                         self._ptr(GZ), self.stream), "slm_gram_apply")
+        return GZ
+
+    # ---- data preparation for a CV search / a plain fit --------------------
+    def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None):
+        """Pack the design, build per-fold training Grams + the full Gram.
+
+        test_folds: list of index arrays forming a partition of range(n) (the CV
+        test sets), or None for a single fit on all rows.
+        """
+        if isinstance(X, self.torch.Tensor):
+            n, p = X.shape
+        else:
+            X = np.asarray(X)
+            n, p = X.shape
+        row_perm = None
+        if test_folds is None:
+            row_ptr = np.array([0, n], dtype=np.int64)
+        else:
+            sizes = [len(t) for t in test_folds]
+            row_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            perm = np.concatenate([np.asarray(t, dtype=np.int64) for t in test_folds])
+            if len(perm) != n or not np.array_equal(np.sort(perm), np.arange(n)):
+                raise ValueError("test_folds must partition the rows")
+            if not np.array_equal(perm, np.arange(n)):
+                row_perm = perm
+        sw = None
+        if sample_weight is not None:
+            sw = np.asarray(sample_weight, dtype=np.float64)
+        Xa = self.pack(X, y, sw, col_perm, row_perm)
+        pa = Xa.shape[1]
+        F = len(row_ptr) - 1
+        if F > 1:
+            allG = self.gram_blocks(Xa, row_ptr, extra=1)  # slot F receives the full Gram
+            G_train, G_full = allG[:F], allG[F]
+            self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
+            n_train = (n - np.diff(row_ptr)).astype(np.float64)
+        else:
+            allG = self.gram_blocks(Xa, row_ptr)
+            G_full = allG[0]
+            G_train = allG[:0]
+            n_train = np.zeros(0)
+        if sw is not None:
+            # the n of the data term is the row count; weights are renormalised per
+            # training set to sum to it (reference: _base.py:214)
+            raise NotImplementedError("sample_weight is not wired through the engine yet")
+        if fit_intercept:
+            self.gram_center(G_full, p)
+            if F > 1:
+                self.gram_center(G_train, p)
+        lam = self.lipschitz(allG, p) * self.LIPSCHITZ_MARGIN
+        lam = np.maximum(lam, 1e-300)
+        ns = np.concatenate([n_train, [float(n)]])
+        L = lam / ns
+        return FoldData(n=n, p=p, pa=pa, Xa=Xa, row_ptr=row_ptr, G_train=G_train, G_full=G_full,
+                        n_train=n_train, L_train=L[:-1], L_full=float(L[-1]),
+                        fit_intercept=bool(fit_intercept), row_perm=row_perm)
+
+    # ---- K5-K8: batched solve ------------------------------------------------
+    def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,
+              check_every=10):
+        """Solve grids[f] (a PenaltyGrid) on Gram G[f] for every f, as one batch.
+
+        Returns dict with B (torch [F,p,ldz]), and numpy [F][K_f] arrays gap, primal,
+        n_iter, status, n_pass.
+        """
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        if F > _lib.SLM_MAX_FOLDS:
+            raise ValueError(f"at most {_lib.SLM_MAX_FOLDS} Grams per batch")
+        assert len(grids) == F
+        g0 = grids[0]
+        Ks = [g.K for g in grids]
+        ldz = max(8, _round_up(max(Ks), 8))
+        Gn = g0.n_groups
+        gptr_dev = None if g0.gptr is None else self.to_device(np.asarray(g0.gptr, dtype=np.int32))
+        dev = self.device
+
+        def stack_cols(rows, getter):
+            out = np.zeros((F, rows, ldz))
+            for f, g in enumerate(grids):
+                v = getter(g)
+                out[f, :, : g.K] = v
+            return out
+
+        lam1 = self.to_device(stack_cols(1, lambda g: np.asarray(g.lam1, dtype=float)[None, :]).reshape(F, ldz))
+        use_W2 = any(g.W2 is not None for g in grids)
+        use_D2 = any(g.D2 is not None for g in grids)
+        W2 = self.to_device(stack_cols(Gn, lambda g: g.W2 if g.W2 is not None else 0.0)) if use_W2 else None
+        D2 = self.to_device(stack_cols(Gn, lambda g: g.D2 if g.D2 is not None else 0.0)) if use_D2 else None
+        W1 = None
+
+        B = torch.zeros((F, p, ldz), dtype=torch.float64, device=dev)
+        if B0 is not None:
+            B.copy_(B0)
+        nbytes = self.lib.slm_solve_workspace(p, ldz, F, Gn)
+        work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        gap = torch.zeros((F, ldz), dtype=torch.float64, device=dev)
+        primal = torch.zeros((F, ldz), dtype=torch.float64, device=dev)
+        n_iter = torch.zeros((F, ldz), dtype=torch.int32, device=dev)
+        status = torch.full((F, ldz), -1, dtype=torch.int32, device=dev)
+
+        bt = _lib.SlmBatch()
+        bt.n_folds, bt.n_groups, bt.p, bt.pa, bt.ldz = F, Gn, p, pa, ldz
+        bt.G_dev, bt.g_stride = Gs.data_ptr(), pa * pa
+        bt.gptr_dev = 0 if gptr_dev is None else gptr_dev.data_ptr()
+        for f in range(F):
+            bt.K[f] = Ks[f]
+            bt.n_obs[f] = float(n_obs[f])
+            bt.lipschitz[f] = float(lipschitz[f])
+        bt.lam1_dev = lam1.data_ptr()
+        bt.W2_dev = 0 if W2 is None else W2.data_ptr()
+        bt.D2_dev = 0 if D2 is None else D2.data_ptr()
+        bt.B_dev = B.data_ptr()
+        bt.work_dev, bt.work_bytes = work.data_ptr(), nbytes
+        bt.tol, bt.floor_rel, bt.max_iter, bt.check_every = tol, floor_rel, int(max_iter), int(check_every)
+        bt.gap_dev, bt.primal_dev = gap.data_ptr(), primal.data_ptr()
+        bt.n_iter_dev, bt.status_dev = n_iter.data_ptr(), status.data_ptr()
+
+        ad = g0.adaptive
+        n_pass = np.ones((F, ldz), dtype=np.int64)
+        total_iters = 0
+        if ad is None:
+            bt.W1_dev, bt.skip_dev = 0, 0
+            self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
+            total_iters = bt.iters_run
+        else:
+            max_pass = int(ad["max_iter"])
+            use_w1 = ad.get("a1") is not None
+            use_w2 = ad.get("a2") is not None
+            if use_w2 and W2 is None:
+                W2 = torch.zeros((F, Gn, ldz), dtype=torch.float64, device=dev)
+                bt.W2_dev = W2.data_ptr()
+
+            def colvec(key):
+                out = np.zeros((F, ldz))
+                for f, g in enumerate(grids):
+                    v = g.adaptive.get(key)
+                    if v is not None:
+                        out[f, : g.K] = v
+                return self.to_device(out)
+
+            a1 = colvec("a1") if use_w1 else None
+            a2 = colvec("a2") if use_w2 else None
+            alpha = colvec("alpha")
+            gw = None if ad.get("gw") is None else self.to_device(np.asarray(ad["gw"], dtype=float))
+            dnorm = torch.zeros((F, ldz), dtype=torch.float64, device=dev)
+            skip = torch.zeros((F, ldz), dtype=torch.int32, device=dev)
+            n_pass[:] = 0
+            conv = np.zeros((F, ldz), dtype=bool)
+            for f in range(F):
+                conv[f, Ks[f]:] = True
+            for ps in range(max_pass):
+                bt.W1_dev = 0 if W1 is None else W1.data_ptr()
+                bt.skip_dev = skip.data_ptr()
+                self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
+                total_iters += bt.iters_run
+                n_pass[~conv] = ps + 1
+                if use_w1 and W1 is None:  # previous l1 weights were lam1 (broadcast)
+                    W1 = lam1[:, None, :].expand(F, p, ldz).contiguous()
+                if ad.get("update_function") is not None:
+                    self._host_update(ad, grids, B, W1, W2, dnorm, a1, a2, gptr_dev, gw, p, ldz, Ks)
+                else:
+                    for f in range(F):
+                        self._ck(self.lib.slm_adaptive_update(
+                            self.h, self._ptr(B[f]), p, ldz, Ks[f], Gn, self._ptr(gptr_dev), self._ptr(gw),
+                            self._ptr(None if a1 is None else a1[f]), self._ptr(None if a2 is None else a2[f]),
+                            self._ptr(alpha[f]), float(ad["eps"]), self._ptr(None if W1 is None else W1[f]),
+                            self._ptr(None if not use_w2 else W2[f]), self._ptr(dnorm[f]), self.stream),
+                            "slm_adaptive_update")
+                dn = dnorm.cpu().numpy()
+                conv |= dn <= float(ad["tol"])  # _adaptive_lasso.py:189-194
+                if conv.all():
+                    break
+                skip.copy_(torch.from_numpy(conv.astype(np.int32)))
+
+        res = {
+            "B": B, "ldz": ldz, "K": Ks,
+            "gap": gap.cpu().numpy(), "primal": primal.cpu().numpy(),
+            "n_iter": n_iter.cpu().numpy(), "status": status.cpu().numpy(),
+            "n_pass": n_pass, "iters_run": int(total_iters), "n_unconverged": int(bt.n_unconverged),
+            "W1": W1, "W2": W2,
+        }
+        return res
+
+    def _host_update(self, ad, grids, B, W1, W2, dnorm, a1, a2, gptr_dev, gw, p, ldz, Ks):
+        """User-supplied update_function (arbitrary Python, _adaptive_lasso.py:116-118,
+        177-182): evaluated on the host between passes."""
+        torch = self.torch
+        fn = ad["update_function"]
+        Bh = B.cpu().numpy()
+        F = Bh.shape[0]
+        g0 = grids[0]
+        gptr = np.arange(p + 1) if g0.gptr is None else np.asarray(g0.gptr)
+        gwh = np.ones(len(gptr) - 1) if ad.get("gw") is None else np.asarray(ad["gw"], dtype=float)
+        dn = np.zeros((F, ldz))
+        W1h = None if W1 is None else W1.cpu().numpy()
+        W2h = None if (W2 is None or a2 is None) else W2.cpu().numpy()
+        for f, g in enumerate(grids):
+            for k in range(Ks[f]):
+                acc = 0.0
+                b = Bh[f, :, k]
+                if W1h is not None and a1 is not None:
+                    wn = float(g.adaptive["a1"][k]) * np.asarray(fn(b, ad["eps"]), dtype=float)
+                    acc += float(((wn - W1h[f, :, k]) ** 2).sum())
+                    W1h[f, :, k] = wn
+                if W2h is not None:
+                    norms = np.sqrt(np.add.reduceat(b * b, gptr[:-1]))
+                    wn = (float(g.adaptive["a2"][k]) * gwh) * np.asarray(fn(norms, ad["eps"]), dtype=float)
+                    acc += float(((wn - W2h[f, :, k]) ** 2).sum())
+                    W2h[f, :, k] = wn
+                dn[f, k] = np.sqrt(acc)
+        if W1h is not None and a1 is not None:
+            W1.copy_(torch.from_numpy(W1h))
+        if W2h is not None:
+            W2.copy_(torch.from_numpy(W2h))
+        dnorm.copy_(torch.from_numpy(dn))
+
+    # ---- K9 / K10 ---------------------------------------------------------------
+    def fold_back(self, Bext, inv_ptr_dev, inv_idx_dev, p, K):
+        torch = self.torch
+        ldz = Bext.shape[-1]
+        coef = torch.zeros((p, ldz), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.slm_fold_back(self.h, self._ptr(Bext), self._ptr(inv_ptr_dev), self._ptr(inv_idx_dev),
+                                        p, ldz, K, self._ptr(coef), self.stream), "slm_fold_back")
+        return coef
+
+    def intercepts(self, G, p, B, K):
+        torch = self.torch
+        ldz = B.shape[-1]
+        out = torch.zeros(ldz, dtype=torch.float64, device=self.device)
+        self._ck(self.lib.slm_intercepts(self.h, self._ptr(G), G.shape[-1], p, self._ptr(B), ldz, K,
+                                         self._ptr(out), self.stream), "slm_intercepts")
+        return out
+
+    def cv_score(self, Xa, p, r0, r1, B, K, intercept=None):
+        """(sse[K], sae[K]) of the rows [r0, r1) of Xa for the K columns of B."""
+        torch = self.torch
+        ldz = B.shape[-1]
+        m = int(r1 - r0)
+        yhat = torch.empty((m + 256, ldz), dtype=torch.float64, device=self.device)
+        out = torch.zeros((2, ldz), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.slm_cv_score(self.h, self._ptr(Xa), Xa.shape[1], p, int(r0), int(r1), self._ptr(B), ldz,
+                                       K, self._ptr(intercept), self._ptr(yhat), self._ptr(out), self.stream),
+                 "slm_cv_score")
+        return out
+
+
+_engines: dict = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine per device (one handle per (process, device))."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise EngineError("sparselm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    idx = torch.cuda.current_device() if device is None else int(device)
+    if idx not in _engines:
+        _engines[idx] = Engine(idx)
+    return _engines[idx]

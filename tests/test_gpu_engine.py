@@ -1,0 +1,299 @@
+"""GPU parity tests of the CUDA engine, kernel by kernel and end to end, through
+the C ABI (ctypes).  Checker = oracle/ (CPU) and torch fp64 for plain GEMMs."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import engine_model as M  # noqa: E402
+import oracle.reference as R  # noqa: E402
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _rng(seed=0):
+    return np.random.default_rng(seed)
+
+
+# --------------------------------------------------------------------------- #
+# K1: pack + Gram build + complement + centering
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("n,p,F", [(37, 5, 1), (300, 81, 3), (1000, 250, 5), (513, 130, 4)])
+def test_gram_build_matches_fp64_reference(engine, n, p, F):
+    torch = _torch()
+    rng = _rng(n + p)
+    X = rng.standard_normal((n, p))
+    y = rng.standard_normal(n)
+    Xa = engine.pack(X, y)
+    pa = engine.padded_cols(p)
+    Xa_ref = np.zeros((n, pa))
+    Xa_ref[:, :p], Xa_ref[:, p], Xa_ref[:, p + 1] = X, y, 1.0
+    np.testing.assert_array_equal(Xa.cpu().numpy(), Xa_ref)
+
+    row_ptr = np.linspace(0, n, F + 1).astype(np.int64)
+    G = engine.gram_blocks(Xa, row_ptr, extra=1)
+    torch.cuda.synchronize()
+    for f in range(F):
+        blk = Xa_ref[row_ptr[f]:row_ptr[f + 1]]
+        ref = blk.T @ blk
+        got = G[f].cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-12 * np.abs(ref).max())
+        assert np.array_equal(got, got.T), "Gram must be exactly symmetric"
+    if F > 1:
+        blocks = G[:F].cpu().numpy().copy()
+        engine.gram_complement(G, F, out=G[F])
+        tot = blocks.sum(0)
+        np.testing.assert_allclose(G[F].cpu().numpy(), tot, rtol=1e-14, atol=0)
+        for f in range(F):
+            np.testing.assert_allclose(G[f].cpu().numpy(), tot - blocks[f], rtol=1e-12,
+                                       atol=1e-12 * np.abs(tot).max())
+
+
+def test_pack_with_permutations(engine):
+    rng = _rng(5)
+    n, p = 50, 13
+    X = rng.standard_normal((n, p))
+    y = rng.standard_normal(n)
+    cp = rng.permutation(p)
+    rp = rng.permutation(n)
+    Xa = engine.pack(X, y, col_perm=cp, row_perm=rp).cpu().numpy()
+    np.testing.assert_array_equal(Xa[:, :p], X[rp][:, cp])
+    np.testing.assert_array_equal(Xa[:, p], y[rp])
+
+
+def test_gram_center(engine):
+    rng = _rng(7)
+    n, p = 200, 33
+    X = rng.random((n, p)) + 3.0
+    y = rng.standard_normal(n) + 10.0
+    Xa = engine.pack(X, y)
+    G = engine.gram_blocks(Xa, np.array([0, n]))
+    engine.gram_center(G, p)
+    got = G[0].cpu().numpy()
+    Xc, yc = X - X.mean(0), y - y.mean()
+    np.testing.assert_allclose(got[:p, :p], Xc.T @ Xc, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got[p, :p], Xc.T @ yc, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got[p, p], yc @ yc, rtol=1e-10)
+    np.testing.assert_allclose(got[p + 1, :p], X.sum(0), rtol=1e-13)  # ones row intact
+
+
+# --------------------------------------------------------------------------- #
+# K5: batched tensor-core apply, every tile shape
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("p,Ks", [(80, [1]), (80, [10, 7]), (515, [100, 100, 100]), (1030, [33]),
+                                  (2048, [104] * 5), (1200, [128, 60, 17, 8]), (300, [250, 3])])
+def test_gram_apply_matches_matmul(engine, p, Ks):
+    torch = _torch()
+    rng = _rng(p)
+    F = len(Ks)
+    pa = engine.padded_cols(p)
+    A = rng.standard_normal((F, pa, pa))
+    A = A + A.transpose(0, 2, 1)
+    G = torch.from_numpy(A).cuda()
+    ldz = max(8, (max(Ks) + 7) // 8 * 8)
+    Zh = np.zeros((F, p, ldz))
+    for f, k in enumerate(Ks):
+        Zh[f, :, :k] = rng.standard_normal((p, k))
+    Z = torch.from_numpy(Zh).cuda()
+    GZ = engine.gram_apply(G, p, Ks, Z).cpu().numpy()
+    for f, k in enumerate(Ks):
+        ref = A[f, :p, :p] @ Zh[f]
+        np.testing.assert_allclose(GZ[f][:, :k], ref[:, :k], rtol=0, atol=1e-11 * np.abs(ref).max())
+
+
+def test_lipschitz_is_tight_lower_bound(engine):
+    torch = _torch()
+    rng = _rng(3)
+    for n, p in [(400, 100), (3000, 700), (60, 60)]:
+        X = rng.standard_normal((n, p))
+        Xa = engine.pack(X, np.zeros(n))
+        G = engine.gram_blocks(Xa, np.array([0, n]))
+        lam = engine.lipschitz(G, p)[0]
+        true = np.linalg.eigvalsh(X.T @ X)[-1]
+        assert lam <= true * (1 + 1e-12)
+        assert lam * engine.LIPSCHITZ_MARGIN >= true, (lam, true)
+
+
+# --------------------------------------------------------------------------- #
+# K6/K7: one prox step and the gap against the numpy model of the kernels
+# --------------------------------------------------------------------------- #
+def _problem(n, p, Gn, seed, noise=1.0):
+    rng = _rng(seed)
+    X = rng.standard_normal((n, p))
+    w = np.zeros(p)
+    w[rng.choice(p, max(1, p // 10), replace=False)] = 10 * rng.random(max(1, p // 10))
+    y = X @ w + noise * rng.standard_normal(n)
+    sizes = rng.multinomial(p - Gn, np.ones(Gn) / Gn) + 1
+    gptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    return X, y, gptr
+
+
+def _grid(kind, p, gptr, alphas, rng):
+    from sparselm_b200.engine import PenaltyGrid
+
+    K = len(alphas)
+    Gn = len(gptr) - 1
+    gw = 0.5 + rng.random(Gn)
+    if kind == "lasso":
+        return PenaltyGrid(p=p, lam1=alphas)
+    if kind == "group":
+        return PenaltyGrid(p=p, lam1=np.zeros(K), gptr=gptr, W2=gw[:, None] * alphas[None, :])
+    if kind == "sgl":
+        return PenaltyGrid(p=p, lam1=0.5 * alphas, gptr=gptr, W2=gw[:, None] * (0.5 * alphas)[None, :])
+    if kind == "ridged":
+        return PenaltyGrid(p=p, lam1=np.zeros(K), gptr=gptr, W2=gw[:, None] * alphas[None, :],
+                           D2=np.tile((0.1 + rng.random(Gn))[:, None], (1, K)))
+    raise ValueError(kind)
+
+
+def _oracle_pen(grid, k):
+    p = grid.p
+    gptr = np.arange(p + 1) if grid.gptr is None else grid.gptr
+    Gn = len(gptr) - 1
+    labels = np.repeat(np.arange(Gn), np.diff(gptr))
+    w2 = np.zeros(Gn) if grid.W2 is None else grid.W2[:, k]
+    d2 = np.zeros(Gn) if grid.D2 is None else grid.D2[:, k]
+    return R.Penalty(labels, np.full(p, grid.lam1[k]), w2, d2)
+
+
+@pytest.mark.parametrize("kind", ["lasso", "group", "sgl", "ridged"])
+def test_solve_matches_oracle(engine, kind):
+    n, p, Gn = 300, 90, 12
+    X, y, gptr = _problem(n, p, Gn, seed=11)
+    rng = _rng(1)
+    amax = np.abs(X.T @ y).max() / n
+    alphas = amax * np.logspace(0.1, -3, 13)
+    grid = _grid(kind, p, gptr, alphas, rng)
+    fd = engine.prepare(X, y)
+    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    B = res["B"][0].cpu().numpy()
+    assert (res["status"][0, : grid.K] == 0).all(), res["status"]
+    for k in range(grid.K):
+        pen = _oracle_pen(grid, k)
+        b_ref, info = R.solve(X, y, pen, tol=1e-14)
+        scale = max(np.abs(b_ref).max(), 1e-12)
+        assert np.abs(B[:, k] - b_ref).max() <= 1e-6 * scale, (kind, k, np.abs(B[:, k] - b_ref).max(), scale)
+        assert np.array_equal(np.abs(B[:, k]) > 1e-6, np.abs(b_ref) > 1e-6)
+        obj, obj_ref = R.objective(X, y, B[:, k], pen), R.objective(X, y, b_ref, pen)
+        assert abs(obj - obj_ref) <= 1e-8 * max(abs(obj_ref), 1e-300)
+        # reported primal/gap agree with an independent certificate from X, y
+        cert = R.certificate(X, y, B[:, k], pen)
+        assert abs(res["primal"][0, k] - cert["primal"]) <= 1e-9 * abs(cert["primal"])
+        assert res["gap"][0, k] <= 1e-11 * abs(cert["primal"]) + 1e-12 * (y @ y) / (2 * n)
+
+
+def test_solve_multi_fold_batch_and_model_iterations(engine):
+    """5 folds x 20 columns in one batch; compare with the numpy model of the kernels."""
+    n, p, Gn = 500, 120, 15
+    X, y, gptr = _problem(n, p, Gn, seed=2)
+    rng = _rng(2)
+    folds = np.array_split(np.arange(n), 5)
+    fd = engine.prepare(X, y, test_folds=folds)
+    amax = np.abs(X.T @ y).max() / n
+    alphas = amax * np.logspace(0, -2.5, 20)
+    grid = _grid("sgl", p, gptr, alphas, rng)
+    res = engine.solve(fd.G_train, p, fd.n_train, fd.L_train, [grid] * 5, tol=1e-11)
+    B = res["B"].cpu().numpy()
+    assert (res["status"][:, :20] == 0).all()
+    for f in range(5):
+        tr = np.setdiff1d(np.arange(n), folds[f])
+        Xt, yt = X[tr], y[tr]
+        G = Xt.T @ Xt
+        # Gram of the fold agrees with a direct build
+        got = fd.G_train[f].cpu().numpy()
+        np.testing.assert_allclose(got[:p, :p], G, rtol=0, atol=1e-10 * np.abs(G).max())
+        pb = M.BatchProblem(G, Xt.T @ yt, yt @ yt, len(tr), gptr, np.tile(grid.lam1, (p, 1)), grid.W2,
+                            np.zeros_like(grid.W2), L=fd.L_train[f])
+        Bm, info = M.solve(pb, tol=1e-11)
+        # same algorithm => same iteration counts (up to reduction-order ties) and same answer
+        assert np.abs(B[f][:, :20] - Bm).max() <= 1e-8 * np.abs(Bm).max()
+        assert np.abs(res["n_iter"][f, :20] - info["iters"]).max() <= 10
+        for k in (0, 10, 19):
+            b_ref, _ = R.solve(Xt, yt, _oracle_pen(grid, k), tol=1e-14)
+            assert np.abs(B[f][:, k] - b_ref).max() <= 1e-6 * max(np.abs(b_ref).max(), 1e-12)
+
+
+def test_adaptive_passes_match_oracle(engine):
+    from sparselm_b200.engine import PenaltyGrid
+
+    n, p, Gn = 200, 40, 8
+    X, y, gptr = _problem(n, p, Gn, seed=4)
+    rng = _rng(4)
+    alphas = np.array([0.05, 0.3, 1.0])
+    K = len(alphas)
+    gw = 0.5 + rng.random(Gn)
+    labels = np.repeat(np.arange(Gn), np.diff(gptr))
+    fd = engine.prepare(X, y)
+    # AdaptiveLasso
+    grid = PenaltyGrid(p=p, lam1=alphas, adaptive=dict(a1=alphas, a2=None, alpha=alphas, gw=None, eps=1e-6,
+                                                       tol=1e-10, max_iter=3, update_function=None))
+    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    B = res["B"][0].cpu().numpy()
+    for k, a in enumerate(alphas):
+        b_ref, _ = R.fit("AdaptiveLasso", X, y, alpha=a)
+        assert np.abs(B[:, k] - b_ref).max() <= 1e-6 * np.abs(b_ref).max(), (k, np.abs(B[:, k] - b_ref).max())
+    # AdaptiveSparseGroupLasso
+    l1r = 0.3
+    grid = PenaltyGrid(p=p, lam1=l1r * alphas, gptr=gptr, W2=np.tile(((1 - l1r) * alphas)[None, :], (Gn, 1)),
+                       adaptive=dict(a1=l1r * alphas, a2=(1 - l1r) * alphas, alpha=alphas, gw=gw, eps=1e-6,
+                                     tol=1e-10, max_iter=3, update_function=None))
+    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    B = res["B"][0].cpu().numpy()
+    for k, a in enumerate(alphas):
+        b_ref, _ = R.fit("AdaptiveSparseGroupLasso", X, y, alpha=a, groups=labels, group_weights=gw, l1_ratio=l1r)
+        assert np.abs(B[:, k] - b_ref).max() <= 1e-6 * np.abs(b_ref).max(), (k, np.abs(B[:, k] - b_ref).max())
+    assert (res["n_pass"][0, :K] == 3).all()
+
+
+def test_cv_score_and_intercepts(engine):
+    torch = _torch()
+    rng = _rng(9)
+    n, p, K = 700, 45, 11
+    X = rng.standard_normal((n, p)) + 1.0
+    y = rng.standard_normal(n) + 2.0
+    Xa = engine.pack(X, y)
+    ldz = 16
+    Bh = np.zeros((p, ldz))
+    Bh[:, :K] = rng.standard_normal((p, K))
+    B = torch.from_numpy(Bh).cuda()
+    G = engine.gram_blocks(Xa, np.array([0, n]))
+    icpt = engine.intercepts(G[0], p, B, K)
+    ref_icpt = y.mean() - X.mean(0) @ Bh[:, :K]
+    np.testing.assert_allclose(icpt.cpu().numpy()[:K], ref_icpt, rtol=1e-11, atol=1e-11)
+    r0, r1 = 100, 433
+    out = engine.cv_score(Xa, p, r0, r1, B, K, icpt).cpu().numpy()
+    resid = y[r0:r1, None] - X[r0:r1] @ Bh[:, :K] - ref_icpt[None, :]
+    np.testing.assert_allclose(out[0, :K], (resid ** 2).sum(0), rtol=1e-11)
+    np.testing.assert_allclose(out[1, :K], np.abs(resid).sum(0), rtol=1e-11)
+
+
+def test_overlap_gather_and_fold_back(engine):
+    torch = _torch()
+    rng = _rng(12)
+    n, p = 120, 17
+    X = rng.standard_normal((n, p))
+    y = rng.standard_normal(n)
+    group_list = [list(rng.choice(5, size=rng.integers(1, 3), replace=False)) for _ in range(p)]
+    idx, ext_groups, Gn = R.expand_overlap(group_list, p)
+    pe = len(idx)
+    fd = engine.prepare(X, y)
+    idx_dev = torch.from_numpy(idx.astype(np.int32)).cuda()
+    Ge = engine.gram_gather(fd.G_full, p, idx_dev, pe)[0].cpu().numpy()
+    Xe = X[:, idx]
+    np.testing.assert_allclose(Ge[:pe, :pe], Xe.T @ Xe, rtol=0, atol=1e-11 * n)
+    np.testing.assert_allclose(Ge[pe, :pe], Xe.T @ y, rtol=0, atol=1e-11 * n)
+    np.testing.assert_allclose(Ge[pe, pe], y @ y, rtol=1e-13)
+    # fold back
+    order = np.argsort(idx, kind="stable")
+    inv_ptr = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=p))]).astype(np.int32)
+    Be = np.zeros((pe, 8))
+    Be[:, :3] = rng.standard_normal((pe, 3))
+    coef = engine.fold_back(torch.from_numpy(Be).cuda(), torch.from_numpy(inv_ptr).cuda(),
+                            torch.from_numpy(order.astype(np.int32)).cuda(), p, 3).cpu().numpy()
+    for k in range(3):
+        np.testing.assert_allclose(coef[:, k], R.fold_back(Be[:, k], idx, p), rtol=1e-14, atol=1e-15)
