@@ -50,6 +50,8 @@ struct slm_ctx {
     Family fam[FAM_COUNT];
     int* d_counter = nullptr;
     int* h_counter = nullptr;
+    int* d_flags = nullptr;      // stream-K per-tile flags
+    int n_flags_cap = 0;
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
 };
@@ -119,40 +121,50 @@ struct Shape {
     double eff; // measured fraction of the per-SM DMMA peak this warp layout reaches
 };
 
-static void fill_units(GemmBatch& b, const Shape& sh, bool sym, int sms) {
+static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
     long long u = 0;
-    int max_kt = 1;
+    int nflags = 0;
     for (int i = 0; i < b.n_problems; ++i) {
         GemmProblem& pr = b.pr[i];
-        pr.tiles_m = (pr.M + sh.bm - 1) / sh.bm;
-        pr.tiles_n = (pr.N + sh.bn - 1) / sh.bn;
+        pr.tiles_m = (pr.M + bm - 1) / bm;
+        pr.tiles_n = (pr.N + bn - 1) / bn;
         pr.kt = std::max(1, (pr.Kd + kBK - 1) / kBK);
         if (pr.N <= 0 || pr.M <= 0 || pr.Kd <= 0) pr.tiles_m = pr.tiles_n = 0;
         pr.n_tiles = sym ? pr.tiles_n * (pr.tiles_n + 1) / 2 : pr.tiles_m * pr.tiles_n;
         pr.unit_begin = (int)u;
+        pr.flag_begin = nflags;
+        nflags += pr.n_tiles;
         u += (long long)pr.n_tiles * pr.kt;
-        if (pr.n_tiles > 0) max_kt = std::max(max_kt, pr.kt);
     }
     b.total_units = (int)u;
-    // range length >= slabs per tile => at most two contributions per tile
-    long long n_cta = std::min<long long>((long long)sms * sh.minb, std::max<long long>(1, u / max_kt));
+    b.n_flags = nflags;
+    // persistent grid: every CTA is resident, ranges are equal => SMs finish together
+    long long n_cta = std::min<long long>(max_ctas, std::max<long long>(1, u));
     b.units_per_cta = (int)((u + n_cta - 1) / n_cta);
-    if (b.units_per_cta < max_kt) b.units_per_cta = max_kt;
 }
 
 template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB>
-static cudaError_t launch_gemm_t(const GemmBatch& b, cudaStream_t s) {
+static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     using Cfg = GemmCfg<WM, WN, MI, NI, kBK, kStages, AM>;
     auto kern = gemm_f64_kernel<WM, WN, MI, NI, kBK, kStages, AM, SYM, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    static int occupancy = 0;  // resident CTAs per SM (the spin-wait fix-up needs co-residency)
+    if (occupancy == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        occupancy = std::min(occ, MINB);
     }
+    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy);
     if (b.total_units <= 0) return cudaSuccess;
+    if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
+    b.flags = ctx->d_flags;
     int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
+    cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);
+    if (e != cudaSuccess) return e;
     kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b);
     return cudaGetLastError();
 }
@@ -164,40 +176,40 @@ static const Shape kApplyShapes[] = {
 };
 constexpr int kNumApplyShapes = sizeof(kApplyShapes) / sizeof(Shape);
 
-static cudaError_t launch_apply_shape(int id, const GemmBatch& b, cudaStream_t s) {
+static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
-        case 0: return launch_gemm_t<2, 4, 8, 4, false, false, 1>(b, s);
-        case 1: return launch_gemm_t<8, 1, 2, 13, false, false, 1>(b, s);
-        case 2: return launch_gemm_t<16, 1, 1, 13, false, false, 1>(b, s);
-        case 3: return launch_gemm_t<8, 1, 2, 7, false, false, 2>(b, s);
-        case 4: return launch_gemm_t<4, 4, 4, 4, false, false, 1>(b, s);
-        case 5: return launch_gemm_t<4, 2, 4, 4, false, false, 2>(b, s);
-        case 6: return launch_gemm_t<8, 1, 1, 13, false, false, 2>(b, s);
-        case 7: return launch_gemm_t<8, 1, 2, 4, false, false, 2>(b, s);
-        case 8: return launch_gemm_t<8, 1, 2, 2, false, false, 2>(b, s);
-        case 9: return launch_gemm_t<8, 1, 2, 1, false, false, 2>(b, s);
+        case 0: return launch_gemm_t<2, 4, 8, 4, false, false, 1>(ctx, b, s);
+        case 1: return launch_gemm_t<8, 1, 2, 13, false, false, 1>(ctx, b, s);
+        case 2: return launch_gemm_t<16, 1, 1, 13, false, false, 1>(ctx, b, s);
+        case 3: return launch_gemm_t<8, 1, 2, 7, false, false, 2>(ctx, b, s);
+        case 4: return launch_gemm_t<4, 4, 4, 4, false, false, 1>(ctx, b, s);
+        case 5: return launch_gemm_t<4, 2, 4, 4, false, false, 2>(ctx, b, s);
+        case 6: return launch_gemm_t<8, 1, 1, 13, false, false, 2>(ctx, b, s);
+        case 7: return launch_gemm_t<8, 1, 2, 4, false, false, 2>(ctx, b, s);
+        case 8: return launch_gemm_t<8, 1, 2, 2, false, false, 2>(ctx, b, s);
+        case 9: return launch_gemm_t<8, 1, 2, 1, false, false, 2>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
 // M-major (scoring) menu
 static const Shape kScoreShapes[] = {{128, 128, 1, 0.84}, {128, 64, 2, 0.85}, {128, 32, 2, 0.8}, {128, 16, 2, 0.7}, {128, 8, 2, 0.6}};
 constexpr int kNumScoreShapes = sizeof(kScoreShapes) / sizeof(Shape);
-static cudaError_t launch_score_shape(int id, const GemmBatch& b, cudaStream_t s) {
+static cudaError_t launch_score_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
-        case 0: return launch_gemm_t<2, 4, 8, 4, true, false, 1>(b, s);
-        case 1: return launch_gemm_t<4, 2, 4, 4, true, false, 2>(b, s);
-        case 2: return launch_gemm_t<8, 1, 2, 4, true, false, 2>(b, s);
-        case 3: return launch_gemm_t<8, 1, 2, 2, true, false, 2>(b, s);
-        case 4: return launch_gemm_t<8, 1, 2, 1, true, false, 2>(b, s);
+        case 0: return launch_gemm_t<2, 4, 8, 4, true, false, 1>(ctx, b, s);
+        case 1: return launch_gemm_t<4, 2, 4, 4, true, false, 2>(ctx, b, s);
+        case 2: return launch_gemm_t<8, 1, 2, 4, true, false, 2>(ctx, b, s);
+        case 3: return launch_gemm_t<8, 1, 2, 2, true, false, 2>(ctx, b, s);
+        case 4: return launch_gemm_t<8, 1, 2, 1, true, false, 2>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
 // symmetric (Gram build) menu
 static const Shape kSyrkShapes[] = {{128, 128, 1, 0.84}, {128, 128, 1, 0.85}};
-static cudaError_t launch_syrk_shape(int id, const GemmBatch& b, cudaStream_t s) {
+static cudaError_t launch_syrk_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
-        case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1>(b, s);
-        case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1>(b, s);
+        case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
+        case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -255,11 +267,8 @@ static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_
         }
         int sid = pick_shape(kApplyShapes, kNumApplyShapes, pd, nf, ctx->sm_count);
         if (ctx->force_apply_shape >= 0 && ctx->force_apply_shape < kNumApplyShapes) sid = ctx->force_apply_shape;
-        fill_units(b, kApplyShapes[sid], false, ctx->sm_count);
         FamTimer tm(ctx, FAM_APPLY, s, algo_flops >= 0 ? algo_flops : flops);
-        // partial tiles are accumulated with atomics: the output starts from zero
-        cudaMemsetAsync(GZ + (int64_t)f0 * p * ldz, 0, sizeof(double) * (size_t)nf * p * ldz, s);
-        cudaError_t e = launch_apply_shape(sid, b, s);
+        cudaError_t e = launch_apply_shape(ctx, sid, b, s);
         if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("gram apply: ") + cudaGetErrorString(e));
         ctx->launches++;
     }
@@ -582,7 +591,9 @@ int slm_create(int device, slm_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SLM_FORCE_APPLY_SHAPE")) ctx->force_apply_shape = atoi(e);
     if (const char* e = getenv("SLM_FORCE_SYRK_SHAPE")) ctx->force_syrk_shape = atoi(e);
-    if (cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess ||
+    ctx->n_flags_cap = 1 << 20;
+    if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counter, sizeof(int)) != cudaSuccess) {
         delete ctx;
         return 6;
@@ -599,6 +610,7 @@ void slm_destroy(slm_ctx* ctx) {
         for (auto e : F.pool) cudaEventDestroy(e);
     }
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
     delete ctx;
 }
@@ -670,7 +682,6 @@ int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* 
     if (lda % 8) return fail(ctx, 1, "slm_gram_blocks: lda must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
     int sid = ctx->force_syrk_shape >= 0 && ctx->force_syrk_shape < 2 ? ctx->force_syrk_shape : 0;
-    const Shape sh = kSyrkShapes[sid];
     for (int f0 = 0; f0 < n_blocks; f0 += kMaxGemmProblems) {
         int nf = std::min(n_blocks - f0, (int)kMaxGemmProblems);
         GemmBatch b;
@@ -688,10 +699,8 @@ int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* 
             pr.Kd = (int)(r1 - r0);
             flops += (double)(r1 - r0) * (double)lda * (double)(lda + 1);  // SYRK count
         }
-        fill_units(b, sh, true, ctx->sm_count);
         FamTimer tm(ctx, FAM_GRAM, s, flops);
-        cudaMemsetAsync(Gblk + (int64_t)f0 * lda * lda, 0, sizeof(double) * (size_t)nf * lda * lda, s);
-        cudaError_t e = launch_syrk_shape(sid, b, s);
+        cudaError_t e = launch_syrk_shape(ctx, sid, b, s);
         if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("gram build: ") + cudaGetErrorString(e));
         ctx->launches++;
     }
@@ -947,11 +956,9 @@ int slm_cv_score(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int64_t
     pr.Kd = (int)p;
     ProblemDims pd = {pr.M, pr.N};
     int sid = pick_shape(kScoreShapes, kNumScoreShapes, &pd, 1, ctx->sm_count);
-    fill_units(b, kScoreShapes[sid], false, ctx->sm_count);
     {
         FamTimer tm(ctx, FAM_SCORE, s, 2.0 * (double)m * (double)p * (double)K);
-        cudaMemsetAsync(yhat, 0, sizeof(double) * (size_t)m * ldz, s);
-        cudaError_t e = launch_score_shape(sid, b, s);
+        cudaError_t e = launch_score_shape(ctx, sid, b, s);
         if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("score gemm: ") + cudaGetErrorString(e));
         ctx->launches++;
     }

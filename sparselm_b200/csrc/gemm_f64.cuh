@@ -14,10 +14,13 @@
 // Scheduling is stream-K: the (tile, k-slab) work units of all problems of a
 // batch are laid out on one line and cut into equal contiguous ranges, one per
 // persistent CTA (grid = SMs x CTAs/SM), so that the 148 SMs finish together
-// whatever the tile count.  A CTA whose range covers a whole tile stores it; a
-// partial tile is accumulated with red.global.add.f64 into the (pre-zeroed)
-// output.  The host keeps range length >= slabs per tile, so a tile has at most
-// two contributions and the sum is order independent (bit-reproducible).
+// whatever the tile count.  A CTA whose range covers a whole tile stores it.  A
+// tile cut into several chunks is combined in a FIXED order (descending k: the
+// chunk holding the tile's last slab stores, every earlier chunk waits on the
+// tile's flag for the chunks after it and then adds), so results are
+// bit-reproducible; the wait is short because in stream-K the later chunks of a
+// tile are the ones that finish first.  All CTAs are co-resident (persistent
+// grid), which makes the spin-wait safe.
 //
 // Shared-memory tiles are padded by 4 doubles per row: for the m8n8k4 fragment
 // pattern (k = lane%4, x = lane/4) a row stride == 4 or 12 (mod 16) doubles makes
@@ -40,12 +43,15 @@ struct GemmProblem {
     int n_tiles;     // tiles of this problem (upper triangle only when SYM)
     int kt;          // k-slabs per tile
     int unit_begin;  // first linear work unit (tile * kt + slab) of this problem
+    int flag_begin;  // first per-tile flag of this problem
 };
 
 struct GemmBatch {
     int n_problems;
     int total_units;
     int units_per_cta;
+    int* flags;  // one int per tile, zero on entry
+    int n_flags;
     GemmProblem pr[kMaxGemmProblems];
 };
 
@@ -109,6 +115,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         const int KT = pr.kt;
         const int local = u - pr.unit_begin;
         int tl = local / KT;
+        const int tile_lin = tl;
         const int kt0 = local - tl * KT;
         const int kt1 = min(KT, kt0 + (u_end - u));
         u += kt1 - kt0;
@@ -220,6 +227,18 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         // ---- epilogue --------------------------------------------------------------
         double* __restrict__ C = pr.C;
         const bool whole = (kt0 == 0) && (kt1 == KT);
+        const bool first_writer = (kt1 == KT);  // holds the tile's last slab: stores
+        int* flag = batch.flags + pr.flag_begin + tile_lin;
+        if (!whole && !first_writer) {
+            // chunks after mine = CTAs between me and the one owning the tile's last unit
+            const int tile_last_unit = pr.unit_begin + tile_lin * KT + KT - 1;
+            const int after = tile_last_unit / batch.units_per_cta - (int)blockIdx.x;
+            if (tid == 0) {
+                while (atomicAdd(flag, 0) < after) __nanosleep(64);
+                __threadfence();
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
             int row = m0 + (wm * MI + i) * 8 + lx;
@@ -227,27 +246,26 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
             for (int j = 0; j < NI; ++j) {
                 int col = n0 + (wn * NI + j) * 8 + lk * 2;
                 if (row < M && col < N) {  // N is even: col+1 < N too
-                    const double v0 = acc[i][j][0], v1 = acc[i][j][1];
-                    double* dst = C + (long long)row * ldc + col;
-                    if (whole) {
-                        *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-                    } else {
-                        atomicAdd(dst, v0);
-                        atomicAdd(dst + 1, v1);
+                    double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
+                    if (!first_writer) {
+                        const double2 old = __ldcg(dst);
+                        v0 += old.x;
+                        v1 += old.y;
                     }
+                    __stcg(dst, make_double2(v0, v1));
                     if (SYM && tm != tn) {
-                        double* d0 = C + (long long)col * ldc + row;
-                        double* d1 = C + (long long)(col + 1) * ldc + row;
-                        if (whole) {
-                            *d0 = v0;
-                            *d1 = v1;
-                        } else {
-                            atomicAdd(d0, v0);
-                            atomicAdd(d1, v1);
-                        }
+                        // mirrored copy: same value as the upper entry (kept bit-identical)
+                        __stcg(C + (long long)col * ldc + row, v0);
+                        __stcg(C + (long long)(col + 1) * ldc + row, v1);
                     }
                 }
             }
+        }
+        if (!whole) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(flag, 1);
         }
     }
 }

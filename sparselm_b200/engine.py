@@ -279,21 +279,27 @@ class Engine:
             G_full = allG[0]
             G_train = allG[:0]
             n_train = np.zeros(0)
+        extra = {}
         if sw is not None:
-            # the n of the data term is the row count; weights are renormalised per
-            # training set to sum to it (reference: _base.py:214)
-            raise NotImplementedError("sample_weight is not wired through the engine yet")
+            # reference: weights are rescaled to sum to n (_base.py:214), i.e. the data term is
+            # 1/(2 sum(sw)) sum_i sw_i r_i^2 -- the "n" of a weighted problem is sum(sw) of its rows
+            swp = sw if row_perm is None else sw[row_perm]
+            tot = float(sw.sum())
+            extra["n_obs_full"] = tot
+            if F > 1:
+                extra["n_obs_train"] = tot - np.add.reduceat(swp, row_ptr[:-1])
+            extra["weighted"] = True
         if fit_intercept:
             self.gram_center(G_full, p)
             if F > 1:
                 self.gram_center(G_train, p)
         lam = self.lipschitz(allG, p) * self.LIPSCHITZ_MARGIN
         lam = np.maximum(lam, 1e-300)
-        ns = np.concatenate([n_train, [float(n)]])
+        ns = np.concatenate([extra.get("n_obs_train", n_train), [extra.get("n_obs_full", float(n))]])
         L = lam / ns
         return FoldData(n=n, p=p, pa=pa, Xa=Xa, row_ptr=row_ptr, G_train=G_train, G_full=G_full,
                         n_train=n_train, L_train=L[:-1], L_full=float(L[-1]),
-                        fit_intercept=bool(fit_intercept), row_perm=row_perm)
+                        fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra)
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,

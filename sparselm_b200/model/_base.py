@@ -1,0 +1,256 @@
+"""Base class of the engine-backed estimators.
+
+Mirrors the reference's ``CVXRegressor`` (src/sparselm/model/_base.py:69-519):
+same constructor arguments, ``fit(X, y, sample_weight=None) -> self``, ``coef_``
+/ ``intercept_`` / ``predict`` / ``score``, and the same order of operations in
+``fit`` (validate -> preprocess -> hyper-parameter validation -> solve -> set
+intercept, _base.py:173-202).  What differs is the solve seam: instead of
+building a cvxpy problem (``generate_problem``, _base.py:414-467) and calling
+``problem.solve`` (_base.py:512-519) the estimator describes its penalty as a
+``ProblemSpec`` and hands it to the CUDA engine, which works on the Gram matrix
+of the (centred, weighted) design.
+
+cvxpy-specific surface (``canonicals_``, ``add_constraints``) is not part of the
+path and is not provided; ``generate_problem(X, y)`` is kept as "validate and
+describe the problem" and returns the ProblemSpec.
+"""
+
+from __future__ import annotations
+
+import warnings
+from abc import ABCMeta, abstractmethod
+from dataclasses import dataclass, field
+from numbers import Real
+
+import numpy as np
+from sklearn.base import BaseEstimator, RegressorMixin
+from sklearn.utils._param_validation import Interval
+from sklearn.utils.validation import check_is_fitted, validate_data
+
+from ..engine import PenaltyGrid, get_engine
+
+__all__ = ["EngineRegressor", "CVXRegressor", "ProblemSpec"]
+
+
+@dataclass
+class ProblemSpec:
+    """One penalised least-squares problem in solver feature order.
+
+    min_b 1/(2n)||y - X b||^2 + lam1 ||b||_1 + sum_g w2_g ||b_g|| + 1/2 sum_g d2_g ||b_g||^2
+    """
+
+    p: int                               # features of X
+    pe: int                              # solver features (== p unless overlap expansion)
+    lam1: float = 0.0
+    col_perm: np.ndarray | None = None   # solver order -> column of X (groups made contiguous)
+    ext_idx: np.ndarray | None = None    # overlap: solver feature a duplicates column ext_idx[a]
+    gptr: np.ndarray | None = None       # int32 (G+1,)
+    gw: np.ndarray | None = None         # (G,) group weights (adaptive update needs them)
+    w2: np.ndarray | None = None         # (G,)
+    d2: np.ndarray | None = None         # (G,)
+    adaptive: dict | None = None         # a1, a2, alpha, eps, tol, max_iter, update_function
+    key: tuple = field(default_factory=tuple)  # structure key: specs with equal keys can be batched
+
+    @property
+    def n_groups(self):
+        return self.pe if self.gptr is None else len(self.gptr) - 1
+
+
+def stack_specs(specs):
+    """Columns of one engine batch from specs that share their structure key."""
+    s0 = specs[0]
+    K = len(specs)
+    lam1 = np.array([s.lam1 for s in specs], dtype=float)
+    W2 = None if s0.w2 is None else np.stack([s.w2 for s in specs], axis=1)
+    D2 = None if s0.d2 is None else np.stack([s.d2 for s in specs], axis=1)
+    ad = None
+    if s0.adaptive is not None:
+        a = s0.adaptive
+        ad = dict(
+            a1=None if a["a1"] is None else np.array([s.adaptive["a1"] for s in specs], dtype=float),
+            a2=None if a["a2"] is None else np.array([s.adaptive["a2"] for s in specs], dtype=float),
+            alpha=np.array([s.adaptive["alpha"] for s in specs], dtype=float),
+            gw=s0.gw, eps=a["eps"], tol=a["tol"], max_iter=a["max_iter"],
+            update_function=a["update_function"],
+        )
+    assert W2 is None or W2.shape == (s0.n_groups, K)
+    return PenaltyGrid(p=s0.pe, lam1=lam1, gptr=s0.gptr, W2=W2, D2=D2, adaptive=ad)
+
+
+def group_structure(groups, p):
+    """(col_perm, gptr, n_groups): labels in np.sort(np.unique()) order
+    (reference _lasso.py:248), features permuted so that groups are contiguous."""
+    labels = np.asarray(groups)
+    _, inv = np.unique(labels, return_inverse=True)
+    inv = inv.reshape(-1)
+    n_groups = int(inv.max()) + 1 if len(inv) else 0
+    order = np.argsort(inv, kind="stable")
+    counts = np.bincount(inv, minlength=n_groups)
+    gptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    col_perm = None if np.array_equal(order, np.arange(p)) else order.astype(np.int32)
+    return col_perm, gptr, n_groups
+
+
+class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
+    """Abstract sklearn-compatible regressor solved on the B200 engine.
+
+    Args:
+        fit_intercept (bool): estimate an intercept (data centred first).
+        copy_X (bool): kept for API compatibility; X is never modified (it is
+            copied to the device).
+        warm_start (bool): kept for API compatibility (reference _base.py:132).
+        solver (str | None): accepted and ignored (there is one solver: the engine).
+        solver_options (dict | None): engine options: ``tol`` (relative duality
+            gap, default 1e-10), ``max_iter``, ``check_every``, ``floor_rel``,
+            ``device``.
+    """
+
+    _parameter_constraints: dict = {
+        "fit_intercept": ["boolean"],
+        "copy_X": ["boolean"],
+        "warm_start": ["boolean"],
+        "solver": [str, None],
+        "solver_options": [dict, None],
+    }
+
+    def __init__(self, fit_intercept=False, copy_X=True, warm_start=False, solver=None, solver_options=None):
+        self.fit_intercept = fit_intercept
+        self.copy_X = copy_X
+        self.warm_start = warm_start
+        self.solver = solver
+        self.solver_options = solver_options
+
+    # ---- hooks --------------------------------------------------------------
+    @abstractmethod
+    def _problem_spec(self, n_features: int) -> ProblemSpec:
+        """Describe the penalty for the current hyper-parameters."""
+
+    def _validate_hyperparams(self, X, y) -> None:
+        """Reference: CVXRegressor._validate_params(X, y) (_base.py:229-245)."""
+        self._validate_params()  # sklearn: checks _parameter_constraints
+
+    def _engine_options(self):
+        opts = dict(self.solver_options) if self.solver_options is not None else {}
+        if not isinstance(opts, dict):
+            raise TypeError("solver_options must be a dictionary")
+        known = {"tol", "max_iter", "check_every", "floor_rel", "device"}
+        return {k: v for k, v in opts.items() if k in known}
+
+    # ---- sklearn API ---------------------------------------------------------
+    def fit(self, X, y, sample_weight=None):
+        """Fit the linear model coefficients on the GPU engine."""
+        X, y = validate_data(self, X, y, accept_sparse=False, y_numeric=True, multi_output=False,
+                             dtype=np.float64)
+        self._validate_hyperparams(X, y)
+        opts = self._engine_options()
+        spec = self._problem_spec(X.shape[1])
+        engine = get_engine(opts.pop("device", None))
+        sw = None
+        if sample_weight is not None:
+            from sklearn.utils.validation import _check_sample_weight
+
+            sw = _check_sample_weight(sample_weight, X, dtype=np.float64)
+        fd = engine.prepare(X, y, None, self.fit_intercept, sw, col_perm=spec.col_perm)
+        self._fit_prepared(engine, fd, spec, opts)
+        return self
+
+    def _fit_prepared(self, engine, fd, spec, opts):
+        """Solve on an already prepared (device-resident) design."""
+        out = solve_specs(engine, fd, [spec], use_full=True, **opts)
+        coef = out["coef"][0, :, 0].cpu().numpy()
+        self.coef_ = _to_original_order(coef, spec)
+        if self.fit_intercept:
+            self.intercept_ = float(out["intercept"][0, 0].item())
+        else:
+            self.intercept_ = 0.0
+        if spec.adaptive is not None:
+            self.n_iter_ = int(out["n_pass"][0, 0])
+        self.solver_info_ = {
+            "gap": float(out["gap"][0, 0]), "objective": float(out["primal"][0, 0]),
+            "iterations": int(out["n_iter"][0, 0]), "status": int(out["status"][0, 0]),
+        }
+        if self.solver_info_["status"] != 0:
+            from sklearn.exceptions import ConvergenceWarning
+
+            warnings.warn(
+                f"{type(self).__name__}: the engine stopped with status {self.solver_info_['status']} "
+                f"(gap {self.solver_info_['gap']:.3e}); raise solver_options['max_iter']",
+                ConvergenceWarning,
+            )
+        return self
+
+    def predict(self, X):
+        check_is_fitted(self, "coef_")
+        X = validate_data(self, X, accept_sparse=False, reset=False, dtype=np.float64)
+        return X @ self.coef_ + self.intercept_
+
+    def generate_problem(self, X, y, preprocess_data=True, sample_weight=None):
+        """Validate hyper-parameters against (X, y) and return the problem description
+        (the reference builds its cvxpy problem here, _base.py:414-467)."""
+        X = np.asarray(X)
+        self._validate_hyperparams(X, np.asarray(y))
+        self.problem_spec_ = self._problem_spec(X.shape[1])
+        return self.problem_spec_
+
+    def __sklearn_tags__(self):
+        tags = super().__sklearn_tags__()
+        tags.target_tags.required = True
+        return tags
+
+
+# historical name of the base class in the reference
+CVXRegressor = EngineRegressor
+
+
+def _to_original_order(coef_solver, spec: ProblemSpec):
+    if spec.col_perm is None:
+        return np.ascontiguousarray(coef_solver)
+    out = np.empty_like(coef_solver)
+    out[spec.col_perm] = coef_solver
+    return out
+
+
+def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, check_every=10,
+                floor_rel=1e-14):
+    """Solve the K problems `specs` (equal structure keys) on every training Gram of
+    `fd` (or on its full Gram when use_full) as one engine batch.
+
+    Returns device tensors in the column order of fd.Xa: coef [F, p, ldz], intercept
+    [F, ldz], and numpy [F, ldz] gap / primal / n_iter / status / n_pass.
+    """
+    torch = engine.torch
+    s0 = specs[0]
+    p = fd.p
+    grid = stack_specs(specs)
+    K = grid.K
+    if use_full:
+        G = fd.G_full[None]
+        n_obs = np.array([fd.extra.get("n_obs_full", float(fd.n))])
+        L = np.array([fd.L_full])
+    else:
+        G, n_obs, L = fd.G_train, fd.extra.get("n_obs_train", fd.n_train), fd.L_train
+    F = G.shape[0]
+    if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
+        idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))
+        Gs = engine.gram_gather(G, p, idx_dev, s0.pe)
+        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / np.asarray(n_obs, dtype=float)
+    else:
+        Gs = G
+    res = engine.solve(Gs, s0.pe, n_obs, L, [grid] * F, tol=tol, max_iter=max_iter,
+                       check_every=check_every, floor_rel=floor_rel)
+    B = res["B"]
+    ldz = res["ldz"]
+    if s0.ext_idx is not None:  # fold back (_lasso.py:492-501)
+        idx = np.asarray(s0.ext_idx)
+        order = np.argsort(idx, kind="stable").astype(np.int32)
+        inv_ptr = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=p))]).astype(np.int32)
+        ip, ii = engine.to_device(inv_ptr), engine.to_device(order)
+        coef = torch.stack([engine.fold_back(B[f], ip, ii, p, K) for f in range(F)])
+    else:
+        coef = B
+    if fd.fit_intercept:
+        icpt = torch.stack([engine.intercepts(G[f], p, coef[f], K) for f in range(F)])
+    else:
+        icpt = torch.zeros((F, ldz), dtype=torch.float64, device=engine.device)
+    res.update(coef=coef, intercept=icpt)
+    return res

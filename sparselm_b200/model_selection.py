@@ -1,0 +1,410 @@
+"""Hyper-parameter search: GridSearchCV with the one-standard-error rule and
+LineSearchCV (reference: src/sparselm/model_selection.py).
+
+The reference runs ``n_candidates x n_splits`` independent Python fits through
+joblib (model_selection.py:304-323), each rebuilding its cvxpy problem.  Here the
+whole (candidate, fold) grid of an engine-backed estimator is ONE batch on the
+GPU: the per-fold Gram matrices are built once, every candidate is a column of
+the batched accelerated proximal-gradient solve, and the CV scores are computed
+on the device.  Anything the batched seam does not cover (foreign estimators,
+fit params, exotic scorers or splitters) takes sklearn's generic per-fit path,
+which still fits on the engine through ``estimator.fit``.
+"""
+
+from __future__ import annotations
+
+import numbers
+import re
+import time
+from copy import deepcopy
+
+import numpy as np
+from numpy.ma import MaskedArray
+from scipy.stats import rankdata
+from sklearn.base import clone
+from sklearn.model_selection import GridSearchCV as _SkGridSearchCV
+from sklearn.model_selection import ParameterGrid, check_cv
+from sklearn.model_selection._search import BaseSearchCV
+from sklearn.utils.validation import check_X_y
+
+from .engine import get_engine
+from .model._base import EngineRegressor, _to_original_order, solve_specs
+
+__all__ = ["GridSearchCV", "LineSearchCV"]
+
+_DEVICE_SCORERS = {None, "r2", "neg_root_mean_squared_error", "neg_mean_squared_error",
+                   "neg_mean_absolute_error"}
+
+
+def _select_best_index_onestd(refit, refit_metric, results):
+    """One-standard-error rule (reference model_selection.py:190-223): among the
+    candidates whose summed non-negative numeric hyper-parameters are at least those
+    of the best-scoring candidate, take the one whose mean score is closest to
+    (best mean - its std)."""
+    if callable(refit):
+        best_index = refit(results)
+        if not isinstance(best_index, numbers.Integral):
+            raise TypeError("best_index_ returned is not an integer")
+        if best_index < 0 or best_index >= len(results["params"]):
+            raise IndexError("best_index_ index out of range")
+        return best_index
+    opt_index = results[f"rank_test_{refit_metric}"].argmin()
+    m = results[f"mean_test_{refit_metric}"][opt_index]
+    sig = results[f"std_test_{refit_metric}"][opt_index]
+    metrics = results[f"mean_test_{refit_metric}"]
+    params = []
+    for name in [key for key in results if re.match(r"^param_(\w+)", key)]:
+        if all(isinstance(val, numbers.Number) for val in results[name]):
+            pv = np.array(results[name], dtype=float)
+            if np.all(pv > -1e-9):
+                params.append(pv)
+    params_sum = np.sum(params, axis=0)
+    one_std_dists = np.abs(metrics - m + sig)
+    candidates = np.arange(len(metrics))[params_sum >= params_sum[opt_index]]
+    return candidates[np.argmin(one_std_dists[candidates])]
+
+
+def _is_partition(splits, n):
+    seen = np.zeros(n, dtype=np.int64)
+    for train, test in splits:
+        seen[test] += 1
+        if len(train) + len(test) != n:
+            return False
+        mask = np.ones(n, dtype=bool)
+        mask[test] = False
+        if not np.array_equal(np.flatnonzero(mask), np.sort(train)):
+            return False
+    return bool(np.all(seen == 1))
+
+
+def _metric(scoring, sse, sae, n_rows, sst):
+    """Score per column from residual sums (greater is better, sklearn convention)."""
+    if scoring == "neg_root_mean_squared_error":
+        return -np.sqrt(sse / n_rows)
+    if scoring == "neg_mean_squared_error":
+        return -sse / n_rows
+    if scoring == "neg_mean_absolute_error":
+        return -sae / n_rows
+    # r2 (estimator.score / "r2"), with sklearn's force_finite convention
+    if sst == 0.0:
+        return np.where(sse == 0.0, 1.0, 0.0)
+    return 1.0 - sse / sst
+
+
+def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_train_score=False, cache=None,
+               cache_key=None):
+    """Solve every (candidate, fold) problem as device batches and score them.
+
+    X: (n, p) numpy array or torch tensor (host, pinned or already on the device);
+    y: (n,) numpy array; test_folds: list of index arrays partitioning the rows;
+    ests/specs: one configured estimator and its ProblemSpec per candidate.
+    Returns test_scores [n_cand, n_splits] (+ train scores, timings, solver info and
+    the device-resident FoldData objects keyed by (fit_intercept, column order)).
+    """
+    n, p = X.shape
+    n_splits, n_cand = len(test_folds), len(specs)
+    yv = np.asarray(y, dtype=np.float64)
+    test_scores = np.full((n_cand, n_splits), np.nan)
+    train_scores = np.full((n_cand, n_splits), np.nan) if return_train_score else None
+    fit_time = np.zeros(n_cand)
+    score_time = np.zeros(n_cand)
+    info = dict(n_iter=np.zeros((n_cand, n_splits), dtype=int), status=np.zeros((n_cand, n_splits), dtype=int),
+                gap=np.zeros((n_cand, n_splits)), n_pass=np.zeros((n_cand, n_splits), dtype=int))
+    need_r2 = scoring == "r2"
+    sst_test = np.array([float(((yv[t] - yv[t].mean()) ** 2).sum()) if need_r2 else 0.0 for t in test_folds])
+    tot_sum, tot_sq = float(yv.sum()), float((yv * yv).sum())
+    n_unconverged = 0
+    iters_run = 0
+
+    fds = {}
+    batches = {}
+    for ci, s in enumerate(specs):
+        batches.setdefault(s.key, []).append(ci)
+    for key, idxs in batches.items():
+        s0, e0 = specs[idxs[0]], ests[idxs[0]]
+        fkey = (bool(e0.fit_intercept), None if s0.col_perm is None else s0.col_perm.tobytes())
+        if fkey not in fds:
+            ck = None
+            if cache is not None and cache_key is not None:
+                ck = (cache_key, fkey, tuple(len(t) for t in test_folds), tuple(int(t[0]) for t in test_folds))
+            if ck is not None and ck in cache:
+                fds[fkey] = cache[ck]
+            else:
+                fds[fkey] = engine.prepare(X, yv, test_folds, e0.fit_intercept, None, col_perm=s0.col_perm)
+                if ck is not None:
+                    cache[ck] = fds[fkey]
+        fd = fds[fkey]
+        t0 = time.perf_counter()
+        out = solve_specs(engine, fd, [specs[i] for i in idxs], **opts)
+        t1 = time.perf_counter()
+        K = len(idxs)
+        icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
+        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], K, icpt(f))
+                  for f in range(n_splits)]
+        sc = engine.torch.stack(sc_dev).cpu().numpy()  # one D2H for all folds
+        sse, sae = sc[:, 0, :K], sc[:, 1, :K]
+        if train_scores is not None:
+            tsse = np.zeros((n_splits, K))
+            tsae = np.zeros((n_splits, K))
+            for f in range(n_splits):
+                for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
+                    if r1 > r0:
+                        t = engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], K, icpt(f)).cpu().numpy()
+                        tsse[f] += t[0, :K]
+                        tsae[f] += t[1, :K]
+        t2 = time.perf_counter()
+        for f in range(n_splits):
+            nt = len(test_folds[f])
+            test_scores[idxs, f] = _metric(scoring, sse[f], sae[f], nt, sst_test[f])
+            if train_scores is not None:
+                ntr = n - nt
+                s_tr = tot_sum - float(yv[test_folds[f]].sum())
+                q_tr = tot_sq - float((yv[test_folds[f]] ** 2).sum())
+                train_scores[idxs, f] = _metric(scoring, tsse[f], tsae[f], ntr, q_tr - s_tr * s_tr / ntr)
+            info["n_iter"][idxs, f] = out["n_iter"][f, :K]
+            info["status"][idxs, f] = out["status"][f, :K]
+            info["gap"][idxs, f] = out["gap"][f, :K]
+            info["n_pass"][idxs, f] = out["n_pass"][f, :K]
+        fit_time[idxs] = (t1 - t0) / (K * n_splits)
+        score_time[idxs] = (t2 - t1) / (K * n_splits)
+        n_unconverged += int(out["n_unconverged"])
+        iters_run += int(out["iters_run"])
+    return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
+                info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run)
+
+
+class GridSearchCV(_SkGridSearchCV):
+    """Exhaustive search over a parameter grid, batched on the GPU for engine-backed
+    estimators.  Same constructor as the reference (model_selection.py:160-187):
+    sklearn's GridSearchCV plus ``opt_selection_method`` in {"max_score",
+    "one_std_score"} and default scoring "neg_root_mean_squared_error"; fitted
+    attributes ``best_params_``, ``best_score_``, ``best_score_std_``,
+    ``best_estimator_``, ``cv_results_`` (:376-422).
+    """
+
+    def __init__(self, estimator, param_grid, *, opt_selection_method="max_score",
+                 scoring="neg_root_mean_squared_error", n_jobs=None, refit=True, cv=None, verbose=0,
+                 pre_dispatch="2*n_jobs", error_score=np.nan, return_train_score=False):
+        super().__init__(estimator=estimator, param_grid=param_grid, scoring=scoring, n_jobs=n_jobs,
+                         refit=refit, cv=cv, verbose=verbose, pre_dispatch=pre_dispatch,
+                         error_score=error_score, return_train_score=return_train_score)
+        self.opt_selection_method = opt_selection_method
+
+    # sklearn calls self._select_best_index(self.refit, refit_metric, results)
+    def _select_best_index(self, refit, refit_metric, results):
+        if self.opt_selection_method == "max_score":
+            return _SkGridSearchCV._select_best_index(refit, refit_metric, results)
+        if self.opt_selection_method == "one_std_score":
+            return _select_best_index_onestd(refit, refit_metric, results)
+        raise NotImplementedError(f"Method {self.opt_selection_method} not implemented!")
+
+    _select_best_index_onestd = staticmethod(_select_best_index_onestd)
+
+    # ------------------------------------------------------------------ #
+    def fit(self, X, y=None, **params):
+        """Run the search.  Engine-backed estimators with batchable grids are solved as
+        one device batch; everything else goes through sklearn's per-fit loop."""
+        plan = self._batch_plan(X, y, params)
+        if plan is None:
+            super().fit(X, y, **params)
+            if hasattr(self, "best_index_") and not callable(self.refit):
+                self.best_score_std_ = self.cv_results_["std_test_score"][self.best_index_] \
+                    if "std_test_score" in self.cv_results_ else None
+            self.batched_ = False
+            return self
+        return self._fit_batched(plan)
+
+    # ------------------------------------------------------------------ #
+    def _batch_plan(self, X, y, params):
+        est = self.estimator
+        if not isinstance(est, EngineRegressor) or y is None:
+            return None
+        if any(v is not None for v in params.values()):
+            return None
+        if not (self.scoring is None or (isinstance(self.scoring, str) and self.scoring in _DEVICE_SCORERS)):
+            return None
+        if callable(self.refit) or hasattr(X, "columns"):
+            return None
+        if self.opt_selection_method not in ("max_score", "one_std_score"):
+            raise NotImplementedError(f"Method {self.opt_selection_method} not implemented!")
+        try:
+            Xv, yv = check_X_y(X, y, dtype=np.float64, y_numeric=True, ensure_min_samples=2)
+        except Exception:
+            return None
+        n, p = Xv.shape
+        cv = check_cv(self.cv, yv, classifier=False)
+        splits = list(cv.split(Xv, yv, None))
+        if len(splits) < 2 or len(splits) > 15 or not _is_partition(splits, n):
+            return None
+        candidates = list(ParameterGrid(self.param_grid))
+        valid = set(est.get_params(deep=False))
+        if any(not set(c) <= valid for c in candidates):
+            return None
+        ests, specs = [], []
+        try:
+            for c in candidates:
+                e = clone(est).set_params(**c)
+                e._validate_hyperparams(Xv, yv)
+                ests.append(e)
+                specs.append(e._problem_spec(p))
+        except NotImplementedError:
+            raise
+        except Exception:
+            return None  # sklearn's loop applies error_score semantics per candidate
+        return dict(X=Xv, y=yv, n=n, p=p, splits=splits, candidates=candidates, ests=ests, specs=specs)
+
+    def _fit_batched(self, plan):
+        Xv, yv, n, p = plan["X"], plan["y"], plan["n"], plan["p"]
+        splits, candidates, specs, ests = plan["splits"], plan["candidates"], plan["specs"], plan["ests"]
+        n_splits, n_cand = len(splits), len(candidates)
+        base = self.estimator
+        opts = base._engine_options()
+        engine = get_engine(opts.pop("device", None))
+        scoring = self.scoring if self.scoring is not None else "r2"
+        test_folds = [np.asarray(test) for _, test in splits]
+        cache = getattr(self, "_fd_cache", None)
+        cache_key = None if cache is None else (id(plan["X"]), id(plan["y"]))
+        res = batched_cv(engine, Xv, yv, test_folds, ests, specs, opts, scoring,
+                         return_train_score=self.return_train_score, cache=cache, cache_key=cache_key)
+        test_scores, train_scores = res["test_scores"], res["train_scores"]
+        fit_time, score_time, info, fds = res["fit_time"], res["score_time"], res["info"], res["fds"]
+        if res["n_unconverged"]:
+            import warnings
+
+            from sklearn.exceptions import ConvergenceWarning
+
+            warnings.warn(f"{res['n_unconverged']} (candidate, fold) problems did not reach the gap tolerance",
+                          ConvergenceWarning)
+
+        # ---- cv_results_ in sklearn's layout ------------------------------------------
+        results = {}
+
+        def _store(name, arr, splits_=False, rank=False):
+            if splits_:
+                for i in range(n_splits):
+                    results[f"split{i}_{name}"] = arr[:, i]
+            mean = arr.mean(axis=1)
+            results[f"mean_{name}"] = mean
+            results[f"std_{name}"] = np.sqrt(((arr - mean[:, None]) ** 2).mean(axis=1))
+            if rank:
+                if np.isnan(mean).all():
+                    ranks = np.ones_like(mean, dtype=np.int32)
+                else:
+                    m = np.nan_to_num(mean, nan=np.nanmin(mean) - 1)
+                    ranks = rankdata(-m, method="min").astype(np.int32, copy=False)
+                results[f"rank_{name}"] = ranks
+
+        _store("fit_time", np.tile(fit_time[:, None], (1, n_splits)))
+        _store("score_time", np.tile(score_time[:, None], (1, n_splits)))
+        names = sorted({k for c in candidates for k in c})
+        for name in names:
+            vals = [c.get(name, None) for c in candidates]
+            try:
+                arr = np.array(vals)
+                if arr.ndim != 1 or arr.dtype.kind not in "fiub":
+                    raise ValueError
+                ma = MaskedArray(arr, mask=[name not in c for c in candidates])
+            except Exception:
+                ma = MaskedArray(np.empty(n_cand, dtype=object), mask=[name not in c for c in candidates])
+                for i, v in enumerate(vals):
+                    ma[i] = v
+            results[f"param_{name}"] = ma
+        results["params"] = candidates
+        _store("test_score", test_scores, splits_=True, rank=True)
+        if train_scores is not None:
+            _store("train_score", train_scores, splits_=True)
+
+        self.multimetric_ = False
+        refit_metric = "score"
+        if self.refit or not self.multimetric_:
+            self.best_index_ = int(self._select_best_index(self.refit, refit_metric, results))
+            self.best_score_ = results["mean_test_score"][self.best_index_]
+            self.best_score_std_ = results["std_test_score"][self.best_index_]
+            self.best_params_ = results["params"][self.best_index_]
+        if self.refit:
+            bi = self.best_index_
+            self.best_estimator_ = clone(base).set_params(**clone(self.best_params_, safe=False))
+            spec = specs[bi]
+            fkey = (bool(ests[bi].fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
+            t0 = time.time()
+            self.best_estimator_.n_features_in_ = p
+            self.best_estimator_._fit_prepared(engine, fds[fkey], spec, dict(opts))
+            self.refit_time_ = time.time() - t0
+        from sklearn.metrics import check_scoring
+
+        self.scorer_ = check_scoring(base, scoring=self.scoring)
+        self.cv_results_ = results
+        self.n_splits_ = n_splits
+        self.solver_info_ = info
+        self.batched_ = True
+        return self
+
+
+class LineSearchCV(BaseSearchCV):
+    """Coordinate-wise line search over several hyper-parameters
+    (reference model_selection.py:427-703): ``n_iter`` successive 1-D grid searches,
+    parameter ``i % n_params`` swept while the others stay at their last best value
+    (initially the first value of their grid).
+
+    Args:
+        estimator: estimator object.
+        param_grid (list[tuple[str, list]]): ordered (name, values) pairs.
+        opt_selection_method (str | list[str] | None): selection rule per parameter.
+        n_iter (int | None): number of line searches; default ``2 * n_params``.
+        (remaining arguments as GridSearchCV)
+    """
+
+    def __init__(self, estimator, param_grid, *, opt_selection_method=None, n_iter=None,
+                 scoring="neg_root_mean_squared_error", n_jobs=None, refit=True, cv=None, verbose=0,
+                 pre_dispatch="2*n_jobs", error_score=np.nan, return_train_score=False):
+        super().__init__(estimator=estimator, scoring=scoring, n_jobs=n_jobs, refit=refit, cv=cv, verbose=verbose,
+                         pre_dispatch=pre_dispatch, error_score=error_score, return_train_score=return_train_score)
+        self.param_grid = param_grid
+        self.opt_selection_method = opt_selection_method
+        self.n_iter = n_iter
+
+    def fit(self, X, y=None, *, groups=None, **fit_params):
+        grid = self.param_grid
+        if not (isinstance(grid, (list, tuple)) and len(grid) > 0 and isinstance(grid[0], (tuple, list))
+                and isinstance(grid[0][0], str)):
+            raise ValueError("Parameter grid is not given in the correct format!")
+        n_params = len(grid)
+        if self.opt_selection_method is None:
+            methods = ["max_score"] * n_params
+        elif isinstance(self.opt_selection_method, str):
+            methods = [self.opt_selection_method] * n_params
+        elif (isinstance(self.opt_selection_method, (list, tuple))
+              and all(isinstance(m, str) for m in self.opt_selection_method)
+              and len(self.opt_selection_method) == n_params):
+            methods = list(self.opt_selection_method)
+        else:
+            raise ValueError(
+                "Optimal hyperparams selection methods should be given as a single string, or as a list of "
+                "strings with the same amount of parameters!")
+        n_iter = self.n_iter if (self.n_iter is not None and self.n_iter > 0) else 2 * n_params
+
+        history = []
+        fd_cache = {}  # device-resident design shared by every line (same X, y, folds)
+        best = None
+        for i in range(n_iter):
+            pid = i % n_params
+            last = [values[0] for _, values in grid] if best is None else [best[name] for name, _ in grid]
+            line = {name: (values if j == pid else [last[j]]) for j, (name, values) in enumerate(grid)}
+            gs = GridSearchCV(estimator=self.estimator, param_grid=line, opt_selection_method=methods[pid],
+                              scoring=self.scoring, n_jobs=self.n_jobs, refit=self.refit, cv=self.cv,
+                              verbose=self.verbose, pre_dispatch=self.pre_dispatch, error_score=self.error_score,
+                              return_train_score=self.return_train_score)
+            gs._fd_cache = fd_cache
+            if groups is not None:
+                fit_params = dict(fit_params, groups=groups)
+            gs.fit(X, y, **fit_params)
+            best = deepcopy(gs.best_params_)
+            history.append(gs)
+        for attr in [v for v in vars(history[-1]) if v.endswith("_") and not v.startswith("__")]:
+            setattr(self, attr, getattr(history[-1], attr))
+        self.history_ = history
+        return self
+
+    def _run_search(self, evaluate_candidates):
+        """Unused: the search is driven by ``fit``."""
+        return

@@ -1,0 +1,311 @@
+"""The reference's own estimator tests (tests/test_lasso.py, tests/test_common.py,
+tests/test_model_selection.py of CederGroupHub/sparse-lm), re-stated against the
+engine-backed estimators, plus coefficient parity with the CPU oracle."""
+
+import warnings
+
+import numpy as np
+import numpy.testing as npt
+import pytest
+from sklearn.datasets import make_regression
+
+pytestmark = pytest.mark.gpu
+
+import oracle.reference as R  # noqa: E402
+from sparselm_b200.model import (  # noqa: E402
+    AdaptiveGroupLasso,
+    AdaptiveLasso,
+    AdaptiveOverlapGroupLasso,
+    AdaptiveRidgedGroupLasso,
+    AdaptiveSparseGroupLasso,
+    GroupLasso,
+    Lasso,
+    OverlapGroupLasso,
+    RidgedGroupLasso,
+    SparseGroupLasso,
+)
+from sparselm_b200.model_selection import GridSearchCV, LineSearchCV  # noqa: E402
+
+THRESHOLD = 1e-8
+ADAPTIVE = [AdaptiveLasso, AdaptiveGroupLasso, AdaptiveSparseGroupLasso, AdaptiveOverlapGroupLasso,
+            AdaptiveRidgedGroupLasso]
+ALL = [Lasso, GroupLasso, OverlapGroupLasso, SparseGroupLasso, RidgedGroupLasso] + ADAPTIVE
+
+
+@pytest.fixture(scope="module", params=[20, 30])
+def random_model(request):
+    rng = np.random.default_rng(0)
+    X, y, beta = make_regression(n_samples=25, n_features=request.param, n_informative=10, coef=True,
+                                 random_state=int(rng.integers(0, 2 ** 31 - 1)), bias=10 * rng.random())
+    return X, y, beta
+
+
+@pytest.fixture(scope="module", params=[4, 6])
+def random_model_with_groups(random_model, request):
+    X, y, beta = random_model
+    rng = np.random.default_rng(request.param)
+    groups = rng.integers(0, request.param, size=len(beta))
+    groups[: request.param] = np.arange(request.param)
+    return X, y, beta, groups
+
+
+def _kwargs(cls, groups, rng, p):
+    if cls.__name__ in ("Lasso", "AdaptiveLasso"):
+        return {}
+    if "Overlap" in cls.__name__:
+        gids = np.unique(groups)
+        return {"group_list": [list(rng.choice(gids, replace=False, size=rng.integers(1, 3))) for _ in range(p)]}
+    return {"groups": groups}
+
+
+# ---- reference tests/test_lasso.py:29-61 (the only numeric KAT) ------------------
+def test_lasso_toy():
+    X = [[-1], [0], [1]]
+    Y = [-1, 0, 1]
+    T = [[2], [3], [4]]
+    for alpha, coef, pred in [(1e-8, [1], [2, 3, 4]), (0.1, [0.85], [1.7, 2.55, 3.4]),
+                              (0.5, [0.25], [0.5, 0.75, 1.0]), (1.0, [0.0], [0, 0, 0])]:
+        lasso = Lasso(alpha=alpha)
+        lasso.fit(X, Y)
+        npt.assert_array_almost_equal(lasso.coef_, coef)
+        npt.assert_array_almost_equal(lasso.predict(T), pred)
+
+
+# ---- reference tests/test_lasso.py:64-74 -----------------------------------------
+def test_lasso_non_float_y():
+    X = [[0, 0], [1, 1], [-1, -1]]
+    lasso = Lasso(fit_intercept=False).fit(X, [0, 1, 2])
+    lasso_float = Lasso(fit_intercept=False).fit(X, [0.0, 1.0, 2.0])
+    npt.assert_array_equal(lasso.coef_, lasso_float.coef_)
+
+
+# ---- reference tests/test_lasso.py:77-85 -----------------------------------------
+def test_adaptive_lasso_sparser(random_model):
+    X, y, _ = random_model
+    lasso = Lasso(fit_intercept=True).fit(X, y)
+    alasso = AdaptiveLasso(fit_intercept=True).fit(X, y)
+    assert sum(abs(lasso.coef_) > THRESHOLD) >= sum(abs(alasso.coef_) > THRESHOLD)
+
+
+# ---- reference tests/test_lasso.py:89-155 (standardize=False arm) ------------------
+def test_group_lasso_all_or_nothing(random_model_with_groups):
+    X, y, _, groups = random_model_with_groups
+    gw = np.ones(len(np.unique(groups)))
+    for est in (AdaptiveGroupLasso(groups=groups, alpha=0.1, fit_intercept=True),
+                AdaptiveGroupLasso(groups=groups, alpha=0.1, group_weights=gw, fit_intercept=True),
+                AdaptiveRidgedGroupLasso(groups=groups, alpha=0.1, group_weights=gw, fit_intercept=True)):
+        est.fit(X, y)
+        m = np.max(abs(est.coef_))
+        for gid in np.unique(groups):
+            c = abs(est.coef_[groups == gid])
+            assert (c > m * THRESHOLD).all() or (c <= m * THRESHOLD).all()
+
+
+def test_standardize_fails_loudly(random_model_with_groups):
+    X, y, _, groups = random_model_with_groups
+    with pytest.raises(NotImplementedError):
+        GroupLasso(groups=groups, standardize=True).fit(X, y)
+
+
+# ---- reference tests/test_lasso.py:203-260: warnings that need a completed fit -----
+def test_warnings_on_missing_groups(random_model_with_groups):
+    X, y, beta, groups = random_model_with_groups
+    with pytest.warns(UserWarning):
+        GroupLasso().fit(X, y)
+    with pytest.warns(UserWarning):
+        OverlapGroupLasso().fit(X, y)
+    with pytest.warns(UserWarning):
+        SparseGroupLasso(groups, l1_ratio=0.0).fit(X, y)
+    with pytest.warns(UserWarning):
+        SparseGroupLasso(groups, l1_ratio=1.0).fit(X, y)
+
+
+# ---- reference tests/test_common.py:35-67 --------------------------------------------
+@pytest.mark.parametrize("cls", ALL)
+def test_general_fit(cls, random_model):
+    X, y, beta = random_model
+    rng = np.random.default_rng(3)
+    args = {}
+    if "Overlap" in cls.__name__:
+        args["group_list"] = [list(np.sort(rng.choice(range(5), replace=False, size=rng.integers(1, 5))))
+                              for _ in range(len(beta))]
+    elif cls.__name__ not in ("Lasso", "AdaptiveLasso"):
+        args["groups"] = rng.integers(0, 5, size=len(beta))
+    est = cls(**args).fit(X, y)
+    assert isinstance(est.coef_, np.ndarray) and len(est.coef_) == len(beta)
+    assert len(est.predict(X)) == len(y)
+    assert est.intercept_ == 0.0
+    est = cls(fit_intercept=True, **args).fit(X, y)
+    assert isinstance(est.coef_, np.ndarray) and len(est.coef_) == len(beta)
+    assert est.intercept_ != 0.0
+
+
+# ---- coefficient parity of every estimator with the oracle ----------------------------
+@pytest.mark.parametrize("cls", ALL)
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_estimator_matches_oracle(cls, fit_intercept):
+    rng = np.random.default_rng(42)
+    n, p = 120, 36
+    X = rng.standard_normal((n, p)) + (0.7 if fit_intercept else 0.0)
+    w = np.zeros(p)
+    w[rng.choice(p, 6, replace=False)] = 3 * rng.standard_normal(6)
+    y = X @ w + 0.3 * rng.standard_normal(n) + (2.0 if fit_intercept else 0.0)
+    groups = rng.integers(0, 7, size=p)
+    kw = _kwargs(cls, groups, rng, p)
+    extra = {}
+    if "Ridged" in cls.__name__:
+        extra["delta"] = (0.7,)
+    if "Sparse" in cls.__name__:
+        extra["l1_ratio"] = 0.4
+    if cls.__name__ not in ("Lasso", "AdaptiveLasso"):
+        ng = len(np.unique(groups)) if "groups" in kw else len(np.unique([g for gl in kw["group_list"] for g in gl]))
+        extra["group_weights"] = 0.5 + rng.random(ng)
+    alpha = 0.08
+    est = cls(alpha=alpha, fit_intercept=fit_intercept, solver_options={"tol": 1e-12}, **kw, **extra).fit(X, y)
+    b_ref, i_ref, det = R.fit(cls.__name__, X, y, alpha=alpha, fit_intercept=fit_intercept, return_details=True,
+                              **kw, **extra)
+    scale = np.abs(b_ref).max()
+    assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * scale, np.abs(est.coef_ - b_ref).max()
+    assert np.array_equal(np.abs(est.coef_) > 1e-6, np.abs(b_ref) > 1e-6)
+    assert abs(est.intercept_ - i_ref) <= 1e-6 * max(1.0, abs(i_ref))
+    if cls in ADAPTIVE:
+        assert est.n_iter_ == det["n_iter"]
+
+
+def test_sample_weight_matches_oracle():
+    rng = np.random.default_rng(5)
+    n, p = 90, 15
+    X = rng.standard_normal((n, p))
+    y = X[:, :3] @ [1.0, -2.0, 0.5] + 0.1 * rng.standard_normal(n) + 1.0
+    sw = rng.random(n) + 0.1
+    for fi in (False, True):
+        est = Lasso(alpha=0.05, fit_intercept=fi, solver_options={"tol": 1e-12}).fit(X, y, sample_weight=sw)
+        b_ref, i_ref = R.fit("Lasso", X, y, alpha=0.05, fit_intercept=fi, sample_weight=sw)
+        assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+        assert abs(est.intercept_ - i_ref) <= 1e-7
+
+
+def test_user_update_function():
+    rng = np.random.default_rng(6)
+    X = rng.standard_normal((60, 12))
+    y = X[:, 0] - X[:, 3] + 0.05 * rng.standard_normal(60)
+    fn = lambda beta, eps: 1.0 / (np.abs(beta) ** 0.5 + eps)  # noqa: E731
+    est = AdaptiveLasso(alpha=0.05, update_function=fn, solver_options={"tol": 1e-12}).fit(X, y)
+    b_ref, _ = R.fit("AdaptiveLasso", X, y, alpha=0.05, update_function=fn)
+    assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+
+
+# ---- model selection --------------------------------------------------------------------
+def _cv_reference(name, X, y, alphas, cv, scoring="neg_root_mean_squared_error", **kw):
+    from sklearn.model_selection import KFold
+
+    scores = np.zeros((len(alphas), cv))
+    for f, (tr, te) in enumerate(KFold(cv).split(X)):
+        for i, a in enumerate(alphas):
+            b, icpt = R.fit(name, X[tr], y[tr], alpha=a, **kw)
+            r = y[te] - X[te] @ b - icpt
+            if scoring == "neg_root_mean_squared_error":
+                scores[i, f] = -np.sqrt(np.mean(r ** 2))
+            else:
+                scores[i, f] = 1 - (r ** 2).sum() / ((y[te] - y[te].mean()) ** 2).sum()
+    return scores
+
+
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_grid_search_matches_per_fit_oracle(fit_intercept):
+    rng = np.random.default_rng(8)
+    n, p = 150, 40
+    X = rng.standard_normal((n, p))
+    w = np.zeros(p)
+    w[:5] = [3, -2, 1.5, 1, -1]
+    y = X @ w + 0.5 * rng.standard_normal(n) + (1.5 if fit_intercept else 0)
+    groups = rng.permutation(np.repeat(np.arange(8), 5))
+    alphas = np.logspace(-2.5, 0, 9)
+    gs = GridSearchCV(SparseGroupLasso(groups=groups, l1_ratio=0.5, fit_intercept=fit_intercept,
+                                       solver_options={"tol": 1e-12}),
+                      {"alpha": alphas}, cv=5, return_train_score=True)
+    gs.fit(X, y)
+    assert gs.batched_
+    ref = _cv_reference("SparseGroupLasso", X, y, alphas, 5, groups=groups, l1_ratio=0.5,
+                        fit_intercept=fit_intercept)
+    got = np.stack([gs.cv_results_[f"split{i}_test_score"] for i in range(5)], axis=1)
+    npt.assert_allclose(got, ref, rtol=1e-8, atol=1e-10)
+    npt.assert_allclose(gs.cv_results_["mean_test_score"], ref.mean(1), rtol=1e-8)
+    best = int(np.argmax(ref.mean(1)))
+    assert gs.best_index_ == best and gs.best_params_["alpha"] == alphas[best]
+    assert gs.best_score_ == pytest.approx(ref.mean(1)[best], rel=1e-8)
+    assert gs.best_score_std_ == pytest.approx(ref.std(1)[best], rel=1e-6)
+    b_ref, i_ref = R.fit("SparseGroupLasso", X, y, alpha=alphas[best], groups=groups, l1_ratio=0.5,
+                         fit_intercept=fit_intercept)
+    assert np.abs(gs.best_estimator_.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+    assert gs.cv_results_["mean_train_score"].shape == (9,)
+    assert np.all(gs.cv_results_["mean_train_score"] >= gs.cv_results_["mean_test_score"] - 1e-9)
+    # same search through sklearn's generic per-fit path gives the same table
+    from sklearn.model_selection import GridSearchCV as SkGS
+
+    sk = SkGS(SparseGroupLasso(groups=groups, l1_ratio=0.5, fit_intercept=fit_intercept,
+                               solver_options={"tol": 1e-12}),
+              {"alpha": alphas[:3]}, cv=5, scoring="neg_root_mean_squared_error").fit(X, y)
+    npt.assert_allclose(sk.cv_results_["mean_test_score"], ref.mean(1)[:3], rtol=1e-8)
+
+
+def test_grid_search_two_parameters_and_r2_default_scoring():
+    rng = np.random.default_rng(9)
+    X = rng.standard_normal((100, 20))
+    y = X[:, :4] @ [2.0, -1.0, 1.0, 0.5] + 0.3 * rng.standard_normal(100)
+    groups = np.repeat(np.arange(5), 4)
+    grid = {"alpha": [0.01, 0.1, 0.5], "l1_ratio": [0.2, 0.8]}
+    gs = GridSearchCV(SparseGroupLasso(groups=groups), grid, cv=4, scoring=None).fit(X, y)
+    assert gs.batched_ and len(gs.cv_results_["params"]) == 6
+    for i, prm in enumerate(gs.cv_results_["params"]):
+        ref = _cv_reference("SparseGroupLasso", X, y, [prm["alpha"]], 4, scoring="r2", groups=groups,
+                            l1_ratio=prm["l1_ratio"])
+        assert gs.cv_results_["mean_test_score"][i] == pytest.approx(ref.mean(), rel=1e-7)
+
+
+# ---- reference tests/test_model_selection.py:122-167 (one-std rule) -----------------------
+def test_onestd_selects_larger_alpha_and_sparser_model():
+    success = 0
+    for seed in range(6):
+        X, y, coef = make_regression(n_samples=200, n_features=100, n_informative=10, noise=40.0, bias=-15.0,
+                                     coef=True, random_state=seed)
+        grid = {"alpha": np.logspace(-1, 1.2, 8)}
+        g1 = GridSearchCV(Lasso(fit_intercept=True), grid, opt_selection_method="max_score").fit(X, y)
+        g2 = GridSearchCV(Lasso(fit_intercept=True), grid, opt_selection_method="one_std_score").fit(X, y)
+        a1, a2 = g1.best_params_["alpha"], g2.best_params_["alpha"]
+        assert a1 <= a2
+        c1, c2 = g1.best_estimator_.coef_, g2.best_estimator_.coef_
+        if a1 < a2 and np.sum(np.abs(c1) > 1e-8) >= np.sum(np.abs(c2) > 1e-8):
+            success += 1
+    assert success >= 4
+
+
+def test_line_search_alpha_l1_ratio():
+    rng = np.random.default_rng(10)
+    X = rng.standard_normal((120, 24))
+    y = X[:, :3] @ [2.0, -1.5, 1.0] + 0.4 * rng.standard_normal(120)
+    groups = np.repeat(np.arange(6), 4)
+    grid = [("alpha", list(np.logspace(-2, 0, 5))), ("l1_ratio", [0.1, 0.5, 0.9])]
+    ls = LineSearchCV(SparseGroupLasso(groups=groups), grid, cv=4, n_iter=3).fit(X, y)
+    assert ls.best_params_["alpha"] in grid[0][1] and ls.best_params_["l1_ratio"] in grid[1][1]
+    assert ls.best_score_ <= 0 and hasattr(ls, "best_estimator_") and len(ls.history_) == 3
+    # the last line search is an alpha sweep at the l1_ratio chosen by the second one
+    assert ls.history_[2].param_grid["l1_ratio"] == [ls.history_[1].best_params_["l1_ratio"]]
+    npt.assert_allclose(ls.predict(X), X @ ls.best_estimator_.coef_ + ls.best_estimator_.intercept_)
+
+
+def test_readme_example_adaptive_lasso_grid():
+    """BASELINE config 1: README example; best_params_ compared tie-tolerantly."""
+    from sklearn.model_selection import GridSearchCV as SkGS
+
+    X, y = make_regression(n_samples=100, n_features=80, n_informative=10, random_state=0)
+    alphas = np.logspace(-8, 2, 10)
+    opts = {"tol": 1e-10, "max_iter": 200000}
+    gs = GridSearchCV(AdaptiveLasso(fit_intercept=False, solver_options=opts), {"alpha": alphas}, scoring=None,
+                      cv=5).fit(X, y)
+    mean = gs.cv_results_["mean_test_score"]
+    # oracle per cell
+    ref = _cv_reference("AdaptiveLasso", X, y, alphas, 5, scoring="r2")
+    npt.assert_allclose(mean, ref.mean(1), rtol=0, atol=2e-6)
+    ties = np.flatnonzero(ref.mean(1) >= ref.mean(1).max() - 1e-6)
+    assert gs.best_index_ in ties

@@ -1,0 +1,99 @@
+"""Pins the CPU oracle (oracle/) before it is trusted as the parity checker:
+reference KAT, sklearn's Lasso, orthonormal closed forms, KKT/gap certificates."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+from sklearn.datasets import make_regression
+
+import oracle.reference as R
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.json")))
+
+
+def test_reference_known_answer_lasso_toy():
+    kat = GOLD["reference_kat"]
+    X, y, T = np.array(kat["X"], float), np.array(kat["y"], float), np.array(kat["T"], float)
+    for c in kat["cases"]:
+        b, icpt = R.fit("Lasso", X, y, alpha=c["alpha"])
+        np.testing.assert_array_almost_equal(b, c["coef"], decimal=kat["decimal"])
+        np.testing.assert_array_almost_equal(T @ b + icpt, c["pred"], decimal=kat["decimal"])
+
+
+@pytest.mark.parametrize("case", GOLD["sklearn_lasso"], ids=lambda c: f"s{c['seed']}-{c['fit_intercept']}-{c['alpha']:.3g}")
+def test_oracle_lasso_matches_sklearn_golden(case):
+    X, y = make_regression(n_samples=case["n"], n_features=case["p"], n_informative=case["n_informative"],
+                           noise=case["noise"], random_state=case["seed"], bias=case["bias"])
+    b, icpt = R.fit("Lasso", X, y, alpha=case["alpha"], fit_intercept=case["fit_intercept"])
+    ref = np.array(case["coef"])
+    assert np.abs(b - ref).max() <= 1e-9 * max(np.abs(ref).max(), 1.0)
+    assert abs(icpt - case["intercept"]) <= 1e-9 * max(abs(case["intercept"]), 1.0)
+
+
+@pytest.mark.parametrize("name", ["Lasso", "GroupLasso", "SparseGroupLasso", "RidgedGroupLasso", "AdaptiveLasso",
+                                  "AdaptiveGroupLasso", "AdaptiveSparseGroupLasso", "AdaptiveRidgedGroupLasso"])
+def test_oracle_closed_forms_on_orthonormal_design(name):
+    o = GOLD["orthonormal"]
+    X, y = np.array(o["X"]), np.array(o["y"])
+    kw = {}
+    if name not in ("Lasso", "AdaptiveLasso"):
+        kw.update(groups=np.array(o["groups"]), group_weights=np.array(o["group_weights"]))
+    if "Sparse" in name:
+        kw["l1_ratio"] = o["l1_ratio"]
+    if "Ridged" in name:
+        kw["delta"] = np.array(o["delta"])
+    b, _ = R.fit(name, X, y, alpha=o["alpha"], **kw)
+    np.testing.assert_allclose(b, np.array(o[name]), rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["GroupLasso", "SparseGroupLasso", "RidgedGroupLasso", "OverlapGroupLasso"])
+def test_oracle_solution_satisfies_kkt_and_gap(name):
+    rng = np.random.default_rng(3)
+    n, p = 60, 24
+    X = rng.standard_normal((n, p))
+    y = X[:, :4] @ [2.0, -1.0, 0.5, 1.0] + 0.2 * rng.standard_normal(n)
+    groups = rng.integers(0, 6, size=p)
+    kw = dict(groups=groups, group_weights=0.5 + rng.random(len(np.unique(groups))))
+    if name == "OverlapGroupLasso":
+        gl = [list(rng.choice(5, size=rng.integers(1, 3), replace=False)) for _ in range(p)]
+        kw = dict(group_list=gl)
+    if name == "RidgedGroupLasso":
+        kw["delta"] = (0.3,)
+    b, _, det = R.fit(name, X, y, alpha=0.1, return_details=True, **kw)
+    pen = R.Penalty(det["labels"], det["w1"], det["w2"], det["delta"])
+    Xs, ys, bs = det["X_solve"], det["y_solve"], det["beta_solve"]
+    assert R.kkt_residual(Xs, ys, bs, pen) <= 1e-9
+    cert = R.certificate(Xs, ys, bs, pen)
+    assert 0 <= cert["gap"] + 1e-15 and cert["gap"] <= 1e-11 * max(cert["primal"], 1e-300)
+    assert cert["primal"] == pytest.approx(R.objective(Xs, ys, bs, pen), rel=1e-12)
+    # any perturbation increases the objective (convexity + optimality)
+    for _ in range(5):
+        d = 1e-4 * rng.standard_normal(len(bs))
+        assert R.objective(Xs, ys, bs + d, pen) >= cert["primal"] - 1e-14
+
+
+def test_oracle_overlap_expansion_and_fold_back():
+    group_list = [[0], [0, 1], [1], [2, 0], []]
+    idx, ext, ng = R.expand_overlap(group_list, 5)
+    np.testing.assert_array_equal(idx, [0, 1, 3, 1, 2, 3])
+    np.testing.assert_array_equal(ext, [0, 0, 0, 1, 1, 2])
+    assert ng == 3
+    np.testing.assert_allclose(R.fold_back(np.arange(1.0, 7.0), idx, 5), [1, 2 + 4, 5, 3 + 6, 0])
+
+
+def test_oracle_preprocess_matches_weighted_least_squares():
+    # reference tests/test_ols.py:36-66 pins sample_weight + intercept handling: a vanishing
+    # penalty must reproduce closed-form weighted least squares
+    rng = np.random.default_rng(4)
+    n, p = 50, 5
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) + 0.1 * rng.standard_normal(n) + 2.0
+    sw = rng.random(n) + 0.2
+    b, icpt = R.fit("Lasso", X, y, alpha=1e-12, fit_intercept=True, sample_weight=sw)
+    Xa = np.hstack([X, np.ones((n, 1))])
+    W = np.diag(sw)
+    sol = np.linalg.solve(Xa.T @ W @ Xa, Xa.T @ W @ y)
+    np.testing.assert_allclose(b, sol[:p], atol=1e-8)
+    assert icpt == pytest.approx(sol[p], abs=1e-8)
