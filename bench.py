@@ -1,0 +1,459 @@
+"""Benchmark of the hot path: CV grid fits/sec (alpha x fold), device-timed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
+                    [--workload c3|c2|c1|c4]
+
+One "step" = one full cross-validated grid search of the workload (every
+(alpha, fold) problem solved to the duality-gap tolerance and scored).
+
+* value     : fits/sec with X, y already resident in HBM when the timed region starts
+              (Gram build + Lipschitz + batched solve + CV scoring, CUDA events, max over ranks)
+* e2e       : the same through the public API, sparselm_b200.model_selection.GridSearchCV.fit on
+              HOST (pinned) arrays: H2D copy of X, y and D2H of scores/coefficients inside the
+              timed region, refit on the full data included
+* roofline  : the dominant kernel (FP64 DMMA Gram apply) against the FP64 tensor peak, which
+              MEASURED_PEAKS.json does not hold: it is measured here with cuBLAS DGEMM 8192^3
+* cpu_baseline / --impl reference : the CPU oracle (oracle/, block coordinate descent in C with
+              OpenMP over independent fits) on a bounded sample of the same workload.  The
+              reference's own cvxpy path cannot run in this image (cvxpy is not installed).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TOL = 1e-9  # relative duality gap (one decade inside the 1e-8 parity spec)
+
+
+# --------------------------------------------------------------------------- #
+# workloads
+# --------------------------------------------------------------------------- #
+def make_data(n, p, seed=0, noise=10.0):
+    """make_regression-style synthetic data (X ~ N(0,1), p/10 informative coefficients
+    100*U(0,1), y = Xw + noise*N(0,1)); generated with numpy for speed."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, p))
+    w = np.zeros(p)
+    idx = rng.choice(p, p // 10, replace=False)
+    w[idx] = 100.0 * rng.random(p // 10)
+    y = X @ w + noise * rng.standard_normal(n)
+    return X, y
+
+
+def workload(name):
+    from sparselm_b200.model import AdaptiveLasso, AdaptiveOverlapGroupLasso, Lasso, SparseGroupLasso
+
+    opts = {"tol": TOL}
+    if name == "c3":
+        n, p, G, K, F = 20000, 4000, 200, 100, 5
+        X, y = make_data(n, p)
+        rng = np.random.default_rng(1)
+        groups = rng.permutation(np.repeat(np.arange(G), p // G))  # shuffled labels (dataset.py:129-134)
+        est = SparseGroupLasso(groups=groups, l1_ratio=0.5, solver_options=opts)
+        desc = "SparseGroupLasso, 200 groups, 100 alphas x 5 folds, n=20000 p=4000 (BASELINE configs[2])"
+        oracle = dict(name="SparseGroupLasso", groups=groups, l1_ratio=0.5)
+    elif name == "c2":
+        n, p, K, F = 10000, 2000, 100, 5
+        X, y = make_data(n, p)
+        est = Lasso(solver_options=opts)
+        desc = "Lasso, 100 alphas x 5 folds, n=10000 p=2000 (BASELINE configs[1], one line of LineSearchCV)"
+        oracle = dict(name="Lasso")
+    elif name == "c1":
+        from sklearn.datasets import make_regression
+
+        n, p, K, F = 100, 80, 10, 5
+        X, y = make_regression(n_samples=100, n_features=80, n_informative=10, random_state=0)
+        est = AdaptiveLasso(solver_options={"tol": TOL, "max_iter": 100000})
+        alphas = np.logspace(-8, 2, 10)
+        desc = "AdaptiveLasso GridSearchCV, 10 alphas x 5 folds, make_regression n=100 p=80 (README, configs[0])"
+        return dict(X=X, y=y, est=est, alphas=alphas, F=F, desc=desc, name=name,
+                    oracle=dict(name="AdaptiveLasso"))
+    elif name == "c4":
+        n, p, G, K, F = 5000, 1500, 150, 20, 5
+        X, y = make_data(n, p)
+        rng = np.random.default_rng(2)
+        base = rng.permutation(np.repeat(np.arange(G), p // G))
+        extra = rng.random(p) < 0.3
+        group_list = [[int(base[j])] + ([int((base[j] + 1 + rng.integers(G - 1)) % G)] if extra[j] else [])
+                      for j in range(p)]
+        est = AdaptiveOverlapGroupLasso(group_list=group_list, solver_options={"tol": TOL, "max_iter": 50000})
+        desc = "AdaptiveOverlapGroupLasso, 30% overlap, 3 reweight passes, 20 alphas x 5 folds, n=5000 p=1500 (configs[3])"
+        oracle = dict(name="AdaptiveOverlapGroupLasso", group_list=group_list)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    alpha_max = np.abs(X.T @ y).max() / n
+    alphas = alpha_max * np.logspace(0, -3, K)
+    return dict(X=X, y=y, est=est, alphas=alphas, F=F, desc=desc, name=name, oracle=oracle)
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- #
+# CPU baseline: the oracle on a bounded sample, all host threads
+# --------------------------------------------------------------------------- #
+def cpu_sample_problem(wl, n_fits):
+    """One training fold + n_fits alphas spread over the grid, as inputs of slmo_bcd_many."""
+    import oracle.reference as R
+
+    X, y, o = wl["X"], wl["y"], wl["oracle"]
+    n, p = X.shape
+    te = np.arange(0, n // wl["F"])  # fold 0 of KFold(F)
+    tr = np.setdiff1d(np.arange(n), te)
+    Xt, yt = X[tr], y[tr]
+    name = o["name"]
+    if name not in ("Lasso", "SparseGroupLasso"):
+        return None
+    if name == "Lasso":
+        labels, G = np.arange(p), p
+        l1r = 1.0
+    else:
+        labels, G = R.group_labels(o["groups"], p)
+        l1r = o["l1_ratio"]
+    sel = np.unique(np.linspace(0, len(wl["alphas"]) - 1, n_fits).round().astype(int))
+    alphas = wl["alphas"][sel]
+    order = np.argsort(labels, kind="stable")
+    gptr = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=G))]).astype(np.int64)
+    Xc = np.asfortranarray(Xt[:, order])
+    return dict(Xc=Xc, y=np.ascontiguousarray(yt), gptr=gptr, G=G, p=p, n=len(tr), alphas=alphas, l1r=l1r,
+                name=name)
+
+
+def cpu_run(sp):
+    import ctypes
+
+    import oracle.reference as R
+
+    lib = R._load()
+    K, p, G = len(sp["alphas"]), sp["p"], sp["G"]
+    w1 = np.repeat((sp["l1r"] * sp["alphas"])[:, None], p, axis=1).copy()
+    w2 = np.repeat(((1 - sp["l1r"]) * sp["alphas"])[:, None], G, axis=1).copy()
+    dl = np.zeros((K, G))
+    betas = np.zeros((K, p))
+    infos = np.zeros((K, 4))
+    ns = np.full(K, sp["n"], dtype=np.int64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    Xs = (dp * K)(*[R._dp(sp["Xc"])] * K)
+    ys = (dp * K)(*[R._dp(sp["y"])] * K)
+    t0 = time.perf_counter()
+    lib.slmo_bcd_many(K, R._ip(ns), p, Xs, ys, G, R._ip(sp["gptr"]), R._dp(w1), R._dp(w2), R._dp(dl),
+                      TOL, 1e-14, 100000, 2, R._dp(betas), R._dp(infos))
+    dt = time.perf_counter() - t0
+    return K / dt, dt, infos
+
+
+def cpu_baseline(wl, n_fits=None):
+    import oracle.reference as R
+
+    R.build()
+    threads = R.num_threads()
+    n_fits = n_fits or max(4, min(threads, 16))
+    sp = cpu_sample_problem(wl, n_fits)
+    if sp is None:
+        return {"value": None, "unit": "fits/s", "cores": threads, "kind": "port",
+                "sample": "not timed for this workload"}
+    v, dt, infos = cpu_run(sp)
+    return {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
+            "sample": f"{len(sp['alphas'])} of the {len(wl['alphas'])} alphas on training fold 0 "
+                      f"(n={sp['n']}, p={sp['p']}), oracle BCD to gap {TOL:g}, {dt:.1f} s, "
+                      f"mean sweeps {infos[:, 0].mean():.0f}; cvxpy not installed: reference path not timed"}
+
+
+# --------------------------------------------------------------------------- #
+def dist_init(n_gpus):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return rank, world, local
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload)
+    import oracle.reference as R
+
+    R.build()
+    threads = R.num_threads()
+    sp = cpu_sample_problem(wl, max(4, min(threads, 16)))
+    if sp is None:
+        print(json.dumps({"impl": "reference", "unavailable": "CPU oracle arm not wired for this workload"}))
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, _ = cpu_run(sp)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    sample = (f"{len(sp['alphas'])} of {len(wl['alphas'])} alphas x 1 of {wl['F']} folds per step, oracle BCD "
+              f"(C, OpenMP over fits) to gap {TOL:g}; cvxpy is not installed so the reference's own solve "
+              f"cannot be timed")
+    line = {
+        "impl": "reference", "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "tol": TOL},
+        "cpu_baseline": {"value": value, "unit": "fits/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def measure_fp64_peak(torch, dev):
+    N = 8192
+    a = torch.randn(N, N, dtype=torch.float64, device=dev)
+    b = torch.randn(N, N, dtype=torch.float64, device=dev)
+    best = 1e9
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    return 2.0 * N ** 3 / best / 1e9  # TFLOP/s
+
+
+def run_engine(args):
+    import torch
+
+    rank, world, local = dist_init(args.gpus)
+    from sklearn.base import clone
+    from sklearn.model_selection import KFold
+
+    from sparselm_b200.engine import get_engine
+    from sparselm_b200.model_selection import GridSearchCV, batched_cv
+
+    wl = workload(args.workload)
+    X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
+    n, p = X.shape
+    n_fits = len(alphas) * F
+    engine = get_engine(local)
+    dev = engine.device
+    shard = None
+    if world > 1:
+        from sparselm_b200.parallel import GridShard
+
+        shard = GridShard(rank, world)
+
+    peak = measure_fp64_peak(torch, dev)
+
+    # ---- device-resident arm ------------------------------------------------------
+    Xd = torch.from_numpy(X).to(dev)
+    folds = [te for _, te in KFold(F).split(X)]
+    ests = [clone(est).set_params(alpha=a) for a in alphas]
+    specs = [e._problem_spec(p) for e in ests]
+    opts = est._engine_options()
+
+    def step_device():
+        return batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error",
+                          shard=shard) if shard is not None else \
+            batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    engine.timing_enable(True)
+    engine.timing_reset()
+    launches0 = engine.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times = []
+    for _ in range(args.steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = step_device()
+        e1.record()
+        barrier()
+        times.append(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    launches = engine.launch_count() - launches0
+    tim = engine.timing_read()
+    engine.timing_enable(False)
+    ms = float(np.mean(times))
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n_fits / (ms / 1e3)
+
+    # ---- end-to-end arm: public API on host (pinned) arrays --------------------------
+    Xp = torch.from_numpy(X).pin_memory()
+    Xh = Xp.numpy()
+    grid = {"alpha": list(alphas)}
+
+    def step_e2e():
+        gs = GridSearchCV(clone(est), grid, cv=F)
+        if shard is not None:
+            gs._shard = shard
+        gs.fit(Xh, y)
+        return gs
+
+    for _ in range(max(1, args.warmup // 2)):
+        gs = step_e2e()
+    e2e_times = []
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        gs = step_e2e()
+        torch.cuda.synchronize()
+        e2e_times.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = float(np.mean(e2e_times))
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = X.nbytes + y.nbytes
+    d2h = 8 * (n_fits * 2 + n_fits + p + 1)  # residual sums, per-fit info, refit coefficients
+
+    if rank != 0:
+        return
+    ap = tim["gram_apply"]
+    apply_ms = ap["ms"] / max(ap["launches"], 1)
+    algo_flops_per_launch = ap["flops"] / max(ap["launches"], 1)
+    achieved = algo_flops_per_launch / (apply_ms * 1e-3) / 1e12 if apply_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("gram_apply_dram_bytes_per_launch")
+    step_ms = {k: v["ms"] / args.steps for k, v in tim.items()}
+    info = res["info"]
+    line = {
+        "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "tol": TOL, "n_fits_per_step": n_fits,
+                   "iterations_per_step": int(res["iters_run"]), "mean_iterations_per_fit": float(info["n_iter"].mean()),
+                   "unconverged": int(res["n_unconverged"]),
+                   "l2": "inputs larger than L2 between iterations (X %.0f MB, fold Grams %.0f MB vs 126 MB L2)"
+                         % (X.nbytes / 1e6, (F + 1) * (p + 8) ** 2 * 8 / 1e6),
+                   "parallelism": f"grid-sharded x{world}" if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (Gram apply, FP64 DMMA)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                     "executed_tflops": (2.0 * p * p * n_fits / (apply_ms * 1e-3) / 1e12) if apply_ms > 0 else None,
+                     "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
+                     "traffic": traffic, "step_ms_by_kernel_family": step_ms},
+        "e2e": {"value": n_fits / (e2e_ms / 1e3), "unit": "fits/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "api": "sparselm_b200.model_selection.GridSearchCV.fit (pinned host X, refit included)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        try:
+            import torch.distributed as dist
+
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,8 @@ int slm_sm_count(const slm_ctx* ctx);
 int64_t slm_launch_count(const slm_ctx* ctx);
 /* average device time in ms of the `which` kernel family since the last reset,
  * measured with CUDA events on the launching stream when timing is enabled.
- * which: 0 = gram build, 1 = gram apply, 2 = prox, 3 = gap, 4 = score */
+ * which: 0 = gram build, 1 = gram apply (solver), 2 = prox, 3 = gap, 4 = score,
+ *        5 = gram apply inside the Lipschitz power iteration */
 int slm_timing_enable(slm_ctx* ctx, int on);
 int slm_timing_read(slm_ctx* ctx, int which, double* total_ms, int64_t* launches, double* flops);
 int slm_timing_reset(slm_ctx* ctx);

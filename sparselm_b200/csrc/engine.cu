@@ -31,7 +31,7 @@ using namespace slm;
 // ------------------------------------------------------------------------- //
 // context
 // ------------------------------------------------------------------------- //
-enum { FAM_GRAM = 0, FAM_APPLY = 1, FAM_PROX = 2, FAM_GAP = 3, FAM_SCORE = 4, FAM_COUNT = 5 };
+enum { FAM_GRAM = 0, FAM_APPLY = 1, FAM_PROX = 2, FAM_GAP = 3, FAM_SCORE = 4, FAM_LIPS = 5, FAM_COUNT = 6 };
 
 struct Family {
     std::vector<cudaEvent_t> ev;  // begin/end pairs not yet accumulated
@@ -169,25 +169,40 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// K-major (apply) menu; index = shape id
+// K-major (apply) menu.  X(id, WM, WN, MI, NI, MINB, eff): tile = (WM*MI*8) x (WN*NI*8);
+// eff = measured fraction of the per-SM DMMA peak of that warp layout (profiles/).
+#define SLM_APPLY_SHAPES(X)        \
+    X(0, 2, 4, 8, 4, 1, 0.76)      \
+    X(1, 8, 1, 2, 13, 1, 0.72)     \
+    X(2, 16, 1, 1, 13, 1, 0.776)   \
+    X(3, 8, 1, 2, 7, 2, 0.765)     \
+    X(4, 4, 4, 4, 4, 1, 0.80)      \
+    X(5, 4, 2, 4, 4, 2, 0.78)      \
+    X(6, 8, 1, 1, 13, 2, 0.74)     \
+    X(7, 8, 1, 2, 4, 2, 0.84)      \
+    X(8, 8, 1, 2, 2, 2, 0.70)      \
+    X(9, 8, 1, 2, 1, 2, 0.55)      \
+    X(10, 8, 1, 2, 3, 2, 0.78)     \
+    X(11, 8, 1, 2, 5, 2, 0.80)     \
+    X(12, 8, 1, 2, 6, 2, 0.79)     \
+    X(13, 16, 1, 1, 9, 1, 0.775)   \
+    X(14, 16, 1, 1, 10, 1, 0.775)  \
+    X(15, 16, 1, 1, 11, 1, 0.775)  \
+    X(16, 16, 1, 1, 12, 1, 0.775)
+
 static const Shape kApplyShapes[] = {
-    {128, 128, 1, 0.84}, {128, 104, 1, 0.79}, {128, 104, 1, 0.85}, {128, 56, 2, 0.85}, {128, 128, 1, 0.85},
-    {128, 64, 2, 0.85},  {64, 104, 2, 0.85},  {128, 32, 2, 0.80},  {128, 16, 2, 0.70}, {128, 8, 2, 0.60},
+#define X(id, wm, wn, mi, ni, minb, eff) {wm * mi * 8, wn * ni * 8, minb, eff},
+    SLM_APPLY_SHAPES(X)
+#undef X
 };
 constexpr int kNumApplyShapes = sizeof(kApplyShapes) / sizeof(Shape);
 
 static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
-        case 0: return launch_gemm_t<2, 4, 8, 4, false, false, 1>(ctx, b, s);
-        case 1: return launch_gemm_t<8, 1, 2, 13, false, false, 1>(ctx, b, s);
-        case 2: return launch_gemm_t<16, 1, 1, 13, false, false, 1>(ctx, b, s);
-        case 3: return launch_gemm_t<8, 1, 2, 7, false, false, 2>(ctx, b, s);
-        case 4: return launch_gemm_t<4, 4, 4, 4, false, false, 1>(ctx, b, s);
-        case 5: return launch_gemm_t<4, 2, 4, 4, false, false, 2>(ctx, b, s);
-        case 6: return launch_gemm_t<8, 1, 1, 13, false, false, 2>(ctx, b, s);
-        case 7: return launch_gemm_t<8, 1, 2, 4, false, false, 2>(ctx, b, s);
-        case 8: return launch_gemm_t<8, 1, 2, 2, false, false, 2>(ctx, b, s);
-        case 9: return launch_gemm_t<8, 1, 2, 1, false, false, 2>(ctx, b, s);
+#define X(id_, wm, wn, mi, ni, minb, eff) \
+    case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb>(ctx, b, s);
+        SLM_APPLY_SHAPES(X)
+#undef X
     }
     return cudaErrorInvalidValue;
 }
@@ -242,7 +257,7 @@ static int pick_shape(const Shape* shapes, int n_shapes, const ProblemDims* pd, 
 // batched apply: GZ_f = G_f Z_f for f < F, with N_f = round_up(K_f, 8)
 static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int F,
                          const int32_t* K, const double* Z, int64_t ldz, double* GZ, cudaStream_t s,
-                         double algo_flops = -1.0) {
+                         double algo_flops = -1.0, int family = FAM_APPLY) {
     for (int f0 = 0; f0 < F; f0 += kMaxGemmProblems) {
         int nf = std::min(F - f0, (int)kMaxGemmProblems);
         GemmBatch b;
@@ -267,7 +282,7 @@ static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_
         }
         int sid = pick_shape(kApplyShapes, kNumApplyShapes, pd, nf, ctx->sm_count);
         if (ctx->force_apply_shape >= 0 && ctx->force_apply_shape < kNumApplyShapes) sid = ctx->force_apply_shape;
-        FamTimer tm(ctx, FAM_APPLY, s, algo_flops >= 0 ? algo_flops : flops);
+        FamTimer tm(ctx, family, s, algo_flops >= 0 ? algo_flops : flops);
         cudaError_t e = launch_apply_shape(ctx, sid, b, s);
         if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("gram apply: ") + cudaGetErrorString(e));
         ctx->launches++;
@@ -368,14 +383,15 @@ __device__ __forceinline__ T block_col_reduce_sum(T v, T (*red)[CT], int gl, int
     return r;
 }
 
-__global__ void init_cols_kernel(double* theta, double* tmom, int* flag, int* status, int* n_iter,
-                                 const int* skip, long long n) {
+__global__ void init_cols_kernel(double* theta, double* tmom, int* flag, int* colmap, int* status, int* n_iter,
+                                 const int* skip, long long n, int ldz) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     theta[i] = theta[n + i] = 0.0;  // both parities
     tmom[i] = tmom[n + i] = 1.0;
+    colmap[i] = (int)(i % ldz);
     if (skip && skip[i]) {
-        flag[i] = 3;  // frozen from the start; results of the earlier solve are kept
+        flag[i] = 3;  // frozen by the caller; results of the earlier solve are kept
         return;
     }
     flag[i] = 0;
@@ -593,8 +609,8 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_FORCE_SYRK_SHAPE")) ctx->force_syrk_shape = atoi(e);
     ctx->n_flags_cap = 1 << 20;
     if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counter, sizeof(int)) != cudaSuccess ||
-        cudaMallocHost(&ctx->h_counter, sizeof(int)) != cudaSuccess) {
+        cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess) {
         delete ctx;
         return 6;
     }
@@ -758,7 +774,7 @@ int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, i
     power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 1);
     LAUNCH_OK("power_norm_kernel(init)");
     for (int it = 0; it < iters; ++it) {
-        int rc = apply_batched(ctx, G, g_stride, pa, p, n_grams, K.data(), V, 8, W, s, 0.0);
+        int rc = apply_batched(ctx, G, g_stride, pa, p, n_grams, K.data(), V, 8, W, s, -1.0, FAM_LIPS);
         if (rc) return rc;
         power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 0);
         LAUNCH_OK("power_norm_kernel");
@@ -773,7 +789,7 @@ size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups) {
     size_t state = (size_t)n_folds * (size_t)p * (size_t)ldz * sizeof(double);
     size_t cols = (size_t)n_folds * (size_t)ldz;
     size_t part = cols * (size_t)kMaxChunks * NQ * sizeof(double);
-    return 4 * state + cols * (4 * sizeof(double) + sizeof(int)) + part + 256;
+    return 5 * state + cols * (4 * sizeof(double) + 3 * sizeof(int)) + part + 64 * sizeof(int) + 256;
 }
 
 int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
@@ -794,10 +810,14 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     double* GZ = Z + state;
     double* GB = GZ + state;
     double* T = GB + state;
-    double* theta = T + state;       // [2][cols]
+    double* Bw = T + state;
+    double* theta = Bw + state;       // [2][cols]
     double* tmom = theta + 2 * cols;  // [2][cols]
     double* part = tmom + 2 * cols;   // [F][n_chunks][NQ][ldz]
     int* flag = (int*)(part + cols * (size_t)kMaxChunks * NQ);
+    int* colmap = flag + cols;
+    int* src = colmap + cols;
+    int* newK = src + cols;  // [F]
 
     SolveDev sp;
     memset(&sp, 0, sizeof(sp));
@@ -813,7 +833,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.W1 = bt->W1_dev;
     sp.W2 = bt->W2_dev;
     sp.D2 = bt->D2_dev;
-    sp.B = bt->B_dev;
+    sp.B = Bw;
+    sp.Bout = bt->B_dev;
+    sp.colmap = colmap;
+    sp.skip = bt->skip_dev;
     sp.Z = Z;
     sp.GZ = GZ;
     sp.GB = GB;
@@ -833,41 +856,50 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.counter = ctx->d_counter;
     sp.tol = bt->tol;
     sp.floor_rel = bt->floor_rel;
-    int Kmax = 0;
+    int Kcur[SLM_MAX_FOLDS];
+    int Kmax0 = 0;
     long long Ktot = 0;
     for (int f = 0; f < F; ++f) {
         if (bt->K[f] < 0 || bt->K[f] > ldz) return fail(ctx, 1, "slm_solve_batch: K[f] out of range");
-        if (!(bt->lipschitz[f] > 0.0) || !(bt->n_obs[f] > 0.0))
+        if (bt->K[f] > 0 && (!(bt->lipschitz[f] > 0.0) || !(bt->n_obs[f] > 0.0)))
             return fail(ctx, 1, "slm_solve_batch: lipschitz and n_obs must be positive");
-        sp.K[f] = bt->K[f];
-        sp.n_obs[f] = bt->n_obs[f];
-        sp.step[f] = 1.0 / bt->lipschitz[f];
-        Kmax = std::max(Kmax, bt->K[f]);
+        sp.K[f] = Kcur[f] = bt->K[f];
+        sp.n_obs[f] = bt->n_obs[f] > 0.0 ? bt->n_obs[f] : 1.0;
+        sp.step[f] = bt->lipschitz[f] > 0.0 ? 1.0 / bt->lipschitz[f] : 0.0;
+        Kmax0 = std::max(Kmax0, bt->K[f]);
         Ktot += bt->K[f];
     }
     bt->iters_run = 0;
     bt->n_unconverged = 0;
-    if (Kmax == 0) return 0;
+    if (Kmax0 == 0) return 0;
 
-    init_cols_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(theta, tmom, flag, sp.status, sp.n_iter,
-                                                                    bt->skip_dev, (long long)cols);
+    init_cols_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(theta, tmom, flag, colmap, sp.status, sp.n_iter,
+                                                                    bt->skip_dev, (long long)cols, (int)ldz);
     LAUNCH_OK("init_cols_kernel");
+    CUDA_OK(cudaMemcpyAsync(Bw, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemsetAsync(GB, 0, state * sizeof(double), s));
 
-    const dim3 cgrid((unsigned)((Kmax + SC - 1) / SC), (unsigned)sp.n_chunks, (unsigned)F);
-    const dim3 mgrid((unsigned)((Kmax + SC - 1) / SC), (unsigned)((p + MOM_ROWS - 1) / MOM_ROWS), (unsigned)F);
-    const dim3 fgrid((unsigned)((Kmax + 127) / 128), (unsigned)F);
+    auto grids = [&](int Kmax, dim3& cgrid, dim3& mgrid, dim3& fgrid) {
+        cgrid = dim3((unsigned)((Kmax + SC - 1) / SC), (unsigned)sp.n_chunks, (unsigned)F);
+        mgrid = dim3((unsigned)((Kmax + SC - 1) / SC), (unsigned)((p + MOM_ROWS - 1) / MOM_ROWS), (unsigned)F);
+        fgrid = dim3((unsigned)((Kmax + 127) / 128), (unsigned)F);
+    };
+    dim3 cgrid, mgrid, fgrid;
+    int Kmax = Kmax0;
+    grids(Kmax, cgrid, mgrid, fgrid);
     const int check_every = std::max(1, bt->check_every);
     long long n_active = Ktot;
+    int n_active_f[SLM_MAX_FOLDS] = {0};
+    bool do_compact = false;
     int it = 0;
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
         double algo = 2.0 * (double)p * (double)p * (double)n_active;
-        int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, bt->K, Z, ldz, GZ, s, algo);
+        int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
         if (rc) return rc;
         if (it % check_every == 0) {
-            CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), s));
+            CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
             {
                 FamTimer tm(ctx, FAM_GAP, s, 0.0);
                 gap_partial_kernel<<<cgrid, ST, 0, s>>>(sp, par, 0);
@@ -875,10 +907,18 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             }
             LAUNCH_OK("gap kernels");
             ctx->launches++;
-            CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS,
+                                    cudaMemcpyDeviceToHost, s));
             CUDA_OK(cudaStreamSynchronize(s));
-            n_active = *ctx->h_counter;
+            n_active = 0;
+            bool shrink = false;
+            for (int f = 0; f < F; ++f) {
+                n_active_f[f] = ctx->h_counter[f];
+                n_active += n_active_f[f];
+                if (round_up(n_active_f[f], 8) < round_up(Kcur[f], 8)) shrink = true;
+            }
             if (n_active == 0) break;
+            do_compact = shrink;
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);
@@ -887,26 +927,53 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         LAUNCH_OK("prox kernels");
         ctx->launches++;
+        if (do_compact) {
+            // converged columns leave the batch (after this iteration's epilogue, so that GZ of
+            // the old layout is no longer needed): scatter their coefficients to the caller's
+            // array, move the active columns of Z, B, GB to the front
+            compact_plan_kernel<<<F, 32, 0, s>>>(sp, src, newK);
+            scatter_done_kernel<<<mgrid, ST, 0, s>>>(sp, 0);
+            compact_move_kernel<<<dim3((unsigned)((p + 127) / 128), 3, (unsigned)F), 128, 0, s>>>(sp, src, newK);
+            compact_cols_kernel<<<F, 32, 0, s>>>(sp, src, newK, colmap);
+            LAUNCH_OK("compaction kernels");
+            ctx->launches += 3;
+            Kmax = 0;
+            for (int f = 0; f < F; ++f) {
+                sp.K[f] = Kcur[f] = n_active_f[f];
+                Kmax = std::max(Kmax, Kcur[f]);
+            }
+            grids(Kmax, cgrid, mgrid, fgrid);
+            do_compact = false;
+        }
     }
     bt->iters_run = it;
+    // coefficients still in the working array go back to the caller's layout
+    scatter_done_kernel<<<mgrid, ST, 0, s>>>(sp, 1);
+    LAUNCH_OK("scatter_done_kernel");
 
-    // final certificate from an exact G*B
+    // final certificate from an exact G*B, in the original column order
+    SolveDev fin = sp;
+    fin.B = bt->B_dev;
+    fin.colmap = nullptr;
+    for (int f = 0; f < F; ++f) fin.K[f] = bt->K[f];
+    grids(Kmax0, cgrid, mgrid, fgrid);
     CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     {
         int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, bt->K, Z, ldz, GZ, s, 0.0);
         if (rc) return rc;
     }
-    CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), s));
+    CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
     {
         FamTimer tm(ctx, FAM_GAP, s, 0.0);
-        gap_partial_kernel<<<cgrid, ST, 0, s>>>(sp, 0, 1);
-        gap_final_kernel<<<fgrid, 128, 0, s>>>(sp, it, 1);
+        gap_partial_kernel<<<cgrid, ST, 0, s>>>(fin, 0, 1);
+        gap_final_kernel<<<fgrid, 128, 0, s>>>(fin, it, 1);
     }
     LAUNCH_OK("gap kernels(final)");
     ctx->launches++;
-    CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
-    bt->n_unconverged = *ctx->h_counter;
+    bt->n_unconverged = 0;
+    for (int f = 0; f < F; ++f) bt->n_unconverged += ctx->h_counter[f];
     return 0;
 }
 

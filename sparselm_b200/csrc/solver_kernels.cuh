@@ -1,6 +1,8 @@
 // Solver-side kernels of the batched accelerated proximal-gradient method:
 //   K6  prox_main_kernel + prox_momentum_kernel   (fused epilogue of one iteration)
 //   K7  gap_partial_kernel + gap_final_kernel     (duality gap + convergence mask)
+//       compact_* kernels: converged columns drop out of the batch (their coefficients
+//       are scattered to the caller's array, active columns move to the front)
 // All HBM/L2-bound.  State is feature-major [F][p][ldz] (grid columns contiguous),
 // groups are contiguous feature ranges gptr[g]..gptr[g+1].
 //
@@ -33,7 +35,10 @@ struct SolveDev {
     const double* G;
     const int* gptr;
     const double *lam1, *W1, *W2, *D2;
-    double *B, *Z, *GZ, *GB, *T;
+    double *B, *Z, *GZ, *GB, *T;  // B: working coefficients (compact column order)
+    double* Bout;                 // caller's coefficient array (original column order)
+    const int* colmap;            // [F][ldz] compact column -> original column (NULL: identity)
+    const int* skip;              // [F][ldz] original order, columns the caller froze (may be NULL)
     double* theta[2];
     double* tmom[2];
     double* part;  // [F][n_chunks][NQ][ldz]
@@ -97,9 +102,11 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
     const double n = sp.n_obs[f], step = sp.step[f];
     const double son = step / n;
     const long long ldz = sp.ldz;
+    const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;  // original column (penalty arrays)
     const long long sbase = (long long)f * sp.p * ldz + k;
-    const long long gbase = (long long)f * sp.Gn * ldz + k;
-    const double lam1 = (active && sp.lam1) ? sp.lam1[colbase] : 0.0;
+    const long long wbase = (long long)f * sp.p * ldz + ko;
+    const long long gbase = (long long)f * sp.Gn * ldz + ko;
+    const double lam1 = (active && sp.lam1) ? sp.lam1[(long long)f * ldz + ko] : 0.0;
 
     double dot = 0.0;
     if (active) {
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
                 const double gz = sp.GZ[e];
                 sp.GB[e] = (gz + theta * sp.GB[e]) * inv1pt;
                 const double v = sp.Z[e] - son * (gz - cvec[j]);
-                const double w1 = sp.W1 ? sp.W1[e] : lam1;
+                const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
                 const double u = softt(v, step * w1);
                 sp.T[e] = u;  // stash; scaled below
                 ss += u * u;
@@ -234,8 +241,10 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
     __shared__ double red[SG][SC];
     const long long ldz = sp.ldz;
     const long long colbase = (long long)f * ldz + k;
-    const int flag = (k < Kf) ? sp.flag[colbase] : 3;
-    const bool active = flag != 3 && (final_mode || flag == 0);
+    // loop mode: compact columns still iterating; final mode: every original column the
+    // caller did not freeze (state arrays are then in original order, colmap == NULL)
+    bool active = k < Kf;
+    if (active) active = final_mode ? !(sp.skip && sp.skip[colbase]) : (sp.flag[colbase] == 0);
     if (__syncthreads_and(!active)) return;
 
     const double theta = (active && !final_mode) ? sp.theta[par][colbase] : 0.0;
@@ -243,9 +252,11 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
     const double* __restrict__ cvec = sp.G + (long long)f * sp.g_stride + (long long)sp.p * sp.pa;
     const double n = sp.n_obs[f];
     const double inv_n = 1.0 / n;
+    const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;
     const long long sbase = (long long)f * sp.p * ldz + k;
-    const long long gbase = (long long)f * sp.Gn * ldz + k;
-    const double lam1 = (active && sp.lam1) ? sp.lam1[colbase] : 0.0;
+    const long long wbase = (long long)f * sp.p * ldz + ko;
+    const long long gbase = (long long)f * sp.Gn * ldz + ko;
+    const double lam1 = (active && sp.lam1) ? sp.lam1[(long long)f * ldz + ko] : 0.0;
 
     auto gb_at = [&](long long e) {
         const double gz = sp.GZ[e];
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
                 const double gb = gb_at(e);
                 const double b = sp.B[e];
                 const double cj = cvec[j];
-                const double w1 = sp.W1 ? sp.W1[e] : lam1;
+                const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
                 cb += cj * b;
                 bgb += b * gb;
                 pen += w1 * fabs(b);
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
                 const long long e = sbase + (long long)j * ldz;
                 return fabs((cvec[j] - gb_at(e)) * inv_n - d2 * sp.B[e]);
             };
-            auto wfun = [&](int j) { return sp.W1 ? sp.W1[sbase + (long long)j * ldz] : lam1; };
+            auto wfun = [&](int j) { return sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1; };
             double gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
             bool anyinf = false;
             for (int j = ja; j < jb; ++j) {
@@ -354,15 +365,17 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
 }
 
 // ---- K7b: finish the gap per column, set convergence flags --------------------------
+// counter[f] receives the number of columns of fold f that are still iterating.
 __global__ void gap_final_kernel(const __grid_constant__ SolveDev sp, int it, int final_mode) {
     const int f = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sp.K[f]) return;
     const long long ldz = sp.ldz;
     const long long colbase = (long long)f * ldz + k;
-    const int flag = sp.flag[colbase];
-    const bool active = flag != 3 && (final_mode || flag == 0);
+    const bool active = final_mode ? !(sp.skip && sp.skip[colbase]) : (sp.flag[colbase] == 0);
     if (!active) return;
+    const int ko = sp.colmap ? sp.colmap[colbase] : k;
+    const long long obase = (long long)f * ldz + ko;
     double cb = 0.0, bgb = 0.0, pen = 0.0, ridge = 0.0, omega = 0.0;
     for (int ch = 0; ch < sp.n_chunks; ++ch) {
         const double* src = sp.part + (((long long)f * sp.n_chunks + ch) * NQ) * ldz + k;
@@ -386,20 +399,89 @@ __global__ void gap_final_kernel(const __grid_constant__ SolveDev sp, int it, in
     const double scale = fmax(fabs(P), sp.floor_rel * yty / (2.0 * n));
     const bool finite = isfinite(P) && isfinite(gap);
     const bool conv = finite && gap <= sp.tol * scale;
-    if (sp.gap) sp.gap[colbase] = gap;
-    if (sp.primal) sp.primal[colbase] = P;
+    if (sp.gap) sp.gap[obase] = gap;
+    if (sp.primal) sp.primal[obase] = P;
     if (!final_mode) {
         if (conv || !finite) {
             sp.flag[colbase] = 1;
-            if (sp.n_iter) sp.n_iter[colbase] = it;
-            if (sp.status) sp.status[colbase] = finite ? 0 : 2;
+            if (sp.n_iter) sp.n_iter[obase] = it;
+            if (sp.status) sp.status[obase] = finite ? 0 : 2;
         } else {
-            atomicAdd(sp.counter, 1);
+            atomicAdd(sp.counter + f, 1);
         }
-    } else if (flag == 0) {  // not flagged inside the loop: judge the final point
-        if (sp.n_iter) sp.n_iter[colbase] = it;
-        if (sp.status) sp.status[colbase] = !finite ? 2 : (conv ? 0 : 1);
-        if (!conv) atomicAdd(sp.counter, 1);
+    } else {
+        const bool undecided = sp.status ? sp.status[obase] == -1 : true;
+        if (undecided) {  // not flagged inside the loop: judge the final point
+            if (sp.n_iter) sp.n_iter[obase] = it;
+            if (sp.status) sp.status[obase] = !finite ? 2 : (conv ? 0 : 1);
+        }
+        if (!conv) atomicAdd(sp.counter + f, 1);
+    }
+}
+
+// ---- compaction ------------------------------------------------------------------------
+// src[f][kc] = current index of the kc-th still-active column of fold f (kc < newK[f]).
+__global__ void compact_plan_kernel(const __grid_constant__ SolveDev sp, int* __restrict__ src,
+                                    int* __restrict__ newK) {
+    const int f = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const long long base = (long long)f * sp.ldz;
+    int kc = 0;
+    for (int k = 0; k < sp.K[f]; ++k)
+        if (sp.flag[base + k] == 0) src[base + kc++] = k;
+    newK[f] = kc;
+}
+
+// copy finished columns of the working B to the caller's array (original positions).
+// all != 0: every column that is not caller-frozen (end of the solve).
+__global__ void __launch_bounds__(ST) scatter_done_kernel(const __grid_constant__ SolveDev sp, int all) {
+    const int f = blockIdx.z;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, r = threadIdx.x / SC;
+    const int k = k0 + c;
+    if (k >= Kf) return;
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const int flag = sp.flag[colbase];
+    if (flag == 3 || (!all && flag == 0)) return;
+    const int ko = sp.colmap ? sp.colmap[colbase] : k;
+    const long long sb = (long long)f * sp.p * ldz + k, ob = (long long)f * sp.p * ldz + ko;
+    const int j0 = blockIdx.y * MOM_ROWS;
+    const int j1 = min(j0 + MOM_ROWS, sp.p);
+    for (int j = j0 + r; j < j1; j += SG) sp.Bout[ob + (long long)j * ldz] = sp.B[sb + (long long)j * ldz];
+}
+
+// in-place left shift of the active columns of one state array row (src is increasing)
+__global__ void compact_move_kernel(const __grid_constant__ SolveDev sp, const int* __restrict__ src,
+                                    const int* __restrict__ newK) {
+    const int f = blockIdx.z, a = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= sp.p) return;
+    const int nk = newK[f];
+    if (nk == sp.K[f]) return;
+    double* arr = a == 0 ? sp.Z : (a == 1 ? sp.B : sp.GB);
+    double* row = arr + ((long long)f * sp.p + j) * sp.ldz;
+    const int* sf = src + (long long)f * sp.ldz;
+    for (int kc = 0; kc < nk; ++kc) row[kc] = row[sf[kc]];
+}
+
+__global__ void compact_cols_kernel(const __grid_constant__ SolveDev sp, const int* __restrict__ src,
+                                    const int* __restrict__ newK, int* __restrict__ colmap) {
+    const int f = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const int nk = newK[f];
+    if (nk == sp.K[f]) return;
+    const long long base = (long long)f * sp.ldz;
+    for (int kc = 0; kc < nk; ++kc) {
+        const int k = src[base + kc];
+        for (int par = 0; par < 2; ++par) {
+            sp.theta[par][base + kc] = sp.theta[par][base + k];
+            sp.tmom[par][base + kc] = sp.tmom[par][base + k];
+        }
+        colmap[base + kc] = colmap[base + k];
+        sp.flag[base + kc] = 0;
     }
 }
 

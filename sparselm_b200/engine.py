@@ -77,8 +77,10 @@ class FoldData:
 
 
 class Engine:
-    LIPSCHITZ_ITERS = 32
-    LIPSCHITZ_MARGIN = 1.05
+    # 12 block power iterations reach >= 0.93 lambda_max on flat (Marchenko-Pastur) spectra;
+    # the margin turns the lower bound into a safe step size (tests/test_gpu_engine.py)
+    LIPSCHITZ_ITERS = 12
+    LIPSCHITZ_MARGIN = 1.10
 
     def __init__(self, device: int | None = None):
         import torch
@@ -143,7 +145,7 @@ class Engine:
         self.lib.slm_timing_reset(self.h)
 
     def timing_read(self):
-        names = ["gram_build", "gram_apply", "prox", "gap", "score"]
+        names = ["gram_build", "gram_apply", "prox", "gap", "score", "lipschitz_apply"]
         out = {}
         for i, nm in enumerate(names):
             ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
@@ -170,13 +172,15 @@ class Engine:
                  "slm_pack_design")
         return Xa
 
-    def gram_blocks(self, Xa, row_ptr, extra=0):
-        """[F(+extra), pa, pa]: block f = Xa[rows_f]^T Xa[rows_f]; `extra` spare slots."""
+    def gram_blocks(self, Xa, row_ptr, extra=0, zero=False):
+        """[F(+extra), pa, pa]: block f = Xa[rows_f]^T Xa[rows_f]; `extra` spare slots.
+        Empty row ranges leave their block untouched (zero=True pre-clears the array)."""
         torch = self.torch
         row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
         F = len(row_ptr) - 1
         pa = Xa.shape[1]
-        G = torch.empty((F + extra, pa, pa), dtype=torch.float64, device=self.device)
+        alloc = torch.zeros if zero else torch.empty
+        G = alloc((F + extra, pa, pa), dtype=torch.float64, device=self.device)
         self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
                                           row_ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), F,
                                           self._ptr(G), self.stream), "slm_gram_blocks")
@@ -241,7 +245,7 @@ class Engine:
         return GZ
 
     # ---- data preparation for a CV search / a plain fit --------------------
-    def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None):
+    def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None, shard=None):
         """Pack the design, build per-fold training Grams + the full Gram.
 
         test_folds: list of index arrays forming a partition of range(n) (the CV
@@ -269,13 +273,22 @@ class Engine:
         Xa = self.pack(X, y, sw, col_perm, row_perm)
         pa = Xa.shape[1]
         F = len(row_ptr) - 1
+        build_ptr = row_ptr
+        if shard is not None and shard.world > 1:
+            # row-sharded build: this rank contributes the Gram of its own rows only
+            r0, r1 = shard.row_range(n)
+            build_ptr = np.clip(row_ptr, r0, r1)
         if F > 1:
-            allG = self.gram_blocks(Xa, row_ptr, extra=1)  # slot F receives the full Gram
+            allG = self.gram_blocks(Xa, build_ptr, extra=1, zero=build_ptr is not row_ptr)
+            if build_ptr is not row_ptr:
+                shard.allreduce_sum_(allG[:F])  # NCCL all-reduce of the partial Gram blocks
             G_train, G_full = allG[:F], allG[F]
             self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
             n_train = (n - np.diff(row_ptr)).astype(np.float64)
         else:
-            allG = self.gram_blocks(Xa, row_ptr)
+            allG = self.gram_blocks(Xa, build_ptr, zero=build_ptr is not row_ptr)
+            if build_ptr is not row_ptr:
+                shard.allreduce_sum_(allG)
             G_full = allG[0]
             G_train = allG[:0]
             n_train = np.zeros(0)
@@ -293,6 +306,10 @@ class Engine:
             self.gram_center(G_full, p)
             if F > 1:
                 self.gram_center(G_train, p)
+        if not bool(self.torch.isfinite(G_full[p + 1]).all()):
+            # column sums / sum(y) / n of the augmented Gram: any NaN or inf in X, y or the
+            # weights ends up here (input validation without a host pass over X)
+            raise ValueError("Input X, y or sample_weight contains NaN or infinity.")
         lam = self.lipschitz(allG, p) * self.LIPSCHITZ_MARGIN
         lam = np.maximum(lam, 1e-300)
         ns = np.concatenate([extra.get("n_obs_train", n_train), [extra.get("n_obs_full", float(n))]])

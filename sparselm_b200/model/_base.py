@@ -210,19 +210,30 @@ def _to_original_order(coef_solver, spec: ProblemSpec):
     return out
 
 
+def _empty_like_grid(s0):
+    """A zero-column PenaltyGrid with the structure of spec s0 (rank owns no column of a fold)."""
+    G = s0.n_groups
+    ad = None
+    if s0.adaptive is not None:
+        a = s0.adaptive
+        z = np.zeros(0)
+        ad = dict(a1=None if a["a1"] is None else z, a2=None if a["a2"] is None else z, alpha=z, gw=s0.gw,
+                  eps=a["eps"], tol=a["tol"], max_iter=a["max_iter"], update_function=a["update_function"])
+    return PenaltyGrid(p=s0.pe, lam1=np.zeros(0), gptr=s0.gptr, W2=None if s0.w2 is None else np.zeros((G, 0)),
+                       D2=None if s0.d2 is None else np.zeros((G, 0)), adaptive=ad)
+
+
 def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, check_every=10,
                 floor_rel=1e-14):
-    """Solve the K problems `specs` (equal structure keys) on every training Gram of
-    `fd` (or on its full Gram when use_full) as one engine batch.
+    """Solve problems (equal structure keys) on every training Gram of `fd` (or on its
+    full Gram when use_full) as one engine batch.  `specs` is either one list (the same
+    K problems on every fold) or a list of per-fold lists (sharded grids).
 
     Returns device tensors in the column order of fd.Xa: coef [F, p, ldz], intercept
     [F, ldz], and numpy [F, ldz] gap / primal / n_iter / status / n_pass.
     """
     torch = engine.torch
-    s0 = specs[0]
     p = fd.p
-    grid = stack_specs(specs)
-    K = grid.K
     if use_full:
         G = fd.G_full[None]
         n_obs = np.array([fd.extra.get("n_obs_full", float(fd.n))])
@@ -230,13 +241,18 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
     else:
         G, n_obs, L = fd.G_train, fd.extra.get("n_obs_train", fd.n_train), fd.L_train
     F = G.shape[0]
+    fold_specs = specs if (len(specs) and isinstance(specs[0], (list, tuple))) else [specs] * F
+    assert len(fold_specs) == F
+    s0 = next(fs[0] for fs in fold_specs if len(fs))
+    grids = [stack_specs(fs) if len(fs) else _empty_like_grid(s0) for fs in fold_specs]
+    Ks = [g.K for g in grids]
     if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
         idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))
         Gs = engine.gram_gather(G, p, idx_dev, s0.pe)
         L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / np.asarray(n_obs, dtype=float)
     else:
         Gs = G
-    res = engine.solve(Gs, s0.pe, n_obs, L, [grid] * F, tol=tol, max_iter=max_iter,
+    res = engine.solve(Gs, s0.pe, n_obs, L, grids, tol=tol, max_iter=max_iter,
                        check_every=check_every, floor_rel=floor_rel)
     B = res["B"]
     ldz = res["ldz"]
@@ -245,11 +261,11 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
         order = np.argsort(idx, kind="stable").astype(np.int32)
         inv_ptr = np.concatenate([[0], np.cumsum(np.bincount(idx, minlength=p))]).astype(np.int32)
         ip, ii = engine.to_device(inv_ptr), engine.to_device(order)
-        coef = torch.stack([engine.fold_back(B[f], ip, ii, p, K) for f in range(F)])
+        coef = torch.stack([engine.fold_back(B[f], ip, ii, p, Ks[f]) for f in range(F)])
     else:
         coef = B
     if fd.fit_intercept:
-        icpt = torch.stack([engine.intercepts(G[f], p, coef[f], K) for f in range(F)])
+        icpt = torch.stack([engine.intercepts(G[f], p, coef[f], Ks[f]) for f in range(F)])
     else:
         icpt = torch.zeros((F, ldz), dtype=torch.float64, device=engine.device)
     res.update(coef=coef, intercept=icpt)

@@ -78,7 +78,12 @@ class GroupLasso(Lasso):
 
     # -- validation (reference _lasso.py:208-222) --
     def _n_groups(self, n_features):
-        return n_features if self.groups is None else len(np.unique(self.groups))
+        if self.groups is None:
+            return n_features
+        cache = self.__dict__.get("_group_cache")
+        if cache is not None and cache[0] is self.groups:
+            return cache[4]
+        return len(np.unique(self.groups))
 
     def _validate_hyperparams(self, X, y):
         super()._validate_hyperparams(X, y)
@@ -100,14 +105,22 @@ class GroupLasso(Lasso):
             )
 
     def _group_spec(self, n_features):
-        """(col_perm, gptr, gw) for the current groups."""
-        groups = np.arange(n_features) if self.groups is None else np.asarray(self.groups)
-        col_perm, gptr, n_groups = group_structure(groups, n_features)
+        """(col_perm, gptr, gw) for the current groups (memoised on the identity of the
+        `groups` object: a grid search re-describes the same structure per candidate)."""
+        cache = self.__dict__.get("_group_cache")
+        if cache is None or cache[0] is not self.groups or cache[1] != n_features:
+            groups = np.arange(n_features) if self.groups is None else np.asarray(self.groups)
+            col_perm, gptr, n_groups = group_structure(groups, n_features)
+            cache = (self.groups, n_features, col_perm, gptr, n_groups, _arr_key(self.groups))
+            self.__dict__["_group_cache"] = cache
+        _, _, col_perm, gptr, n_groups, _ = cache
         gw = np.ones(n_groups) if self.group_weights is None else np.asarray(self.group_weights, dtype=float)
         return col_perm, gptr, gw
 
     def _structure_key(self, name, n_features):
-        return (name, n_features, bool(self.fit_intercept), bool(self.standardize), _arr_key(self.groups),
+        cache = self.__dict__.get("_group_cache")
+        gkey = cache[5] if (cache is not None and cache[0] is self.groups) else _arr_key(self.groups)
+        return (name, n_features, bool(self.fit_intercept), bool(self.standardize), gkey,
                 _arr_key(self.group_weights))
 
     def _problem_spec(self, n_features):

@@ -92,12 +92,14 @@ def _metric(scoring, sse, sae, n_rows, sst):
 
 
 def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_train_score=False, cache=None,
-               cache_key=None):
+               cache_key=None, shard=None):
     """Solve every (candidate, fold) problem as device batches and score them.
 
     X: (n, p) numpy array or torch tensor (host, pinned or already on the device);
     y: (n,) numpy array; test_folds: list of index arrays partitioning the rows;
     ests/specs: one configured estimator and its ProblemSpec per candidate.
+    shard: optional parallel.GridShard -- this rank builds the Gram of its rows, solves
+    its share of the (fold, candidate) grid, and the score tables are summed over ranks.
     Returns test_scores [n_cand, n_splits] (+ train scores, timings, solver info and
     the device-resident FoldData objects keyed by (fit_intercept, column order)).
     """
@@ -130,45 +132,59 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             if ck is not None and ck in cache:
                 fds[fkey] = cache[ck]
             else:
-                fds[fkey] = engine.prepare(X, yv, test_folds, e0.fit_intercept, None, col_perm=s0.col_perm)
+                fds[fkey] = engine.prepare(X, yv, test_folds, e0.fit_intercept, None, col_perm=s0.col_perm,
+                                           shard=shard)
                 if ck is not None:
                     cache[ck] = fds[fkey]
         fd = fds[fkey]
         t0 = time.perf_counter()
-        out = solve_specs(engine, fd, [specs[i] for i in idxs], **opts)
+        idxs = np.asarray(idxs)
+        if shard is not None and shard.world > 1:
+            mine = shard.my_columns(n_splits, len(idxs))  # per fold: positions in idxs this rank solves
+        else:
+            mine = [np.arange(len(idxs))] * n_splits
+        out = solve_specs(engine, fd, [[specs[idxs[k]] for k in mine[f]] for f in range(n_splits)], **opts)
         t1 = time.perf_counter()
         K = len(idxs)
         icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
-        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], K, icpt(f))
+        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f))
                   for f in range(n_splits)]
         sc = engine.torch.stack(sc_dev).cpu().numpy()  # one D2H for all folds
-        sse, sae = sc[:, 0, :K], sc[:, 1, :K]
         if train_scores is not None:
-            tsse = np.zeros((n_splits, K))
-            tsae = np.zeros((n_splits, K))
+            tsc = np.zeros_like(sc)
             for f in range(n_splits):
                 for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
-                    if r1 > r0:
-                        t = engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], K, icpt(f)).cpu().numpy()
-                        tsse[f] += t[0, :K]
-                        tsae[f] += t[1, :K]
+                    if r1 > r0 and len(mine[f]):
+                        tsc[f] += engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], len(mine[f]),
+                                                  icpt(f)).cpu().numpy()
         t2 = time.perf_counter()
         for f in range(n_splits):
             nt = len(test_folds[f])
-            test_scores[idxs, f] = _metric(scoring, sse[f], sae[f], nt, sst_test[f])
+            kf = len(mine[f])
+            ci = idxs[mine[f]]
+            test_scores[ci, f] = _metric(scoring, sc[f, 0, :kf], sc[f, 1, :kf], nt, sst_test[f])
             if train_scores is not None:
                 ntr = n - nt
                 s_tr = tot_sum - float(yv[test_folds[f]].sum())
                 q_tr = tot_sq - float((yv[test_folds[f]] ** 2).sum())
-                train_scores[idxs, f] = _metric(scoring, tsse[f], tsae[f], ntr, q_tr - s_tr * s_tr / ntr)
-            info["n_iter"][idxs, f] = out["n_iter"][f, :K]
-            info["status"][idxs, f] = out["status"][f, :K]
-            info["gap"][idxs, f] = out["gap"][f, :K]
-            info["n_pass"][idxs, f] = out["n_pass"][f, :K]
+                train_scores[ci, f] = _metric(scoring, tsc[f, 0, :kf], tsc[f, 1, :kf], ntr, q_tr - s_tr * s_tr / ntr)
+            info["n_iter"][ci, f] = out["n_iter"][f, :kf]
+            info["status"][ci, f] = out["status"][f, :kf]
+            info["gap"][ci, f] = out["gap"][f, :kf]
+            info["n_pass"][ci, f] = out["n_pass"][f, :kf]
         fit_time[idxs] = (t1 - t0) / (K * n_splits)
         score_time[idxs] = (t2 - t1) / (K * n_splits)
         n_unconverged += int(out["n_unconverged"])
         iters_run += int(out["iters_run"])
+    if shard is not None and shard.world > 1:
+        # the only data-path exchange of the sharded grid: sum the zero-padded tables
+        dev = engine.device
+        test_scores = shard.allreduce_sum_numpy(np.nan_to_num(test_scores, nan=0.0), dev)
+        if train_scores is not None:
+            train_scores = shard.allreduce_sum_numpy(np.nan_to_num(train_scores, nan=0.0), dev)
+        for k in list(info):
+            info[k] = shard.allreduce_sum_numpy(info[k].astype(np.float64), dev).astype(info[k].dtype)
+        n_unconverged = int(shard.allreduce_sum_numpy(np.array([float(n_unconverged)]), dev)[0])
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
                 info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run)
 
@@ -228,7 +244,9 @@ class GridSearchCV(_SkGridSearchCV):
         if self.opt_selection_method not in ("max_score", "one_std_score"):
             raise NotImplementedError(f"Method {self.opt_selection_method} not implemented!")
         try:
-            Xv, yv = check_X_y(X, y, dtype=np.float64, y_numeric=True, ensure_min_samples=2)
+            # finiteness is checked on the device (engine.prepare) instead of a host pass over X
+            Xv, yv = check_X_y(X, y, dtype=np.float64, y_numeric=True, ensure_min_samples=2,
+                               ensure_all_finite=False)
         except Exception:
             return None
         n, p = Xv.shape
@@ -242,11 +260,20 @@ class GridSearchCV(_SkGridSearchCV):
             return None
         ests, specs = [], []
         try:
-            for c in candidates:
-                e = clone(est).set_params(**c)
-                e._validate_hyperparams(Xv, yv)
-                ests.append(e)
-                specs.append(e._problem_spec(p))
+            # one working estimator re-parametrised per candidate (cloning 100 estimators and
+            # re-deriving their group structure costs more host time than the GPU solve)
+            work = clone(est)
+            import warnings as _w
+            from types import SimpleNamespace
+
+            for ci, c in enumerate(candidates):
+                work.set_params(**c)
+                with _w.catch_warnings():
+                    if ci > 0:  # structural warnings (e.g. groups=None) are emitted once
+                        _w.simplefilter("ignore", UserWarning)
+                    work._validate_hyperparams(Xv, yv)
+                ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
+                specs.append(work._problem_spec(p))
         except NotImplementedError:
             raise
         except Exception:
@@ -265,7 +292,8 @@ class GridSearchCV(_SkGridSearchCV):
         cache = getattr(self, "_fd_cache", None)
         cache_key = None if cache is None else (id(plan["X"]), id(plan["y"]))
         res = batched_cv(engine, Xv, yv, test_folds, ests, specs, opts, scoring,
-                         return_train_score=self.return_train_score, cache=cache, cache_key=cache_key)
+                         return_train_score=self.return_train_score, cache=cache, cache_key=cache_key,
+                         shard=getattr(self, "_shard", None))
         test_scores, train_scores = res["test_scores"], res["train_scores"]
         fit_time, score_time, info, fds = res["fit_time"], res["score_time"], res["info"], res["fds"]
         if res["n_unconverged"]:

@@ -109,14 +109,14 @@ def test_gram_apply_matches_matmul(engine, p, Ks):
 def test_lipschitz_is_tight_lower_bound(engine):
     torch = _torch()
     rng = _rng(3)
-    for n, p in [(400, 100), (3000, 700), (60, 60)]:
+    for n, p in [(400, 100), (3000, 700), (60, 60), (6000, 1500), (500, 1000)]:
         X = rng.standard_normal((n, p))
         Xa = engine.pack(X, np.zeros(n))
         G = engine.gram_blocks(Xa, np.array([0, n]))
         lam = engine.lipschitz(G, p)[0]
         true = np.linalg.eigvalsh(X.T @ X)[-1]
         assert lam <= true * (1 + 1e-12)
-        assert lam * engine.LIPSCHITZ_MARGIN >= true, (lam, true)
+        assert lam * engine.LIPSCHITZ_MARGIN >= true * 1.01, (lam, true)
 
 
 # --------------------------------------------------------------------------- #
