@@ -847,8 +847,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.tmom[1] = tmom + cols;
     sp.part = part;
     sp.flag = flag;
-    sp.gpt = std::max(1, (Gn + SG * kMaxChunks - 1) / (SG * kMaxChunks));
-    sp.n_chunks = (Gn + SG * sp.gpt - 1) / (SG * sp.gpt);
+    const bool grouped = bt->gptr_dev != nullptr;
+    const int gpb = grouped ? GPB : SG;  // groups per block iteration
+    sp.gpt = std::max(1, (Gn + gpb * kMaxChunks - 1) / (gpb * kMaxChunks));
+    sp.n_chunks = (Gn + gpb * sp.gpt - 1) / (gpb * sp.gpt);
     sp.gap = bt->gap_dev;
     sp.primal = bt->primal_dev;
     sp.n_iter = bt->n_iter_dev;
@@ -902,7 +904,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
             {
                 FamTimer tm(ctx, FAM_GAP, s, 0.0);
-                gap_partial_kernel<<<cgrid, ST, 0, s>>>(sp, par, 0);
+                if (grouped)
+                    gap_partial_kernel<true><<<cgrid, ST, 0, s>>>(sp, par, 0);
+                else
+                    gap_partial_kernel<false><<<cgrid, ST, 0, s>>>(sp, par, 0);
                 gap_final_kernel<<<fgrid, 128, 0, s>>>(sp, it, 0);
             }
             LAUNCH_OK("gap kernels");
@@ -922,7 +927,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);
-            prox_main_kernel<<<cgrid, ST, 0, s>>>(sp, par);
+            if (grouped)
+                prox_main_kernel<true><<<cgrid, ST, 0, s>>>(sp, par);
+            else
+                prox_main_kernel<false><<<cgrid, ST, 0, s>>>(sp, par);
             prox_momentum_kernel<<<mgrid, ST, 0, s>>>(sp, par);
         }
         LAUNCH_OK("prox kernels");
@@ -965,7 +973,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
     {
         FamTimer tm(ctx, FAM_GAP, s, 0.0);
-        gap_partial_kernel<<<cgrid, ST, 0, s>>>(fin, 0, 1);
+        if (grouped)
+            gap_partial_kernel<true><<<cgrid, ST, 0, s>>>(fin, 0, 1);
+        else
+            gap_partial_kernel<false><<<cgrid, ST, 0, s>>>(fin, 0, 1);
         gap_final_kernel<<<fgrid, 128, 0, s>>>(fin, it, 1);
     }
     LAUNCH_OK("gap kernels(final)");

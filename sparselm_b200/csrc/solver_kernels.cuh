@@ -82,8 +82,35 @@ __device__ __forceinline__ double lanes_max(double v, double (*red)[SC], int gl,
     return r;
 }
 
+// Group lanes.  GROUPED: a warp owns one group for the block's 8 columns; lane = c + 8*sub,
+// the 4 sub-lanes stride over the group's rows and combine with two xor-shuffles (same
+// value on every sub-lane, fixed order).  Singleton groups (Lasso): every lane is a row.
+constexpr int SUB = 4;             // sub-lanes per group (GROUPED)
+constexpr int GPB = SG / SUB;      // groups per block iteration (GROUPED)
+
+// qmask names the four lanes {c, c+8, c+16, c+24} of one (group, column) quartet: the
+// quartet's lanes hold identical reduced values, hence identical control flow, while
+// different quartets of a warp are free to diverge (e.g. in the Newton iteration).
+__device__ __forceinline__ double sub_sum(unsigned qmask, double v) {
+    v += __shfl_xor_sync(qmask, v, SC);
+    v += __shfl_xor_sync(qmask, v, 2 * SC);
+    return v;
+}
+__device__ __forceinline__ double sub_max(unsigned qmask, double v) {
+    v = fmax(v, __shfl_xor_sync(qmask, v, SC));
+    v = fmax(v, __shfl_xor_sync(qmask, v, 2 * SC));
+    return v;
+}
+__device__ __forceinline__ bool sub_any(unsigned qmask, bool v) {
+    int x = v ? 1 : 0;
+    x |= __shfl_xor_sync(qmask, x, SC);
+    x |= __shfl_xor_sync(qmask, x, 2 * SC);
+    return x != 0;
+}
+
 // ---- K6a: GB recurrence, gradient step, soft-threshold, group shrink, ridge -----
 // writes T = beta_{k+1} and the per-chunk restart dot  sum (z - b+)(b+ - b)
+template <bool GROUPED>
 __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ SolveDev sp, int par) {
     const int f = blockIdx.z, chunk = blockIdx.y;
     const int Kf = sp.K[f];
@@ -103,35 +130,47 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
     const double son = step / n;
     const long long ldz = sp.ldz;
     const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;  // original column (penalty arrays)
-    const long long sbase = (long long)f * sp.p * ldz + k;
-    const long long wbase = (long long)f * sp.p * ldz + ko;
-    const long long gbase = (long long)f * sp.Gn * ldz + ko;
+    // inactive lanes of a partly active block read column 0 of their fold (always valid
+    // memory) so that whole warps can stay in the shuffles; they never write
+    const int kk = active ? k : 0;
+    const long long sbase = (long long)f * sp.p * ldz + kk;
+    const long long wbase = (long long)f * sp.p * ldz + (active ? ko : 0);
+    const long long gbase = (long long)f * sp.Gn * ldz + (active ? ko : 0);
     const double lam1 = (active && sp.lam1) ? sp.lam1[(long long)f * ldz + ko] : 0.0;
+    const int sub = GROUPED ? (gl % SUB) : 0;
+    const int gsl = GROUPED ? (gl / SUB) : gl;       // group slot of this lane
+    const int gstep = GROUPED ? GPB : SG;            // groups per block iteration
+    const int rstep = GROUPED ? SUB : 1;
+    const unsigned qmask = 0x01010101u << c;
 
     double dot = 0.0;
-    if (active) {
-        for (int i = 0; i < sp.gpt; ++i) {
-            const int g = (chunk * sp.gpt + i) * SG + gl;
-            if (g >= sp.Gn) break;
-            const int ja = sp.gptr ? sp.gptr[g] : g;
-            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
-            double ss = 0.0;
-            for (int j = ja; j < jb; ++j) {
-                const long long e = sbase + (long long)j * ldz;
-                const double gz = sp.GZ[e];
-                sp.GB[e] = (gz + theta * sp.GB[e]) * inv1pt;
-                const double v = sp.Z[e] - son * (gz - cvec[j]);
-                const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
-                const double u = softt(v, step * w1);
+    for (int i = 0; i < sp.gpt; ++i) {
+        const int g = (chunk * sp.gpt + i) * gstep + gsl;
+        if (g >= sp.Gn) break;  // uniform over the sub-lanes of a group
+        const int ja = sp.gptr ? sp.gptr[g] : g;
+        const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+        double ss = 0.0;
+        for (int j = ja + sub; j < jb; j += rstep) {
+            const long long e = sbase + (long long)j * ldz;
+            const double gz = sp.GZ[e];
+            const double gb = (gz + theta * sp.GB[e]) * inv1pt;
+            const double v = sp.Z[e] - son * (gz - cvec[j]);
+            const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
+            const double u = softt(v, step * w1);
+            if (active) {
+                sp.GB[e] = gb;
                 sp.T[e] = u;  // stash; scaled below
-                ss += u * u;
             }
-            const double nrm = sqrt(ss);
-            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
-            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
-            double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
-            scale = scale / (1.0 + step * d2);
-            for (int j = ja; j < jb; ++j) {
+            ss += u * u;
+        }
+        if (GROUPED) ss = sub_sum(qmask, ss);
+        const double nrm = sqrt(ss);
+        const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+        const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+        double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
+        scale = scale / (1.0 + step * d2);
+        if (active) {
+            for (int j = ja + sub; j < jb; j += rstep) {
                 const long long e = sbase + (long long)j * ldz;
                 const double bn = scale * sp.T[e];
                 sp.T[e] = bn;
@@ -139,7 +178,7 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
             }
         }
     }
-    dot = lanes_sum(dot, red, gl, c);
+    dot = lanes_sum(active ? dot : 0.0, red, gl, c);
     if (active && gl == 0)
         sp.part[(((long long)f * sp.n_chunks + chunk) * NQ + 0) * ldz + k] = dot;
 }
@@ -189,20 +228,26 @@ __global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant
 
 // dual norm of one group: smallest nu with || S(|g|, nu*w1) ||_2 <= nu*w2, by a
 // monotone Newton iteration from a lower bound (psi is convex and decreasing),
-// finished on the feasible side.  gfun(j) returns |g_j|, wfun(j) returns w1_j.
-template <typename GF, typename WF>
-__device__ __forceinline__ double group_dual_newton(int ja, int jb, double w2, double lo, double hi, GF gfun,
-                                                    WF wfun) {
+// finished on the feasible side.  gfun(j) returns |g_j|, wfun(j) returns w1_j; rows
+// ja+sub, ja+sub+rstep, ... belong to this lane and partial sums are combined over the
+// sub-lanes, so all sub-lanes of a group take identical decisions.
+template <bool GROUPED, typename GF, typename WF>
+__device__ __forceinline__ double group_dual_newton(unsigned qmask, int ja, int jb, int sub, int rstep, double w2,
+                                                    double lo, double hi, GF gfun, WF wfun) {
     double nu = lo;
     for (int it = 0; it < 50; ++it) {
         double s2 = 0.0, sw = 0.0;
-        for (int j = ja; j < jb; ++j) {
+        for (int j = ja + sub; j < jb; j += rstep) {
             const double w = wfun(j);
             const double u = gfun(j) - nu * w;
             if (u > 0.0) {
                 s2 += u * u;
                 sw += w * u;
             }
+        }
+        if (GROUPED) {
+            s2 = sub_sum(qmask, s2);
+            sw = sub_sum(qmask, sw);
         }
         const double s = sqrt(s2);
         const double psi = s - nu * w2;
@@ -217,10 +262,11 @@ __device__ __forceinline__ double group_dual_newton(int ja, int jb, double w2, d
     for (int t = 0; t < 12; ++t) {
         const double cand = nu * (1.0 + bump);
         double s2 = 0.0;
-        for (int j = ja; j < jb; ++j) {
+        for (int j = ja + sub; j < jb; j += rstep) {
             const double u = gfun(j) - cand * wfun(j);
             if (u > 0.0) s2 += u * u;
         }
+        if (GROUPED) s2 = sub_sum(qmask, s2);
         if (sqrt(s2) <= cand * w2) return fmin(cand, hi);
         bump *= 8.0;
     }
@@ -230,6 +276,7 @@ __device__ __forceinline__ double group_dual_newton(int ja, int jb, double w2, d
 // ---- K7a: per-chunk pieces of the duality gap of B_k ------------------------------
 // G B_k comes from the momentum recurrence (GZ, GB_{k-1}, theta) or, in final mode
 // (Z == B), from GZ directly.
+template <bool GROUPED>
 __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__ SolveDev sp, int par,
                                                          int final_mode) {
     const int f = blockIdx.z, chunk = blockIdx.y;
@@ -253,10 +300,16 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
     const double n = sp.n_obs[f];
     const double inv_n = 1.0 / n;
     const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;
-    const long long sbase = (long long)f * sp.p * ldz + k;
-    const long long wbase = (long long)f * sp.p * ldz + ko;
-    const long long gbase = (long long)f * sp.Gn * ldz + ko;
+    const int kk = active ? k : 0;  // inactive lanes shadow column 0 (reads only)
+    const long long sbase = (long long)f * sp.p * ldz + kk;
+    const long long wbase = (long long)f * sp.p * ldz + (active ? ko : 0);
+    const long long gbase = (long long)f * sp.Gn * ldz + (active ? ko : 0);
     const double lam1 = (active && sp.lam1) ? sp.lam1[(long long)f * ldz + ko] : 0.0;
+    const int sub = GROUPED ? (gl % SUB) : 0;
+    const int gsl = GROUPED ? (gl / SUB) : gl;
+    const int gstep = GROUPED ? GPB : SG;
+    const int rstep = GROUPED ? SUB : 1;
+    const unsigned qmask = 0x01010101u << c;
 
     auto gb_at = [&](long long e) {
         const double gz = sp.GZ[e];
@@ -264,96 +317,109 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
     };
 
     double cb = 0.0, bgb = 0.0, pen = 0.0, ridge = 0.0, lbmax = 0.0;
-    if (active) {
-        for (int i = 0; i < sp.gpt; ++i) {
-            const int g = (chunk * sp.gpt + i) * SG + gl;
-            if (g >= sp.Gn) break;
-            const int ja = sp.gptr ? sp.gptr[g] : g;
-            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
-            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
-            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
-            double ss = 0.0, gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
-            bool anyinf = false;
-            for (int j = ja; j < jb; ++j) {
-                const long long e = sbase + (long long)j * ldz;
-                const double gb = gb_at(e);
-                const double b = sp.B[e];
-                const double cj = cvec[j];
-                const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
-                cb += cj * b;
-                bgb += b * gb;
-                pen += w1 * fabs(b);
-                ss += b * b;
-                const double gj = fabs((cj - gb) * inv_n - d2 * b);
-                gg2 += gj * gj;
-                ww2 += w1 * w1;
-                if (gj > 0.0) {
-                    if (w1 > 0.0)
-                        ratio = fmax(ratio, gj / w1);
-                    else
-                        anyinf = true;
-                }
+    for (int i = 0; i < sp.gpt; ++i) {
+        const int g = (chunk * sp.gpt + i) * gstep + gsl;
+        if (g >= sp.Gn) break;
+        const int ja = sp.gptr ? sp.gptr[g] : g;
+        const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+        const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+        const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+        double ss = 0.0, gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
+        bool anyinf = false;
+        for (int j = ja + sub; j < jb; j += rstep) {
+            const long long e = sbase + (long long)j * ldz;
+            const double gb = gb_at(e);
+            const double b = sp.B[e];
+            const double cj = cvec[j];
+            const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
+            cb += cj * b;
+            bgb += b * gb;
+            pen += w1 * fabs(b);
+            ss += b * b;
+            const double gj = fabs((cj - gb) * inv_n - d2 * b);
+            gg2 += gj * gj;
+            ww2 += w1 * w1;
+            if (gj > 0.0) {
+                if (w1 > 0.0)
+                    ratio = fmax(ratio, gj / w1);
+                else
+                    anyinf = true;
             }
+        }
+        if (GROUPED) {
+            ss = sub_sum(qmask, ss);
+            gg2 = sub_sum(qmask, gg2);
+            ww2 = sub_sum(qmask, ww2);
+            ratio = sub_max(qmask, ratio);
+            anyinf = sub_any(qmask, anyinf);
+        }
+        if (sub == 0) {  // per-group terms are counted once
             pen += w2 * sqrt(ss);
             ridge += d2 * ss;
-            // lower bound of this group's dual norm (exact when a closed form exists)
-            double lb;
-            const double gn = sqrt(gg2);
-            if (gg2 == 0.0)
-                lb = 0.0;
-            else if (w2 <= 0.0)
-                lb = anyinf ? INFINITY : ratio;
-            else if (ww2 == 0.0)
-                lb = gn / w2;
-            else
-                lb = gn / (w2 + sqrt(ww2));
-            lbmax = fmax(lbmax, lb);
         }
+        // lower bound of this group's dual norm (exact when a closed form exists)
+        double lb;
+        const double gn = sqrt(gg2);
+        if (gg2 == 0.0)
+            lb = 0.0;
+        else if (w2 <= 0.0)
+            lb = anyinf ? INFINITY : ratio;
+        else if (ww2 == 0.0)
+            lb = gn / w2;
+        else
+            lb = gn / (w2 + sqrt(ww2));
+        lbmax = fmax(lbmax, lb);
     }
+    if (!active) lbmax = 0.0;
     // block-wide threshold: only groups whose upper bound exceeds it can hold the max
     const double thr = lanes_max(lbmax, red, gl, c);
     double omega = lbmax;
-    if (active) {
-        for (int i = 0; i < sp.gpt; ++i) {
-            const int g = (chunk * sp.gpt + i) * SG + gl;
-            if (g >= sp.Gn) break;
-            const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
-            if (w2 <= 0.0) continue;  // closed form already in lbmax
-            const int ja = sp.gptr ? sp.gptr[g] : g;
-            const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
-            const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
-            auto gfun = [&](int j) {
-                const long long e = sbase + (long long)j * ldz;
-                return fabs((cvec[j] - gb_at(e)) * inv_n - d2 * sp.B[e]);
-            };
-            auto wfun = [&](int j) { return sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1; };
-            double gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
-            bool anyinf = false;
-            for (int j = ja; j < jb; ++j) {
-                const double gj = gfun(j), w1 = wfun(j);
-                gg2 += gj * gj;
-                ww2 += w1 * w1;
-                if (gj > 0.0) {
-                    if (w1 > 0.0)
-                        ratio = fmax(ratio, gj / w1);
-                    else
-                        anyinf = true;
-                }
+    for (int i = 0; i < sp.gpt; ++i) {
+        const int g = (chunk * sp.gpt + i) * gstep + gsl;
+        if (g >= sp.Gn) break;
+        const double w2 = sp.W2 ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+        const int ja = sp.gptr ? sp.gptr[g] : g;
+        const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+        const double d2 = sp.D2 ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+        auto gfun = [&](int j) {
+            const long long e = sbase + (long long)j * ldz;
+            return fabs((cvec[j] - gb_at(e)) * inv_n - d2 * sp.B[e]);
+        };
+        auto wfun = [&](int j) { return sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1; };
+        double gg2 = 0.0, ratio = 0.0, ww2 = 0.0;
+        bool anyinf = false;
+        for (int j = ja + sub; j < jb; j += rstep) {
+            const double gj = gfun(j), w1 = wfun(j);
+            gg2 += gj * gj;
+            ww2 += w1 * w1;
+            if (gj > 0.0) {
+                if (w1 > 0.0)
+                    ratio = fmax(ratio, gj / w1);
+                else
+                    anyinf = true;
             }
-            if (gg2 == 0.0 || ww2 == 0.0) continue;  // closed form
-            const double gn = sqrt(gg2);
-            double hi = gn / w2;
-            if (!anyinf && ratio < hi) hi = ratio;
-            if (!(hi > thr)) continue;
+        }
+        if (GROUPED) {
+            gg2 = sub_sum(qmask, gg2);
+            ww2 = sub_sum(qmask, ww2);
+            ratio = sub_max(qmask, ratio);
+            anyinf = sub_any(qmask, anyinf);
+        }
+        const double gn = sqrt(gg2);
+        double hi = w2 > 0.0 ? gn / w2 : 0.0;
+        if (!anyinf && ratio < hi) hi = ratio;
+        // identical on the four sub-lanes of the quartet (all inputs are quartet-reduced)
+        const bool refine = active && w2 > 0.0 && gg2 > 0.0 && ww2 > 0.0 && hi > thr;
+        if (refine) {
             const double lo = gn / (w2 + sqrt(ww2));
-            omega = fmax(omega, group_dual_newton(ja, jb, w2, lo, hi, gfun, wfun));
+            omega = fmax(omega, group_dual_newton<GROUPED>(qmask, ja, jb, sub, rstep, w2, lo, hi, gfun, wfun));
         }
     }
-    cb = lanes_sum(cb, red, gl, c);
-    bgb = lanes_sum(bgb, red, gl, c);
-    pen = lanes_sum(pen, red, gl, c);
-    ridge = lanes_sum(ridge, red, gl, c);
-    omega = lanes_max(omega, red, gl, c);
+    cb = lanes_sum(active ? cb : 0.0, red, gl, c);
+    bgb = lanes_sum(active ? bgb : 0.0, red, gl, c);
+    pen = lanes_sum(active ? pen : 0.0, red, gl, c);
+    ridge = lanes_sum(active ? ridge : 0.0, red, gl, c);
+    omega = lanes_max(active ? omega : 0.0, red, gl, c);
     if (active && gl == 0) {
         double* dst = sp.part + (((long long)f * sp.n_chunks + chunk) * NQ) * ldz + k;
         dst[0 * ldz] = cb;

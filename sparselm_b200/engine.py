@@ -65,15 +65,48 @@ class FoldData:
     G_train: object            # torch [F, pa, pa] training Grams (centred if fit_intercept)
     G_full: object             # torch [pa, pa] Gram of all rows (centred if fit_intercept)
     n_train: np.ndarray        # (F,)
-    L_train: np.ndarray        # (F,) Lipschitz constants lambda_max(G)/n with margin
-    L_full: float
     fit_intercept: bool
     row_perm: np.ndarray | None = None
     extra: dict = field(default_factory=dict)
+    _lam: dict = field(default_factory=dict)   # fold index (or "full") -> lambda_max estimate
 
     @property
     def n_folds(self):
         return len(self.n_train)
+
+    def n_obs(self, which):
+        """n of the 1/(2n) data term: rows of the training set (sum of weights if weighted)."""
+        if which == "full":
+            return float(self.extra.get("n_obs_full", float(self.n)))
+        return float(self.extra.get("n_obs_train", self.n_train)[which])
+
+    def lipschitz(self, engine, which):
+        """L >= lambda_max(G)/n for the training Gram of fold `which` (or "full"), computed on
+        first use (a sharded rank only pays for the Grams it iterates on)."""
+        keys = list(which) if isinstance(which, (list, tuple, np.ndarray)) else [which]
+        missing = [k for k in keys if k not in self._lam]
+        if missing:
+            ints = sorted(k for k in missing if k != "full")
+            # contiguous runs of folds go through one batched power iteration
+            runs, start = [], None
+            for i, k in enumerate(ints):
+                if start is None:
+                    start = prev = k
+                elif k == prev + 1:
+                    prev = k
+                else:
+                    runs.append((start, prev))
+                    start = prev = k
+            if start is not None:
+                runs.append((start, prev))
+            for a, b in runs:
+                lam = engine.lipschitz(self.G_train[a:b + 1], self.p)
+                for j, k in enumerate(range(a, b + 1)):
+                    self._lam[k] = float(lam[j])
+            if "full" in missing:
+                self._lam["full"] = float(engine.lipschitz(self.G_full[None], self.p)[0])
+        out = np.array([max(self._lam[k], 1e-300) * engine.LIPSCHITZ_MARGIN / self.n_obs(k) for k in keys])
+        return out if isinstance(which, (list, tuple, np.ndarray)) else float(out[0])
 
 
 class Engine:
@@ -310,13 +343,8 @@ class Engine:
             # column sums / sum(y) / n of the augmented Gram: any NaN or inf in X, y or the
             # weights ends up here (input validation without a host pass over X)
             raise ValueError("Input X, y or sample_weight contains NaN or infinity.")
-        lam = self.lipschitz(allG, p) * self.LIPSCHITZ_MARGIN
-        lam = np.maximum(lam, 1e-300)
-        ns = np.concatenate([extra.get("n_obs_train", n_train), [extra.get("n_obs_full", float(n))]])
-        L = lam / ns
         return FoldData(n=n, p=p, pa=pa, Xa=Xa, row_ptr=row_ptr, G_train=G_train, G_full=G_full,
-                        n_train=n_train, L_train=L[:-1], L_full=float(L[-1]),
-                        fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra)
+                        n_train=n_train, fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra)
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,

@@ -234,24 +234,24 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
     """
     torch = engine.torch
     p = fd.p
-    if use_full:
-        G = fd.G_full[None]
-        n_obs = np.array([fd.extra.get("n_obs_full", float(fd.n))])
-        L = np.array([fd.L_full])
-    else:
-        G, n_obs, L = fd.G_train, fd.extra.get("n_obs_train", fd.n_train), fd.L_train
+    G = fd.G_full[None] if use_full else fd.G_train
     F = G.shape[0]
+    keys = ["full"] if use_full else list(range(F))
+    n_obs = np.array([fd.n_obs(k) for k in keys])
     fold_specs = specs if (len(specs) and isinstance(specs[0], (list, tuple))) else [specs] * F
     assert len(fold_specs) == F
     s0 = next(fs[0] for fs in fold_specs if len(fs))
     grids = [stack_specs(fs) if len(fs) else _empty_like_grid(s0) for fs in fold_specs]
     Ks = [g.K for g in grids]
+    used = [i for i in range(F) if Ks[i] > 0]
+    L = np.ones(F)
     if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
         idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))
         Gs = engine.gram_gather(G, p, idx_dev, s0.pe)
-        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / np.asarray(n_obs, dtype=float)
+        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / n_obs
     else:
         Gs = G
+        L[used] = fd.lipschitz(engine, [keys[i] for i in used])
     res = engine.solve(Gs, s0.pe, n_obs, L, grids, tol=tol, max_iter=max_iter,
                        check_every=check_every, floor_rel=floor_rel)
     B = res["B"]

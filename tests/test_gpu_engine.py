@@ -170,7 +170,7 @@ def test_solve_matches_oracle(engine, kind):
     alphas = amax * np.logspace(0.1, -3, 13)
     grid = _grid(kind, p, gptr, alphas, rng)
     fd = engine.prepare(X, y)
-    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    res = engine.solve(fd.G_full[None], p, [n], [fd.lipschitz(engine, "full")], [grid], tol=1e-12)
     B = res["B"][0].cpu().numpy()
     assert (res["status"][0, : grid.K] == 0).all(), res["status"]
     for k in range(grid.K):
@@ -197,7 +197,7 @@ def test_solve_multi_fold_batch_and_model_iterations(engine):
     amax = np.abs(X.T @ y).max() / n
     alphas = amax * np.logspace(0, -2.5, 20)
     grid = _grid("sgl", p, gptr, alphas, rng)
-    res = engine.solve(fd.G_train, p, fd.n_train, fd.L_train, [grid] * 5, tol=1e-11)
+    res = engine.solve(fd.G_train, p, fd.n_train, fd.lipschitz(engine, list(range(5))), [grid] * 5, tol=1e-11)
     B = res["B"].cpu().numpy()
     assert (res["status"][:, :20] == 0).all()
     for f in range(5):
@@ -208,7 +208,7 @@ def test_solve_multi_fold_batch_and_model_iterations(engine):
         got = fd.G_train[f].cpu().numpy()
         np.testing.assert_allclose(got[:p, :p], G, rtol=0, atol=1e-10 * np.abs(G).max())
         pb = M.BatchProblem(G, Xt.T @ yt, yt @ yt, len(tr), gptr, np.tile(grid.lam1, (p, 1)), grid.W2,
-                            np.zeros_like(grid.W2), L=fd.L_train[f])
+                            np.zeros_like(grid.W2), L=fd.lipschitz(engine, f))
         Bm, info = M.solve(pb, tol=1e-11)
         # same algorithm => same iteration counts (up to reduction-order ties) and same answer
         assert np.abs(B[f][:, :20] - Bm).max() <= 1e-8 * np.abs(Bm).max()
@@ -232,7 +232,7 @@ def test_adaptive_passes_match_oracle(engine):
     # AdaptiveLasso
     grid = PenaltyGrid(p=p, lam1=alphas, adaptive=dict(a1=alphas, a2=None, alpha=alphas, gw=None, eps=1e-6,
                                                        tol=1e-10, max_iter=3, update_function=None))
-    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    res = engine.solve(fd.G_full[None], p, [n], [fd.lipschitz(engine, "full")], [grid], tol=1e-12)
     B = res["B"][0].cpu().numpy()
     for k, a in enumerate(alphas):
         b_ref, _ = R.fit("AdaptiveLasso", X, y, alpha=a)
@@ -242,7 +242,7 @@ def test_adaptive_passes_match_oracle(engine):
     grid = PenaltyGrid(p=p, lam1=l1r * alphas, gptr=gptr, W2=np.tile(((1 - l1r) * alphas)[None, :], (Gn, 1)),
                        adaptive=dict(a1=l1r * alphas, a2=(1 - l1r) * alphas, alpha=alphas, gw=gw, eps=1e-6,
                                      tol=1e-10, max_iter=3, update_function=None))
-    res = engine.solve(fd.G_full[None], p, [n], [fd.L_full], [grid], tol=1e-12)
+    res = engine.solve(fd.G_full[None], p, [n], [fd.lipschitz(engine, "full")], [grid], tol=1e-12)
     B = res["B"][0].cpu().numpy()
     for k, a in enumerate(alphas):
         b_ref, _ = R.fit("AdaptiveSparseGroupLasso", X, y, alpha=a, groups=labels, group_weights=gw, l1_ratio=l1r)

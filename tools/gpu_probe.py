@@ -149,7 +149,7 @@ def main():
         eng.timing_reset()
         torch.cuda.synchronize()
         t0 = time.time()
-        res = eng.solve(fd.G_train, p, fd.n_train, fd.L_train, [grid] * F, tol=tol)
+        res = eng.solve(fd.G_train, p, fd.n_train, fd.lipschitz(eng, list(range(F))), [grid] * F, tol=tol)
         torch.cuda.synchronize()
         dt = time.time() - t0
         tim = eng.timing_read()

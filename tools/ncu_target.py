@@ -23,6 +23,6 @@ alphas = np.abs(c).max() / n * np.logspace(0, -3, K)
 Gn = 200
 gptr = np.linspace(0, p, Gn + 1).astype(np.int32)
 grid = PenaltyGrid(p=p, lam1=0.5 * alphas, gptr=gptr, W2=np.tile((0.5 * alphas)[None, :], (Gn, 1)))
-res = eng.solve(fd.G_train, p, fd.n_train, fd.L_train, [grid] * F, tol=1e-9, max_iter=int(os.environ.get("NCU_ITERS", 12)))
+res = eng.solve(fd.G_train, p, fd.n_train, fd.lipschitz(eng, list(range(F))), [grid] * F, tol=1e-9, max_iter=int(os.environ.get("NCU_ITERS", 12)))
 torch.cuda.synchronize()
 print("iters", res["iters_run"])
