@@ -175,6 +175,22 @@ int slm_gram_apply(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t 
                    int n_folds, const int32_t* K, const double* Z_dev, int64_t ldz,
                    double* GZ_dev, void* stream);
 
+/* Row-sparse form of the same apply, as the solver uses it: the iterates of a sparse
+ * linear model are mostly exact zeros, so for every chunk of chunk_w grid columns only
+ * the rows j of Z_f with a non-zero in the chunk (and, by symmetry, the matching rows of
+ * G_f) enter the contraction.  The row lists are built on the device and the kernel
+ * partitions its stream-K work from the device-side counts.  Same result as
+ * slm_gram_apply up to summation order.  work_dev: slm_rowsparse_workspace bytes. */
+size_t slm_rowsparse_workspace(int64_t p, int64_t ldz, int n_folds);
+int slm_gram_apply_rowsparse(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa,
+                             int64_t p, int n_folds, const int32_t* K, const double* Z_dev,
+                             int64_t ldz, double* GZ_dev, int chunk_w, void* work_dev,
+                             size_t work_bytes, void* stream);
+
+/* flops of the solver's Gram applies since the last slm_timing_reset: executed (rows of the
+ * support lists x real columns x 2p) and dense-equivalent (2 p^2 K_active). */
+int slm_apply_stats(slm_ctx* ctx, double* executed_flops, double* dense_flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,13 @@ struct slm_ctx {
     int* h_counter = nullptr;
     int* d_flags = nullptr;      // stream-K per-tile flags
     int n_flags_cap = 0;
+    unsigned long long* d_stat = nullptr;  // executed contraction length of the row-sparse applies
+    unsigned long long* h_stat = nullptr;
+    double apply_exec_flops = 0.0;   // flops the row-sparse applies executed (useful, unpadded)
+    double apply_dense_flops = 0.0;  // 2 p^2 K_active of the same applies
+    int chunk_w = 32;                // columns per support chunk (SLM_CHUNK_W)
+    bool dense_apply = false;        // SLM_DENSE_APPLY=1: solver uses the dense apply (A/B runs)
+    int force_sparse_shape = -1;     // SLM_FORCE_SPARSE_SHAPE
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
 };
@@ -126,6 +133,7 @@ static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
     int nflags = 0;
     for (int i = 0; i < b.n_problems; ++i) {
         GemmProblem& pr = b.pr[i];
+        if (pr.qlim <= 0) pr.qlim = (int)pr.ldq;
         pr.tiles_m = (pr.M + bm - 1) / bm;
         pr.tiles_n = (pr.N + bn - 1) / bn;
         pr.kt = std::max(1, (pr.Kd + kBK - 1) / kBK);
@@ -143,10 +151,10 @@ static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
     b.units_per_cta = (int)((u + n_cta - 1) / n_cta);
 }
 
-template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB>
+template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB, bool KSP = false>
 static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     using Cfg = GemmCfg<WM, WN, MI, NI, kBK, kStages, AM>;
-    auto kern = gemm_f64_kernel<WM, WN, MI, NI, kBK, kStages, AM, SYM, MINB>;
+    auto kern = gemm_f64_kernel<WM, WN, MI, NI, kBK, kStages, AM, SYM, MINB, KSP>;
     static int occupancy = 0;  // resident CTAs per SM (the spin-wait fix-up needs co-residency)
     if (occupancy == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -163,6 +171,8 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
     b.flags = ctx->d_flags;
     int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
+    // row-sparse: the k extents live on the device, the CTAs partition the units themselves
+    if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
     cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);
     if (e != cudaSuccess) return e;
     kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b);
@@ -202,6 +212,31 @@ static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
 #define X(id_, wm, wn, mi, ni, minb, eff) \
     case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb>(ctx, b, s);
         SLM_APPLY_SHAPES(X)
+#undef X
+    }
+    return cudaErrorInvalidValue;
+}
+// row-sparse apply menu (one tile column per support chunk): id, WM, WN, MI, NI, MINB, eff
+#define SLM_SPARSE_SHAPES(X)      \
+    X(0, 8, 1, 2, 1, 2, 0.55)     \
+    X(1, 8, 1, 2, 2, 2, 0.70)     \
+    X(2, 8, 1, 2, 3, 2, 0.78)     \
+    X(3, 8, 1, 2, 4, 2, 0.84)     \
+    X(4, 8, 1, 2, 5, 2, 0.80)     \
+    X(5, 8, 1, 2, 6, 2, 0.79)     \
+    X(6, 8, 1, 2, 7, 2, 0.765)    \
+    X(7, 4, 2, 4, 4, 2, 0.78)
+static const Shape kSparseShapes[] = {
+#define X(id, wm, wn, mi, ni, minb, eff) {wm * mi * 8, wn * ni * 8, minb, eff},
+    SLM_SPARSE_SHAPES(X)
+#undef X
+};
+constexpr int kNumSparseShapes = sizeof(kSparseShapes) / sizeof(Shape);
+static cudaError_t launch_sparse_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
+    switch (id) {
+#define X(id_, wm, wn, mi, ni, minb, eff) \
+    case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb, true>(ctx, b, s);
+        SLM_SPARSE_SHAPES(X)
 #undef X
     }
     return cudaErrorInvalidValue;
@@ -288,6 +323,65 @@ static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_
         ctx->launches++;
     }
     return 0;
+}
+
+// row-sparse batched apply: GZ_f = G_f Z_f using only the rows of Z_f that hold a non-zero
+// in the column chunk (chunks of chunk_w columns; lists made by support_list_kernel from
+// the zflag bytes).  ncc = chunk slots per fold in sidx / scount.
+static int apply_rowsparse(slm_ctx* ctx, const SolveDev& sp, const int32_t* K, const double* Z, double* GZ,
+                           int chunk_w, int ncc, int* sidx, int* scount, cudaStream_t s, double algo_flops) {
+    const int F = sp.F;
+    const int64_t p = sp.p, ldz = sp.ldz;
+    support_list_kernel<<<dim3((unsigned)ncc, (unsigned)F), 1024, 0, s>>>(sp, chunk_w / SC, ncc, sidx, scount,
+                                                                          ctx->d_stat);
+    LAUNCH_OK("support_list_kernel");
+    GemmBatch b;
+    ProblemDims pd[kMaxGemmProblems];
+    int np = 0;
+    double dense = 0.0;
+    bool first = true;
+    auto flush = [&]() -> int {
+        if (np == 0) return 0;
+        b.n_problems = np;
+        int sid = pick_shape(kSparseShapes, kNumSparseShapes, pd, np, ctx->sm_count);
+        if (ctx->force_sparse_shape >= 0 && ctx->force_sparse_shape < kNumSparseShapes) sid = ctx->force_sparse_shape;
+        FamTimer tm(ctx, FAM_APPLY, s, first ? std::max(algo_flops, 0.0) : 0.0);
+        first = false;
+        cudaError_t e = launch_sparse_shape(ctx, sid, b, s);
+        if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("row-sparse apply: ") + cudaGetErrorString(e));
+        ctx->launches++;
+        np = 0;
+        return 0;
+    };
+    memset(&b, 0, sizeof(b));
+    for (int f = 0; f < F; ++f) {
+        const int Kp = (int)std::min<int64_t>(round_up(K[f], 8), ldz);
+        dense += 2.0 * (double)p * (double)p * (double)K[f];
+        for (int cc = 0; cc * chunk_w < Kp; ++cc) {
+            if (np == kMaxGemmProblems) {
+                int rc = flush();
+                if (rc) return rc;
+                memset(&b, 0, sizeof(b));
+            }
+            GemmProblem& pr = b.pr[np];
+            const int64_t off = (int64_t)f * p * ldz + (int64_t)cc * chunk_w;
+            pr.P = sp.G + (int64_t)f * sp.g_stride;
+            pr.Q = Z + off;
+            pr.C = GZ + off;
+            pr.kidx = sidx + ((int64_t)f * ncc + cc) * p;
+            pr.kcount = scount + f * ncc + cc;
+            pr.ldp = sp.pa;
+            pr.ldq = pr.ldc = ldz;
+            pr.qlim = (int)(ldz - (int64_t)cc * chunk_w);
+            pr.M = (int)p;
+            pr.N = std::min(chunk_w, Kp - cc * chunk_w);
+            pr.Kd = (int)p;
+            pd[np] = {pr.M, pr.N};
+            ++np;
+        }
+    }
+    ctx->apply_dense_flops += dense;
+    return flush();
 }
 
 // ------------------------------------------------------------------------- //
@@ -607,9 +701,14 @@ int slm_create(int device, slm_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("SLM_FORCE_APPLY_SHAPE")) ctx->force_apply_shape = atoi(e);
     if (const char* e = getenv("SLM_FORCE_SYRK_SHAPE")) ctx->force_syrk_shape = atoi(e);
+    if (const char* e = getenv("SLM_FORCE_SPARSE_SHAPE")) ctx->force_sparse_shape = atoi(e);
+    if (const char* e = getenv("SLM_CHUNK_W")) ctx->chunk_w = std::max(8, atoi(e) / 8 * 8);
+    if (const char* e = getenv("SLM_DENSE_APPLY")) ctx->dense_apply = atoi(e) != 0;
     ctx->n_flags_cap = 1 << 20;
     if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stat, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_stat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess) {
         delete ctx;
         return 6;
@@ -626,6 +725,8 @@ void slm_destroy(slm_ctx* ctx) {
         for (auto e : F.pool) cudaEventDestroy(e);
     }
     if (ctx->d_counter) cudaFree(ctx->d_counter);
+    if (ctx->d_stat) cudaFree(ctx->d_stat);
+    if (ctx->h_stat) cudaFreeHost(ctx->h_stat);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
     delete ctx;
@@ -660,8 +761,15 @@ int slm_timing_read(slm_ctx* ctx, int which, double* total_ms, int64_t* launches
     if (flops) *flops = ctx->fam[which].flops;
     return 0;
 }
+int slm_apply_stats(slm_ctx* ctx, double* executed_flops, double* dense_flops) {
+    if (!ctx) return 1;
+    if (executed_flops) *executed_flops = ctx->apply_exec_flops;
+    if (dense_flops) *dense_flops = ctx->apply_dense_flops;
+    return 0;
+}
 int slm_timing_reset(slm_ctx* ctx) {
     if (!ctx) return 1;
+    ctx->apply_exec_flops = ctx->apply_dense_flops = 0.0;
     timing_collect(ctx);
     for (auto& F : ctx->fam) {
         F.ms = 0.0;
@@ -759,6 +867,44 @@ int slm_gram_apply(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, 
     return apply_batched(ctx, G, g_stride, pa, p, n_folds, K, Z, ldz, GZ, (cudaStream_t)stream);
 }
 
+size_t slm_rowsparse_workspace(int64_t p, int64_t ldz, int n_folds) {
+    size_t nblk = (size_t)ldz / 8;
+    return (size_t)n_folds * nblk * ((size_t)p + 1) * sizeof(int) + (size_t)n_folds * (size_t)p * nblk + 64;
+}
+
+int slm_gram_apply_rowsparse(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_folds,
+                             const int32_t* K, const double* Z, int64_t ldz, double* GZ, int chunk_w, void* work,
+                             size_t work_bytes, void* stream) {
+    if (!ctx || !G || !K || !Z || !GZ || !work) return fail(ctx, 1, "slm_gram_apply_rowsparse: null argument");
+    if (ldz % 8 || pa % 2) return fail(ctx, 1, "slm_gram_apply_rowsparse: ldz must be a multiple of 8, pa even");
+    if (n_folds < 1 || n_folds > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_gram_apply_rowsparse: n_folds out of range");
+    if (chunk_w < 8 || chunk_w % 8) return fail(ctx, 1, "slm_gram_apply_rowsparse: chunk_w must be a multiple of 8");
+    if (work_bytes < slm_rowsparse_workspace(p, ldz, n_folds))
+        return fail(ctx, 1, "slm_gram_apply_rowsparse: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ncc = (int)((ldz + chunk_w - 1) / chunk_w);
+    SolveDev sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.F = n_folds;
+    sp.p = (int)p;
+    sp.ldz = ldz;
+    sp.pa = pa;
+    sp.g_stride = g_stride;
+    sp.G = G;
+    sp.nblk = (int)(ldz / SC);
+    int* sidx = (int*)work;
+    int* scount = sidx + (size_t)n_folds * ncc * p;
+    sp.zflag = (unsigned char*)(sidx + (size_t)n_folds * sp.nblk * (p + 1));
+    for (int f = 0; f < n_folds; ++f) {
+        if (K[f] < 0 || K[f] > ldz) return fail(ctx, 1, "slm_gram_apply_rowsparse: K[f] out of range");
+        sp.K[f] = K[f];
+    }
+    const dim3 zgrid((unsigned)(((long long)p * sp.nblk + 255) / 256), (unsigned)n_folds);
+    zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
+    LAUNCH_OK("zflags_kernel");
+    return apply_rowsparse(ctx, sp, K, Z, GZ, chunk_w, ncc, sidx, scount, s, -1.0);
+}
+
 size_t slm_lipschitz_workspace(int64_t p, int n_grams) {
     return (size_t)(2 * (int64_t)n_grams * p * 8 + n_grams) * sizeof(double);
 }
@@ -784,12 +930,25 @@ int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, i
     return 0;
 }
 
+// support-chunk geometry of a solve: chunks of w columns, ncc chunk slots per fold
+static void chunk_geometry(const slm_ctx* ctx, int64_t ldz, int* w, int* ncc) {
+    int cw = ctx ? ctx->chunk_w : 32;
+    cw = std::max(8, cw / 8 * 8);
+    *w = cw;
+    *ncc = (int)((ldz + cw - 1) / cw);
+}
+
 size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups) {
     (void)n_groups;
     size_t state = (size_t)n_folds * (size_t)p * (size_t)ldz * sizeof(double);
     size_t cols = (size_t)n_folds * (size_t)ldz;
     size_t part = cols * (size_t)kMaxChunks * NQ * sizeof(double);
-    return 5 * state + cols * (4 * sizeof(double) + 3 * sizeof(int)) + part + 64 * sizeof(int) + 256;
+    // row-sparse apply: support lists for the finest chunking (8 columns) + flag bytes
+    size_t nblk = (size_t)ldz / 8;
+    size_t lists = (size_t)n_folds * nblk * ((size_t)p + 1) * sizeof(int);
+    size_t zflag = round_up((int64_t)((size_t)n_folds * (size_t)p * nblk), 16);
+    return 5 * state + cols * (4 * sizeof(double) + 3 * sizeof(int)) + part + 64 * sizeof(int) + 256 + lists +
+           zflag + 64;
 }
 
 int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
@@ -817,7 +976,13 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     int* flag = (int*)(part + cols * (size_t)kMaxChunks * NQ);
     int* colmap = flag + cols;
     int* src = colmap + cols;
-    int* newK = src + cols;  // [F]
+    int* newK = src + cols;  // [F] (64 ints reserved)
+    int cw, ncc;
+    chunk_geometry(ctx, ldz, &cw, &ncc);
+    int* sidx = newK + 64;                  // [F][ncc][p]
+    int* scount = sidx + (size_t)F * ncc * p;  // [F][ncc]
+    unsigned char* zflag = (unsigned char*)(newK + 64 + (size_t)F * (ldz / 8) * (p + 1));
+    const bool sparse = !ctx->dense_apply;
 
     SolveDev sp;
     memset(&sp, 0, sizeof(sp));
@@ -856,6 +1021,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.n_iter = bt->n_iter_dev;
     sp.status = bt->status_dev;
     sp.counter = ctx->d_counter;
+    sp.zflag = sparse ? zflag : nullptr;
+    sp.nblk = (int)(ldz / SC);
     sp.tol = bt->tol;
     sp.floor_rel = bt->floor_rel;
     int Kcur[SLM_MAX_FOLDS];
@@ -881,6 +1048,12 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     CUDA_OK(cudaMemcpyAsync(Bw, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemsetAsync(GB, 0, state * sizeof(double), s));
+    const dim3 zgrid((unsigned)(((long long)p * sp.nblk + 255) / 256), (unsigned)F);
+    if (sparse) {
+        CUDA_OK(cudaMemsetAsync(ctx->d_stat, 0, sizeof(unsigned long long), s));
+        zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
+        LAUNCH_OK("zflags_kernel");
+    }
 
     auto grids = [&](int Kmax, dim3& cgrid, dim3& mgrid, dim3& fgrid) {
         cgrid = dim3((unsigned)((Kmax + SC - 1) / SC), (unsigned)sp.n_chunks, (unsigned)F);
@@ -898,7 +1071,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
         double algo = 2.0 * (double)p * (double)p * (double)n_active;
-        int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
+        int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw, ncc, sidx, scount, s, algo)
+                        : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
         if (rc) return rc;
         if (it % check_every == 0) {
             CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
@@ -952,6 +1126,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             }
             grids(Kmax, cgrid, mgrid, fgrid);
             do_compact = false;
+            if (sparse) {  // the column blocks moved: support flags from scratch
+                zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
+                LAUNCH_OK("zflags_kernel");
+            }
         }
     }
     bt->iters_run = it;
@@ -966,7 +1144,13 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     for (int f = 0; f < F; ++f) fin.K[f] = bt->K[f];
     grids(Kmax0, cgrid, mgrid, fgrid);
     CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    {
+    if (sparse) {
+        zflags_kernel<<<zgrid, 256, 0, s>>>(fin, Z);
+        LAUNCH_OK("zflags_kernel");
+        int rc = apply_rowsparse(ctx, fin, bt->K, Z, GZ, cw, ncc, sidx, scount, s, 0.0);
+        if (rc) return rc;
+        CUDA_OK(cudaMemcpyAsync(ctx->h_stat, ctx->d_stat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    } else {
         int rc = apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, bt->K, Z, ldz, GZ, s, 0.0);
         if (rc) return rc;
     }
@@ -985,6 +1169,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     CUDA_OK(cudaStreamSynchronize(s));
     bt->n_unconverged = 0;
     for (int f = 0; f < F; ++f) bt->n_unconverged += ctx->h_counter[f];
+    if (sparse) ctx->apply_exec_flops += 2.0 * (double)p * (double)(*ctx->h_stat);
     return 0;
 }
 

@@ -22,6 +22,14 @@
 // tile are the ones that finish first.  All CTAs are co-resident (persistent
 // grid), which makes the spin-wait safe.
 //
+// Row-sparse contraction (KSPARSE): the iterates of a sparse linear model are
+// mostly exact zeros, so the apply only needs the rows k of Z (and the matching
+// rows of G, by symmetry) where some column of the problem's column chunk is
+// non-zero.  A problem then carries a device-side index list kidx[0..*kcount) of
+// those rows; the contraction runs over the list (row gather in the cp.async
+// loads) and, because the list length is only known on the device, every CTA
+// derives the stream-K unit partition itself from the counts.
+//
 // Shared-memory tiles are padded by 4 doubles per row: for the m8n8k4 fragment
 // pattern (k = lane%4, x = lane/4) a row stride == 4 or 12 (mod 16) doubles makes
 // every half-warp hit 16 distinct 8-byte banks.
@@ -31,13 +39,16 @@
 
 namespace slm {
 
-constexpr int kMaxGemmProblems = 16;
+constexpr int kMaxGemmProblems = 32;
 
 struct GemmProblem {
     const double* P;  // A operand (see A_MMAJOR)
     const double* Q;  // B operand, row-major [Kd][ldq]
     double* C;        // row-major [M][ldc]
+    const int* kidx;    // KSPARSE: rows of the contraction (ascending), else NULL
+    const int* kcount;  // KSPARSE: device-side length of kidx
     long long ldp, ldq, ldc;
+    int qlim;  // readable columns of a Q row from the Q pointer on (<= ldq)
     int M, N, Kd;
     int tiles_m, tiles_n;
     int n_tiles;     // tiles of this problem (upper triangle only when SYM)
@@ -88,9 +99,11 @@ struct GemmCfg {
 
 // SYM: problem is C = A^T A with P == Q; only tiles with tn >= tm exist and each
 // is also written transposed.
-template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool A_MMAJOR, bool SYM, int MINB>
+template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool A_MMAJOR, bool SYM, int MINB,
+          bool KSPARSE = false>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     gemm_f64_kernel(const __grid_constant__ GemmBatch batch) {
+    static_assert(!(KSPARSE && (A_MMAJOR || SYM)), "row-sparse mode is for the K-major apply");
     using Cfg = GemmCfg<WARPS_M, WARPS_N, MI, NI, BK, STAGES, A_MMAJOR>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, NT = Cfg::NT;
     extern __shared__ __align__(16) double smem[];
@@ -101,8 +114,27 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int lk = lane & 3, lx = lane >> 2;
 
-    int u = blockIdx.x * batch.units_per_cta;
-    const int u_end = min(batch.total_units, u + batch.units_per_cta);
+    // unit partition: host-made, or derived here from the device-side row counts
+    __shared__ int s_ub[KSPARSE ? kMaxGemmProblems + 1 : 1];
+    __shared__ int s_kd[KSPARSE ? kMaxGemmProblems : 1];
+    int upc = batch.units_per_cta, total_units = batch.total_units;
+    if (KSPARSE) {
+        if (tid < batch.n_problems) s_kd[tid] = min(batch.pr[tid].Kd, __ldcg(batch.pr[tid].kcount));
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int i = 0; i < batch.n_problems; ++i) {
+                s_ub[i] = acc;
+                acc += batch.pr[i].n_tiles * max(1, (s_kd[i] + BK - 1) / BK);
+            }
+            s_ub[batch.n_problems] = acc;
+        }
+        __syncthreads();
+        total_units = s_ub[batch.n_problems];
+        upc = (total_units + (int)gridDim.x - 1) / (int)gridDim.x;
+    }
+    int u = blockIdx.x * upc;
+    const int u_end = min(total_units, u + upc);
 
 #pragma unroll 1
     while (u < u_end) {
@@ -110,10 +142,12 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         int pi = 0;
 #pragma unroll 1
         for (int i = 1; i < batch.n_problems; ++i)
-            if (u >= batch.pr[i].unit_begin) pi = i;
+            if (u >= (KSPARSE ? s_ub[i] : batch.pr[i].unit_begin)) pi = i;
         const GemmProblem& pr = batch.pr[pi];
-        const int KT = pr.kt;
-        const int local = u - pr.unit_begin;
+        const int Kd = KSPARSE ? s_kd[pi] : pr.Kd;
+        const int KT = KSPARSE ? max(1, (Kd + BK - 1) / BK) : pr.kt;
+        const int unit_begin = KSPARSE ? s_ub[pi] : pr.unit_begin;
+        const int local = u - unit_begin;
         int tl = local / KT;
         const int tile_lin = tl;
         const int kt0 = local - tl * KT;
@@ -135,10 +169,11 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
             tn = tl - tm * pr.tiles_n;
         }
         const int m0 = tm * BM, n0 = tn * BN;
-        const int M = pr.M, N = pr.N, Kd = pr.Kd;
+        const int M = pr.M, N = pr.N, qlim = pr.qlim;
         const long long ldp = pr.ldp, ldq = pr.ldq, ldc = pr.ldc;
         const double* __restrict__ P = pr.P;
         const double* __restrict__ Q = pr.Q;
+        const int* __restrict__ kidx = pr.kidx;
 
         double acc[MI][NI][2];
 #pragma unroll
@@ -156,7 +191,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                     int r = c / CPR, x = (c - r * CPR) * 2;
                     long long col = (long long)m0 + x;
                     bool ok = (k0 + r < Kd) && (col + 2 <= ldp);
-                    const double* src = ok ? (P + (long long)(k0 + r) * ldp + col) : P;
+                    long long kr = k0 + r;
+                    if (KSPARSE) kr = ok ? __ldg(kidx + k0 + r) : 0;
+                    const double* src = ok ? (P + kr * ldp + col) : P;
                     cp_async16(as + r * Cfg::A_LD + x, src, ok);
                 }
             } else {
@@ -175,8 +212,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                 for (int c = tid; c < BK * CPR; c += NT) {
                     int r = c / CPR, x = (c - r * CPR) * 2;
                     long long col = (long long)n0 + x;
-                    bool ok = (k0 + r < Kd) && (col + 2 <= ldq);
-                    const double* src = ok ? (Q + (long long)(k0 + r) * ldq + col) : Q;
+                    bool ok = (k0 + r < Kd) && (col + 2 <= qlim);
+                    long long kr = k0 + r;
+                    if (KSPARSE) kr = ok ? __ldg(kidx + k0 + r) : 0;
+                    const double* src = ok ? (Q + kr * ldq + col) : Q;
                     cp_async16(bs + r * Cfg::B_LD + x, src, ok);
                 }
             }
@@ -231,8 +270,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         int* flag = batch.flags + pr.flag_begin + tile_lin;
         if (!whole && !first_writer) {
             // chunks after mine = CTAs between me and the one owning the tile's last unit
-            const int tile_last_unit = pr.unit_begin + tile_lin * KT + KT - 1;
-            const int after = tile_last_unit / batch.units_per_cta - (int)blockIdx.x;
+            const int tile_last_unit = unit_begin + tile_lin * KT + KT - 1;
+            const int after = tile_last_unit / upc - (int)blockIdx.x;
             if (tid == 0) {
                 while (atomicAdd(flag, 0) < after) __nanosleep(64);
                 __threadfence();

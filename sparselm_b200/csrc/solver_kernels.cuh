@@ -46,6 +46,10 @@ struct SolveDev {
     double *gap, *primal;
     int *n_iter, *status;
     int* counter;
+    // row support of Z per block of SC columns (row-sparse Gram apply): zflag[f][j][cb] != 0
+    // iff some active column of column block cb has Z[f][j][k] != 0
+    unsigned char* zflag;
+    int nblk;  // column blocks per row (ldz / SC)
     double tol, floor_rel;
     int K[SLM_MAX_FOLDS];
     double n_obs[SLM_MAX_FOLDS];
@@ -184,6 +188,7 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
 }
 
 // ---- K6b: restart test, momentum, state rotation (elementwise, coalesced) --------
+// also records the row support of the new Z per column block (zflag) for the row-sparse apply
 __global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant__ SolveDev sp, int par) {
     const int f = blockIdx.z;
     const int Kf = sp.K[f];
@@ -195,15 +200,22 @@ __global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant
     const long long ldz = sp.ldz;
     const long long colbase = (long long)f * ldz + k;
     const bool active = (k < Kf) && sp.flag[colbase] == 0;
-    if (__syncthreads_and(!active)) return;
+    const int j0 = blockIdx.y * MOM_ROWS;
+    const int j1 = min(j0 + MOM_ROWS, sp.p);
+    if (__syncthreads_and(!active)) {
+        // nothing iterates in this column block any more: its rows leave the support
+        if (sp.zflag)
+            for (int j = j0 + (int)threadIdx.x; j < j1; j += ST)
+                sp.zflag[((long long)f * sp.p + j) * sp.nblk + blockIdx.x] = 0;
+        return;
+    }
 
     double acc = 0.0;
     if (active)
         for (int ch = r; ch < sp.n_chunks; ch += SG)
             acc += sp.part[(((long long)f * sp.n_chunks + ch) * NQ + 0) * ldz + k];
     const double dsum = lanes_sum(acc, red, r, c);
-    if (!active) return;
-    const double tm = sp.tmom[par][colbase];
+    const double tm = active ? sp.tmom[par][colbase] : 1.0;
     double tn = 0.5 * (1.0 + sqrt(1.0 + 4.0 * tm * tm));
     double th = (tm - 1.0) / tn;
     if (dsum > 0.0) {  // gradient-scheme adaptive restart (O'Donoghue & Candes)
@@ -211,18 +223,101 @@ __global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant
         tn = 1.0;
     }
     const long long sbase = (long long)f * sp.p * ldz + k;
-    const int j0 = blockIdx.y * MOM_ROWS;
-    const int j1 = min(j0 + MOM_ROWS, sp.p);
-    for (int j = j0 + r; j < j1; j += SG) {
-        const long long e = sbase + (long long)j * ldz;
-        const double bn = sp.T[e];
-        const double b = sp.B[e];
-        sp.Z[e] = bn + th * (bn - b);
-        sp.B[e] = bn;
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll 1
+    for (int jj = r; jj < MOM_ROWS; jj += SG) {  // uniform trip count: the ballot needs whole warps
+        const int j = j0 + jj;
+        const bool inb = j < j1;
+        bool nz = false;
+        if (inb && active) {
+            const long long e = sbase + (long long)j * ldz;
+            const double bn = sp.T[e];
+            const double b = sp.B[e];
+            const double z = bn + th * (bn - b);
+            sp.Z[e] = z;
+            sp.B[e] = bn;
+            nz = z != 0.0;
+        }
+        if (sp.zflag) {
+            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            if (c == 0 && inb)
+                sp.zflag[((long long)f * sp.p + j) * sp.nblk + blockIdx.x] =
+                    (unsigned char)(((bal >> (lane & 24u)) & 0xffu) != 0u);
+        }
     }
-    if (blockIdx.y == 0 && r == 0) {
+    if (active && blockIdx.y == 0 && r == 0) {
         sp.theta[par ^ 1][colbase] = th;
         sp.tmom[par ^ 1][colbase] = tn;
+    }
+}
+
+// ---- row support of Z for the row-sparse Gram apply -----------------------------------
+// flags from scratch (start of a solve, after a compaction, final certificate): every
+// column k < K[f] counts
+__global__ void __launch_bounds__(256) zflags_kernel(const __grid_constant__ SolveDev sp,
+                                                     const double* __restrict__ Zsrc) {
+    const int f = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)sp.p * sp.nblk) return;
+    const int j = (int)(i / sp.nblk), cb = (int)(i - (long long)j * sp.nblk);
+    const int Kf = sp.K[f];
+    bool nz = false;
+    const double* row = Zsrc + ((long long)f * sp.p + j) * sp.ldz;
+    for (int k = cb * SC; k < min(cb * SC + SC, Kf); ++k) nz |= row[k] != 0.0;
+    sp.zflag[((long long)f * sp.p + j) * sp.nblk + cb] = nz ? 1 : 0;
+}
+
+// ordered list of the support rows of every (fold, column chunk): chunk cc covers the column
+// blocks [cc*wb, (cc+1)*wb); sidx[(f*ncc + cc)*p + i] ascending, scount[f*ncc + cc] entries.
+// stat accumulates sum(rows x real columns) = executed contraction length (for the roofline).
+__global__ void __launch_bounds__(1024) support_list_kernel(const __grid_constant__ SolveDev sp, int wb, int ncc,
+                                                            int* __restrict__ sidx, int* __restrict__ scount,
+                                                            unsigned long long* __restrict__ stat) {
+    const int f = blockIdx.y, cc = blockIdx.x;
+    const int Kf = sp.K[f];
+    const int nb_f = (Kf + SC - 1) / SC;
+    const int b0 = cc * wb, b1 = min(b0 + wb, nb_f);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int* out = sidx + ((long long)f * ncc + cc) * sp.p;
+    if (b0 >= nb_f) {
+        if (tid == 0) scount[f * ncc + cc] = 0;
+        return;
+    }
+    __shared__ int wtot[32];
+    __shared__ int woff[32];
+    __shared__ int base_s, btot;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < sp.p; j0 += 1024) {
+        const int j = j0 + tid;
+        bool nz = false;
+        if (j < sp.p) {
+            const unsigned char* fl = sp.zflag + ((long long)f * sp.p + j) * sp.nblk;
+            for (int b = b0; b < b1; ++b) nz |= fl[b] != 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            int v = wtot[lane], x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            woff[lane] = x - v;
+            if (lane == 31) btot = x;
+        }
+        __syncthreads();
+        const int base = base_s;
+        if (nz) out[base + woff[warp] + __popc(bal & ((1u << lane) - 1u))] = j;
+        __syncthreads();
+        if (tid == 0) base_s = base + btot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        scount[f * ncc + cc] = base_s;
+        if (stat) atomicAdd(stat, (unsigned long long)base_s * (unsigned long long)(min(b1 * SC, Kf) - b0 * SC));
     }
 }
 

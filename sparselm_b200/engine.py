@@ -277,6 +277,29 @@ class Engine:
                                          self._ptr(GZ), self.stream), "slm_gram_apply")
         return GZ
 
+    def gram_apply_rowsparse(self, G, p, K, Z, chunk_w=32):
+        """The same product through the solver's row-sparse path (support lists per chunk of
+        `chunk_w` columns are built on the device from Z)."""
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        ldz = Z.shape[-1]
+        GZ = torch.zeros_like(Z)
+        Karr = (ctypes.c_int32 * F)(*[int(k) for k in K])
+        nbytes = self.lib.slm_rowsparse_workspace(p, ldz, F)
+        work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._ck(self.lib.slm_gram_apply_rowsparse(self.h, self._ptr(Gs), pa * pa, pa, p, F, Karr, self._ptr(Z), ldz,
+                                                   self._ptr(GZ), int(chunk_w), self._ptr(work), nbytes,
+                                                   self.stream), "slm_gram_apply_rowsparse")
+        return GZ
+
+    def apply_stats(self):
+        """(executed, dense-equivalent) flops of the solver's Gram applies since timing_reset."""
+        ex, de = ctypes.c_double(), ctypes.c_double()
+        self.lib.slm_apply_stats(self.h, ctypes.byref(ex), ctypes.byref(de))
+        return ex.value, de.value
+
     # ---- data preparation for a CV search / a plain fit --------------------
     def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None, shard=None):
         """Pack the design, build per-fold training Grams + the full Gram.

@@ -55,6 +55,18 @@ class ProblemSpec:
     def n_groups(self):
         return self.pe if self.gptr is None else len(self.gptr) - 1
 
+    @property
+    def strength(self):
+        """Scalar penalty strength used to order the columns of a batch: weakly penalised
+        problems have the densest iterates, and the row-sparse Gram apply works on chunks of
+        adjacent columns, so columns of similar strength should sit together."""
+        s = float(self.lam1)
+        if self.w2 is not None and len(self.w2):
+            s += float(np.mean(self.w2))
+        if self.adaptive is not None:
+            s += float(self.adaptive["alpha"])
+        return s
+
 
 def stack_specs(specs):
     """Columns of one engine batch from specs that share their structure key."""

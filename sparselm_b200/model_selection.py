@@ -138,7 +138,9 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
                     cache[ck] = fds[fkey]
         fd = fds[fkey]
         t0 = time.perf_counter()
-        idxs = np.asarray(idxs)
+        # batch columns in order of increasing penalty strength (dense iterates first): the
+        # row-sparse apply shares one support list per chunk of adjacent columns
+        idxs = np.asarray(sorted(idxs, key=lambda ci: (specs[ci].strength, ci)))
         if shard is not None and shard.world > 1:
             mine = shard.my_columns(n_splits, len(idxs))  # per fold: positions in idxs this rank solves
         else:

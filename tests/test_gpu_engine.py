@@ -106,6 +106,51 @@ def test_gram_apply_matches_matmul(engine, p, Ks):
         np.testing.assert_allclose(GZ[f][:, :k], ref[:, :k], rtol=0, atol=1e-11 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("p,Ks,chunk_w,density", [
+    (80, [10, 7], 32, 0.3), (515, [100, 100, 100], 32, 0.05), (1030, [33], 8, 0.5), (2048, [104] * 5, 32, 0.1),
+    (1200, [128, 60, 17, 8], 24, 0.02), (300, [250, 3], 64, 1.0), (700, [40, 0, 40], 16, 0.0),
+    (900, [100] * 9, 32, 0.2),  # 36 problems: more than one launch group
+])
+def test_rowsparse_apply_matches_dense(engine, p, Ks, chunk_w, density):
+    """Row-sparse apply (device-built support lists per column chunk, device-side stream-K
+    partition) == dense product; rows that are zero in one chunk only, empty supports and
+    fully dense iterates included."""
+    torch = _torch()
+    rng = _rng(p + chunk_w)
+    F = len(Ks)
+    pa = engine.padded_cols(p)
+    A = rng.standard_normal((F, pa, pa))
+    A = A + A.transpose(0, 2, 1)
+    G = torch.from_numpy(A).cuda()
+    ldz = max(8, (max(Ks) + 7) // 8 * 8)
+    Zh = np.zeros((F, p, ldz))
+    for f, k in enumerate(Ks):
+        vals = rng.standard_normal((p, k))
+        # row sparsity that differs between column chunks, plus scattered single entries
+        for c0 in range(0, k, chunk_w):
+            keep = rng.random(p) < density
+            vals[~keep, c0:c0 + chunk_w] = 0.0
+        if k and density < 1.0:
+            vals[rng.integers(p, size=3), rng.integers(k, size=3)] = 1.5
+        Zh[f, :, :k] = vals
+    # columns >= K[f] of Z hold garbage that must not enter the lists' products' results
+    Zdev = Zh.copy()
+    for f, k in enumerate(Ks):
+        Zdev[f, :, k:] = 7.0
+    Z = torch.from_numpy(Zdev).cuda()
+    GZ = engine.gram_apply_rowsparse(G, p, Ks, Z, chunk_w=chunk_w).cpu().numpy()
+    GZd = engine.gram_apply(G, p, Ks, Z).cpu().numpy()
+    for f, k in enumerate(Ks):
+        ref = A[f, :p, :p] @ Zh[f]
+        scale = max(np.abs(ref).max(), 1.0)
+        np.testing.assert_allclose(GZ[f][:, :k], ref[:, :k], rtol=0, atol=1e-11 * scale)
+        np.testing.assert_allclose(GZ[f][:, :k], GZd[f][:, :k], rtol=0, atol=1e-11 * scale)
+    # bit-reproducible run to run (fixed-order stream-K fix-up)
+    GZ2 = engine.gram_apply_rowsparse(G, p, Ks, Z, chunk_w=chunk_w).cpu().numpy()
+    for f, k in enumerate(Ks):
+        assert np.array_equal(GZ[f][:, :k], GZ2[f][:, :k])
+
+
 def test_lipschitz_is_tight_lower_bound(engine):
     torch = _torch()
     rng = _rng(3)
