@@ -69,6 +69,18 @@ class FoldData:
     row_perm: np.ndarray | None = None
     extra: dict = field(default_factory=dict)
     _lam: dict = field(default_factory=dict)   # fold index (or "full") -> lambda_max estimate
+    G_all: object = None       # torch [F+1, pa, pa]: G_train followed by G_full (same storage)
+    _finite: object = None     # device flag of the deferred input check (None once checked)
+
+    def check_finite(self):
+        """Deferred input validation (sklearn's ensure_all_finite without a host pass over
+        X): the column sums / sum(y) / n row of the full Gram is non-finite iff X, y or the
+        weights hold a NaN or an infinity.  Evaluated at the first host sync that follows."""
+        if self._finite is not None:
+            ok = bool(self._finite.item())
+            self._finite = None
+            if not ok:
+                raise ValueError("Input X, y or sample_weight contains NaN or infinity.")
 
     @property
     def n_folds(self):
@@ -99,8 +111,16 @@ class FoldData:
                     start = prev = k
             if start is not None:
                 runs.append((start, prev))
+            F = self.n_folds
             for a, b in runs:
-                lam = engine.lipschitz(self.G_train[a:b + 1], self.p)
+                if b == F - 1 and self.G_all is not None and "full" not in self._lam:
+                    # the full-data Gram (refit) rides along in the same batched power iteration
+                    lam = engine.lipschitz(self.G_all[a:F + 1], self.p)
+                    self._lam["full"] = float(lam[-1])
+                    if "full" in missing:
+                        missing.remove("full")
+                else:
+                    lam = engine.lipschitz(self.G_train[a:b + 1], self.p)
                 for j, k in enumerate(range(a, b + 1)):
                     self._lam[k] = float(lam[j])
             if "full" in missing:
@@ -326,24 +346,28 @@ class Engine:
         sw = None
         if sample_weight is not None:
             sw = np.asarray(sample_weight, dtype=np.float64)
-        Xa = self.pack(X, y, sw, col_perm, row_perm)
-        pa = Xa.shape[1]
         F = len(row_ptr) - 1
         build_ptr = row_ptr
-        if shard is not None and shard.world > 1:
+        sharded = shard is not None and shard.world > 1
+        if sharded:
             # row-sharded build: this rank contributes the Gram of its own rows only
             r0, r1 = shard.row_range(n)
             build_ptr = np.clip(row_ptr, r0, r1)
+        on_host = not (isinstance(X, self.torch.Tensor) and X.is_cuda)
+        if on_host and row_perm is None and n >= 4096:
+            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, build_ptr, sharded)
+        else:
+            Xa = self.pack(X, y, sw, col_perm, row_perm)
+            allG = self.gram_blocks(Xa, build_ptr, extra=1 if F > 1 else 0, zero=sharded)
+        pa = Xa.shape[1]
         if F > 1:
-            allG = self.gram_blocks(Xa, build_ptr, extra=1, zero=build_ptr is not row_ptr)
-            if build_ptr is not row_ptr:
+            if sharded:
                 shard.allreduce_sum_(allG[:F])  # NCCL all-reduce of the partial Gram blocks
             G_train, G_full = allG[:F], allG[F]
             self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
             n_train = (n - np.diff(row_ptr)).astype(np.float64)
         else:
-            allG = self.gram_blocks(Xa, build_ptr, zero=build_ptr is not row_ptr)
-            if build_ptr is not row_ptr:
+            if sharded:
                 shard.allreduce_sum_(allG)
             G_full = allG[0]
             G_train = allG[:0]
@@ -362,12 +386,71 @@ class Engine:
             self.gram_center(G_full, p)
             if F > 1:
                 self.gram_center(G_train, p)
-        if not bool(self.torch.isfinite(G_full[p + 1]).all()):
-            # column sums / sum(y) / n of the augmented Gram: any NaN or inf in X, y or the
-            # weights ends up here (input validation without a host pass over X)
-            raise ValueError("Input X, y or sample_weight contains NaN or infinity.")
+        finite = self.torch.isfinite(G_full[p + 1]).all()  # checked at the next host sync
         return FoldData(n=n, p=p, pa=pa, Xa=Xa, row_ptr=row_ptr, G_train=G_train, G_full=G_full,
-                        n_train=n_train, fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra)
+                        n_train=n_train, fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra,
+                        G_all=allG if F > 1 else None, _finite=finite)
+
+    def _prepare_pipelined(self, X, y, sw, col_perm, row_ptr, build_ptr, zero):
+        """Host-resident X: the rows of one test fold at a time are copied to the device on a
+        copy stream while the previous fold is packed and its Gram block is built, so the
+        H2D transfer hides behind the FP64 tensor work (needs pinned memory to be truly
+        asynchronous; pageable arrays still overlap chunk by chunk)."""
+        torch = self.torch
+        Xt = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
+        if Xt.dtype != torch.float64:
+            Xt = Xt.to(torch.float64)
+        n, p = Xt.shape
+        pa = self.padded_cols(p)
+        F = len(row_ptr) - 1
+        dev = self.device
+        yd = self.to_device(y, torch.float64).reshape(-1)
+        swd = None if sw is None else self.to_device(sw, torch.float64)
+        cp = None if col_perm is None else self.to_device(np.asarray(col_perm, dtype=np.int32))
+        Xa = torch.empty((n, pa), dtype=torch.float64, device=dev)
+        alloc = torch.zeros if zero else torch.empty
+        allG = alloc((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=dev)
+        # row blocks: the test folds, split further so that a block stays <= 64 MiB
+        blocks = []
+        max_rows = max(1024, (64 << 20) // (8 * p))
+        for f in range(F):
+            a, b = int(row_ptr[f]), int(row_ptr[f + 1])
+            nb = max(1, -(-(b - a) // max_rows)) if F == 1 else 1
+            edges = np.linspace(a, b, nb + 1).astype(np.int64)
+            blocks += [(int(edges[i]), int(edges[i + 1])) for i in range(nb) if edges[i + 1] > edges[i]]
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._copy_stream.wait_stream(cur)
+        staged = []
+        for a, b in blocks:
+            with torch.cuda.stream(self._copy_stream):
+                blk = Xt[a:b].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            staged.append((a, b, blk, ev))
+        for a, b, blk, ev in staged:
+            cur.wait_event(ev)
+            blk.record_stream(cur)
+            self._ck(self.lib.slm_pack_design(self.h, self._ptr(blk), blk.stride(0), ctypes.c_void_p(yd.data_ptr() + 8 * a),
+                                              ctypes.c_void_p(0 if swd is None else swd.data_ptr() + 8 * a),
+                                              self._ptr(cp), ctypes.c_void_p(0), b - a, p,
+                                              ctypes.c_void_p(Xa.data_ptr() + 8 * a * pa), pa, self.stream),
+                     "slm_pack_design")
+            if F > 1:  # one Gram block per test fold, as soon as its rows are packed
+                f = int(np.searchsorted(row_ptr, a, side="right") - 1)
+                ptr = np.array([max(a, int(build_ptr[f])), min(b, int(build_ptr[f + 1]))], dtype=np.int64)
+                if ptr[1] > ptr[0]:
+                    self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
+                                                      ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
+                                                      ctypes.c_void_p(allG[f].data_ptr()), self.stream),
+                             "slm_gram_blocks")
+        if F == 1:  # single fit: one Gram over all (of this rank's) rows once everything is packed
+            ptr = np.ascontiguousarray(build_ptr, dtype=np.int64)
+            self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
+                                              ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
+                                              self._ptr(allG), self.stream), "slm_gram_blocks")
+        return Xa, allG
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,

@@ -132,6 +132,16 @@ class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
         self.solver = solver
         self.solver_options = solver_options
 
+    @classmethod
+    def _get_param_names(cls):
+        # sklearn re-derives this from inspect.signature on every get_params / set_params /
+        # _validate_params call; a grid search re-parametrises one estimator per candidate
+        names = cls.__dict__.get("_param_names_cache")
+        if names is None:
+            names = super()._get_param_names()
+            cls._param_names_cache = names
+        return names
+
     # ---- hooks --------------------------------------------------------------
     @abstractmethod
     def _problem_spec(self, n_features: int) -> ProblemSpec:
@@ -166,9 +176,11 @@ class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
         self._fit_prepared(engine, fd, spec, opts)
         return self
 
-    def _fit_prepared(self, engine, fd, spec, opts):
-        """Solve on an already prepared (device-resident) design."""
-        out = solve_specs(engine, fd, [spec], use_full=True, **opts)
+    def _fit_prepared(self, engine, fd, spec, opts, B0=None):
+        """Solve on an already prepared (device-resident) design.  B0: optional start point
+        (device tensor [pe], solver feature order), e.g. the CV solution of the same
+        candidate on one training fold."""
+        out = solve_specs(engine, fd, [spec], use_full=True, B0=B0, **opts)
         coef = out["coef"][0, :, 0].cpu().numpy()
         self.coef_ = _to_original_order(coef, spec)
         if self.fit_intercept:
@@ -236,7 +248,7 @@ def _empty_like_grid(s0):
 
 
 def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, check_every=10,
-                floor_rel=1e-14):
+                floor_rel=1e-14, B0=None):
     """Solve problems (equal structure keys) on every training Gram of `fd` (or on its
     full Gram when use_full) as one engine batch.  `specs` is either one list (the same
     K problems on every fold) or a list of per-fold lists (sharded grids).
@@ -264,7 +276,13 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
     else:
         Gs = G
         L[used] = fd.lipschitz(engine, [keys[i] for i in used])
-    res = engine.solve(Gs, s0.pe, n_obs, L, grids, tol=tol, max_iter=max_iter,
+    fd.check_finite()  # the Lipschitz estimate synchronised: deferred input validation is free here
+    B_start = None
+    if B0 is not None and s0.adaptive is None:
+        ldz0 = max(8, (max(Ks) + 7) // 8 * 8)
+        B_start = torch.zeros((F, s0.pe, ldz0), dtype=torch.float64, device=engine.device)
+        B_start[0, :, 0] = B0
+    res = engine.solve(Gs, s0.pe, n_obs, L, grids, B0=B_start, tol=tol, max_iter=max_iter,
                        check_every=check_every, floor_rel=floor_rel)
     B = res["B"]
     ldz = res["ldz"]

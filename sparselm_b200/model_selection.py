@@ -27,7 +27,7 @@ from sklearn.model_selection import ParameterGrid, check_cv
 from sklearn.model_selection._search import BaseSearchCV
 from sklearn.utils.validation import check_X_y
 
-from .engine import get_engine
+from .engine import EngineError, get_engine
 from .model._base import EngineRegressor, _to_original_order, solve_specs
 
 __all__ = ["GridSearchCV", "LineSearchCV"]
@@ -91,8 +91,28 @@ def _metric(scoring, sse, sae, n_rows, sst):
     return 1.0 - sse / sst
 
 
+def _fold_key(est, spec):
+    return (bool(est.fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
+
+
+def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=None, shard=None):
+    """Device-resident design + Grams for (fit_intercept, column order) of `est`/`spec`,
+    through the FoldData cache of a LineSearchCV when there is one.  Only enqueues GPU
+    work (H2D copies, packing, Gram build): the caller can keep working on the host."""
+    ck = None
+    if cache is not None and cache_key is not None:
+        ck = (cache_key, _fold_key(est, spec), tuple(len(t) for t in test_folds),
+              tuple(int(t[0]) for t in test_folds))
+        if ck in cache:
+            return cache[ck]
+    fd = engine.prepare(X, yv, test_folds, est.fit_intercept, None, col_perm=spec.col_perm, shard=shard)
+    if ck is not None:
+        cache[ck] = fd
+    return fd
+
+
 def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_train_score=False, cache=None,
-               cache_key=None, shard=None):
+               cache_key=None, shard=None, fds=None):
     """Solve every (candidate, fold) problem as device batches and score them.
 
     X: (n, p) numpy array or torch tensor (host, pinned or already on the device);
@@ -118,24 +138,16 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     n_unconverged = 0
     iters_run = 0
 
-    fds = {}
+    fds = {} if fds is None else dict(fds)  # may arrive pre-populated (prepare started early)
+    warm = {}  # candidate -> device view [pe] of its solution on some training fold (refit start)
     batches = {}
     for ci, s in enumerate(specs):
         batches.setdefault(s.key, []).append(ci)
     for key, idxs in batches.items():
         s0, e0 = specs[idxs[0]], ests[idxs[0]]
-        fkey = (bool(e0.fit_intercept), None if s0.col_perm is None else s0.col_perm.tobytes())
+        fkey = _fold_key(e0, s0)
         if fkey not in fds:
-            ck = None
-            if cache is not None and cache_key is not None:
-                ck = (cache_key, fkey, tuple(len(t) for t in test_folds), tuple(int(t[0]) for t in test_folds))
-            if ck is not None and ck in cache:
-                fds[fkey] = cache[ck]
-            else:
-                fds[fkey] = engine.prepare(X, yv, test_folds, e0.fit_intercept, None, col_perm=s0.col_perm,
-                                           shard=shard)
-                if ck is not None:
-                    cache[ck] = fds[fkey]
+            fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard)
         fd = fds[fkey]
         t0 = time.perf_counter()
         # batch columns in order of increasing penalty strength (dense iterates first): the
@@ -147,6 +159,9 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             mine = [np.arange(len(idxs))] * n_splits
         out = solve_specs(engine, fd, [[specs[idxs[k]] for k in mine[f]] for f in range(n_splits)], **opts)
         t1 = time.perf_counter()
+        for f in range(n_splits):
+            for pos, k in enumerate(mine[f]):
+                warm.setdefault(int(idxs[k]), out["B"][f, :, pos])
         K = len(idxs)
         icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
         sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f))
@@ -188,7 +203,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             info[k] = shard.allreduce_sum_numpy(info[k].astype(np.float64), dev).astype(info[k].dtype)
         n_unconverged = int(shard.allreduce_sum_numpy(np.array([float(n_unconverged)]), dev)[0])
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
-                info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run)
+                info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm)
 
 
 class GridSearchCV(_SkGridSearchCV):
@@ -261,6 +276,7 @@ class GridSearchCV(_SkGridSearchCV):
         if any(not set(c) <= valid for c in candidates):
             return None
         ests, specs = [], []
+        pre_fds = {}
         try:
             # one working estimator re-parametrised per candidate (cloning 100 estimators and
             # re-deriving their group structure costs more host time than the GPU solve)
@@ -276,11 +292,21 @@ class GridSearchCV(_SkGridSearchCV):
                     work._validate_hyperparams(Xv, yv)
                 ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
                 specs.append(work._problem_spec(p))
-        except NotImplementedError:
+                if ci == 0:
+                    # the design of the first candidate starts its way to the device (H2D, packing,
+                    # Gram build are only enqueued) while the host describes the other candidates
+                    opts0 = est._engine_options()
+                    engine = get_engine(opts0.pop("device", None))
+                    cache = getattr(self, "_fd_cache", None)
+                    pre_fds[_fold_key(ests[0], specs[0])] = prepare_folds(
+                        engine, Xv, yv, [np.asarray(test) for _, test in splits], ests[0], specs[0], cache,
+                        None if cache is None else (id(Xv), id(yv)), getattr(self, "_shard", None))
+        except (NotImplementedError, EngineError):
             raise
         except Exception:
             return None  # sklearn's loop applies error_score semantics per candidate
-        return dict(X=Xv, y=yv, n=n, p=p, splits=splits, candidates=candidates, ests=ests, specs=specs)
+        return dict(X=Xv, y=yv, n=n, p=p, splits=splits, candidates=candidates, ests=ests, specs=specs,
+                    fds=pre_fds)
 
     def _fit_batched(self, plan):
         Xv, yv, n, p = plan["X"], plan["y"], plan["n"], plan["p"]
@@ -295,7 +321,7 @@ class GridSearchCV(_SkGridSearchCV):
         cache_key = None if cache is None else (id(plan["X"]), id(plan["y"]))
         res = batched_cv(engine, Xv, yv, test_folds, ests, specs, opts, scoring,
                          return_train_score=self.return_train_score, cache=cache, cache_key=cache_key,
-                         shard=getattr(self, "_shard", None))
+                         shard=getattr(self, "_shard", None), fds=plan.get("fds"))
         test_scores, train_scores = res["test_scores"], res["train_scores"]
         fit_time, score_time, info, fds = res["fit_time"], res["score_time"], res["info"], res["fds"]
         if res["n_unconverged"]:
@@ -355,10 +381,10 @@ class GridSearchCV(_SkGridSearchCV):
             bi = self.best_index_
             self.best_estimator_ = clone(base).set_params(**clone(self.best_params_, safe=False))
             spec = specs[bi]
-            fkey = (bool(ests[bi].fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
+            fkey = _fold_key(ests[bi], spec)
             t0 = time.time()
             self.best_estimator_.n_features_in_ = p
-            self.best_estimator_._fit_prepared(engine, fds[fkey], spec, dict(opts))
+            self.best_estimator_._fit_prepared(engine, fds[fkey], spec, dict(opts), B0=res["warm"].get(bi))
             self.refit_time_ = time.time() - t0
         from sklearn.metrics import check_scoring
 
