@@ -41,6 +41,8 @@ struct Family {
     int64_t n = 0;
 };
 
+constexpr int kMaxScount = 4096;
+
 struct slm_ctx {
     int device = 0;
     int sm_count = 148;
@@ -54,6 +56,7 @@ struct slm_ctx {
     int n_flags_cap = 0;
     unsigned long long* d_stat = nullptr;  // executed contraction length of the row-sparse applies
     unsigned long long* h_stat = nullptr;
+    int* h_scount = nullptr;         // pinned copy of the support-list lengths (chunk-width choice)
     double apply_exec_flops = 0.0;   // flops the row-sparse applies executed (useful, unpadded)
     double apply_dense_flops = 0.0;  // 2 p^2 K_active of the same applies
     int chunk_w = 32;                // columns per support chunk (SLM_CHUNK_W)
@@ -225,7 +228,11 @@ static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
     X(4, 8, 1, 2, 5, 2, 0.80)     \
     X(5, 8, 1, 2, 6, 2, 0.79)     \
     X(6, 8, 1, 2, 7, 2, 0.765)    \
-    X(7, 4, 2, 4, 4, 2, 0.78)
+    X(7, 4, 2, 4, 4, 2, 0.78)     \
+    X(8, 16, 1, 1, 9, 1, 0.775)   \
+    X(9, 16, 1, 1, 11, 1, 0.775)  \
+    X(10, 16, 1, 1, 13, 1, 0.776) \
+    X(11, 2, 4, 8, 4, 1, 0.76)
 static const Shape kSparseShapes[] = {
 #define X(id, wm, wn, mi, ni, minb, eff) {wm * mi * 8, wn * ni * 8, minb, eff},
     SLM_SPARSE_SHAPES(X)
@@ -709,6 +716,7 @@ int slm_create(int device, slm_ctx** out) {
         cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
         cudaMalloc(&ctx->d_stat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_stat, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_scount, sizeof(int) * kMaxScount) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess) {
         delete ctx;
         return 6;
@@ -727,6 +735,7 @@ void slm_destroy(slm_ctx* ctx) {
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_stat) cudaFree(ctx->d_stat);
     if (ctx->h_stat) cudaFreeHost(ctx->h_stat);
+    if (ctx->h_scount) cudaFreeHost(ctx->h_scount);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
     delete ctx;
@@ -1067,14 +1076,26 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     long long n_active = Ktot;
     int n_active_f[SLM_MAX_FOLDS] = {0};
     bool do_compact = false;
+    // chunk width of the row-sparse apply: narrow chunks (cw) pay when the supports of the
+    // column chunks differ, one wide chunk per fold when they are all (nearly) dense -- the
+    // narrow form then re-reads G once per chunk.  Decided at every convergence check from
+    // the list lengths of that iteration (which always runs narrow).
+    const int cw_wide = (int)std::min<int64_t>(ldz, 128);
+    const bool can_adapt = sparse && cw < cw_wide && F * ncc <= kMaxScount;
+    bool wide = false;
     int it = 0;
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
+        const bool check = (it % check_every == 0);
         double algo = 2.0 * (double)p * (double)p * (double)n_active;
-        int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw, ncc, sidx, scount, s, algo)
+        const int cw_now = (wide && !check) ? cw_wide : cw;
+        int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
+                                          scount, s, algo)
                         : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
         if (rc) return rc;
-        if (it % check_every == 0) {
+        if (check && can_adapt)
+            CUDA_OK(cudaMemcpyAsync(ctx->h_scount, scount, sizeof(int) * (size_t)F * ncc, cudaMemcpyDeviceToHost, s));
+        if (check) {
             CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
             {
                 FamTimer tm(ctx, FAM_GAP, s, 0.0);
@@ -1098,6 +1119,25 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             }
             if (n_active == 0) break;
             do_compact = shrink;
+            if (can_adapt) {
+                double fw = 0.0, fn = 0.0, bw = 0.0, bn = 0.0;  // flops / G bytes, wide and narrow
+                for (int f = 0; f < F; ++f) {
+                    const int Kp = (int)std::min<int64_t>(round_up(Kcur[f], 8), ldz);
+                    int smax = 0;
+                    for (int cc = 0; cc * cw < Kp; ++cc) {
+                        const int sc = ctx->h_scount[f * ncc + cc];
+                        smax = std::max(smax, sc);
+                        fn += 2.0 * (double)p * sc * std::min(cw, Kp - cc * cw);
+                        bn += 8.0 * (double)p * sc;
+                    }
+                    // after this iteration's compaction the fold keeps n_active_f columns
+                    fw += 2.0 * (double)p * smax * std::min(Kp, cw_wide) * ((Kp + cw_wide - 1) / cw_wide);
+                    bw += 8.0 * (double)p * smax * ((Kp + cw_wide - 1) / cw_wide);
+                }
+                const double tn = std::max(fn / (0.84 * 35e12), bn / 6.0e12);
+                const double tw = std::max(fw / (0.776 * 35e12), bw / 6.0e12);
+                wide = (fn == 0.0) || (tw < tn);
+            }
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);

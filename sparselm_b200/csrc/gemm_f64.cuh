@@ -181,6 +181,53 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 #pragma unroll
             for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+        // KSPARSE: the gathered row index of every 16-byte chunk this thread copies is
+        // fetched one slab ahead into registers (pidx_*), so the dependent index -> cp.async
+        // chain never sits on the critical path of the slab loop
+        constexpr int A_CPR = A_MMAJOR ? BK / 2 : BM / 2;  // 16-byte chunks per A tile row
+        constexpr int B_CPR = BN / 2;
+        constexpr int A_IT = (BK * A_CPR + NT - 1) / NT;
+        constexpr int B_IT = (BK * B_CPR + NT - 1) / NT;
+        int pidx_a[KSPARSE ? A_IT : 1], pidx_b[KSPARSE ? B_IT : 1];
+        auto fetch_idx = [&](int kt) {  // indices of slab kt (or -1: zero fill)
+            const int k0 = kt * BK;
+#pragma unroll
+            for (int i = 0; i < A_IT; ++i) {
+                const int c = tid + i * NT, r = c / A_CPR;
+                pidx_a[i] = (c < BK * A_CPR && k0 + r < Kd) ? __ldg(kidx + k0 + r) : -1;
+            }
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int c = tid + i * NT, r = c / B_CPR;
+                pidx_b[i] = (c < BK * B_CPR && k0 + r < Kd) ? __ldg(kidx + k0 + r) : -1;
+            }
+        };
+        auto load_stage_sparse = [&](int stage) {  // slab described by pidx_*
+            double* as = As + (size_t)stage * Cfg::A_STAGE;
+            double* bs = Bs + (size_t)stage * Cfg::B_STAGE;
+#pragma unroll
+            for (int i = 0; i < A_IT; ++i) {
+                const int c = tid + i * NT;
+                if (c < BK * A_CPR) {
+                    const int r = c / A_CPR, x = (c - r * A_CPR) * 2;
+                    const long long col = (long long)m0 + x;
+                    const bool ok = pidx_a[i] >= 0 && (col + 2 <= ldp);
+                    const double* src = ok ? (P + (long long)pidx_a[i] * ldp + col) : P;
+                    cp_async16(as + r * Cfg::A_LD + x, src, ok);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < B_IT; ++i) {
+                const int c = tid + i * NT;
+                if (c < BK * B_CPR) {
+                    const int r = c / B_CPR, x = (c - r * B_CPR) * 2;
+                    const long long col = (long long)n0 + x;
+                    const bool ok = pidx_b[i] >= 0 && (col + 2 <= qlim);
+                    const double* src = ok ? (Q + (long long)pidx_b[i] * ldq + col) : Q;
+                    cp_async16(bs + r * Cfg::B_LD + x, src, ok);
+                }
+            }
+        };
         auto load_stage = [&](int kt, int stage) {
             const int k0 = kt * BK;
             double* as = As + (size_t)stage * Cfg::A_STAGE;
@@ -191,9 +238,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                     int r = c / CPR, x = (c - r * CPR) * 2;
                     long long col = (long long)m0 + x;
                     bool ok = (k0 + r < Kd) && (col + 2 <= ldp);
-                    long long kr = k0 + r;
-                    if (KSPARSE) kr = ok ? __ldg(kidx + k0 + r) : 0;
-                    const double* src = ok ? (P + kr * ldp + col) : P;
+                    const double* src = ok ? (P + (long long)(k0 + r) * ldp + col) : P;
                     cp_async16(as + r * Cfg::A_LD + x, src, ok);
                 }
             } else {
@@ -213,9 +258,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                     int r = c / CPR, x = (c - r * CPR) * 2;
                     long long col = (long long)n0 + x;
                     bool ok = (k0 + r < Kd) && (col + 2 <= qlim);
-                    long long kr = k0 + r;
-                    if (KSPARSE) kr = ok ? __ldg(kidx + k0 + r) : 0;
-                    const double* src = ok ? (Q + kr * ldq + col) : Q;
+                    const double* src = ok ? (Q + (long long)(k0 + r) * ldq + col) : Q;
                     cp_async16(bs + r * Cfg::B_LD + x, src, ok);
                 }
             }
@@ -225,9 +268,17 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         const int nkt = kt1 - kt0;
 #pragma unroll
         for (int s = 0; s < STAGES - 1; ++s) {
-            if (s < nkt) load_stage(kt0 + s, s);
+            if (s < nkt) {
+                if (KSPARSE) {
+                    fetch_idx(kt0 + s);
+                    load_stage_sparse(s);
+                } else {
+                    load_stage(kt0 + s, s);
+                }
+            }
             cp_async_commit();
         }
+        if (KSPARSE && STAGES - 1 < nkt) fetch_idx(kt0 + STAGES - 1);
 
         // ---- main loop -----------------------------------------------------------
 #pragma unroll 1
@@ -236,7 +287,14 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
             __syncthreads();
             {
                 int nk = it + STAGES - 1;
-                if (nk < nkt) load_stage(kt0 + nk, nk % STAGES);
+                if (nk < nkt) {
+                    if (KSPARSE) {
+                        load_stage_sparse(nk % STAGES);
+                        if (nk + 1 < nkt) fetch_idx(kt0 + nk + 1);  // consumed by the next iteration
+                    } else {
+                        load_stage(kt0 + nk, nk % STAGES);
+                    }
+                }
                 cp_async_commit();
             }
             const double* as = As + (size_t)(it % STAGES) * Cfg::A_STAGE;
