@@ -191,6 +191,36 @@ int slm_gram_apply_rowsparse(slm_ctx* ctx, const double* G_dev, int64_t g_stride
  * support lists x real columns x 2p) and dense-equivalent (2 p^2 K_active). */
 int slm_apply_stats(slm_ctx* ctx, double* executed_flops, double* dense_flops);
 
+/* ---- standardize=True (reference _lasso.py:249-252; ridged variant :776-789) ----------
+ * The reference penalises ||X_g b_g||_2, resp. ||sqrtm(X_g^T X_g + sqrt(delta_g) I) b_g||_2,
+ * instead of ||b_g||_2.  With A_g = G_gg (+ shift_g I) = R_g^T R_g (Cholesky) both are
+ * ||R_g b_g||, so in gamma_g = R_g b_g the problem is a plain group Lasso on the Gram
+ * W^T G W, W = blockdiag(W_g), W_g = R_g^{-1}.
+ *
+ * slm_group_whiten_factors: W_g for every group of ONE Gram, stored m_g x m_g row-major at
+ *   W_dev + wptr[g] (wptr_dev: int64[n_groups+1], wptr[g+1]-wptr[g] = m_g^2); scratch_dev has
+ *   the size of W_dev; shift_dev[n_groups] (sqrt(delta_g)) may be NULL; info_dev[0] is
+ *   incremented for every group whose block is not numerically positive definite (the
+ *   group's columns are then linearly dependent on the training rows).
+ * slm_gram_whiten: Gout = W^T G W on the feature block; the y / ones rows and columns are
+ *   transformed on one side, so c = X^T y becomes W^T c and y^T y is kept.  ridge_dev[n_groups]
+ *   (delta_g, may be NULL) folds the ridge 1/2 delta_g ||b_g||^2 into the Gram:
+ *   Gout_gg += ridge_scale * delta_g * W_g^T W_g with ridge_scale = n of the data term.
+ *   tmp_dev: pa*pa doubles.  G, tmp, Gout distinct.
+ * slm_coef_unwhiten: B[g rows][k] = W_g Bg[g rows][k] (coefficients back in the caller's
+ *   variables) for K columns of a [p][ldz] array. */
+int slm_group_whiten_factors(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
+                             const int32_t* gptr_dev, const int64_t* wptr_dev, int32_t n_groups,
+                             const double* shift_dev, double* W_dev, double* scratch_dev,
+                             int32_t* info_dev, void* stream);
+int slm_gram_whiten(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
+                    const int32_t* gptr_dev, const int64_t* wptr_dev, int32_t n_groups,
+                    const double* W_dev, const double* ridge_dev, double ridge_scale,
+                    double* tmp_dev, double* Gout_dev, void* stream);
+int slm_coef_unwhiten(slm_ctx* ctx, const double* Bg_dev, int64_t p, int64_t ldz, int32_t K,
+                      const int32_t* gptr_dev, const int64_t* wptr_dev, int32_t n_groups,
+                      const double* W_dev, double* B_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,17 +367,34 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
         w1[:] = lam1
         w2[:] = lam2 if adaptive else lam2 * gw  # _adaptive_lasso.py:658-667
 
-    if ridge_in_gamma() or (rinv is not None and base == "SparseGroupLasso"):
+    if rinv is not None and base == "SparseGroupLasso":
         raise NotImplementedError(
-            "oracle: standardize=True is restated for (Overlap)GroupLasso only: the l1 term "
-            "of SparseGroupLasso and the ridge of RidgedGroupLasso are not separable in the "
-            "whitened variables")
+            "oracle: standardize=True is restated for the group / overlap / ridged estimators only: "
+            "the l1 term of SparseGroupLasso is not separable in the whitened variables")
+
+    # ridged + standardize: the ridge 1/2 delta_g ||R_g^+ gamma_g||^2 is smooth; it is the data
+    # term of the rows sqrt(n delta_g) R_g^+ appended to the whitened design (targets 0).  The
+    # solver's data term is 1/(2 n_rows), so the whole objective is rescaled by n / n_rows.
+    ysolve, dl_solve, pen_scale = yp, dl, 1.0
+    if ridge_in_gamma():
+        blocks = []
+        for gi, (idx, Ri) in enumerate(rinv):
+            if dl[gi] > 0:
+                blk = np.zeros((len(idx), pe))
+                blk[:, idx] = np.sqrt(n * dl[gi]) * Ri
+                blocks.append(blk)
+        Xsolve = np.vstack([Xsolve] + blocks)
+        ysolve = np.concatenate([yp, np.zeros(Xsolve.shape[0] - n)])
+        dl_solve = np.zeros(G)
+        pen_scale = n / Xsolve.shape[0]
+    elif rinv is not None:
+        dl_solve = np.zeros(G)
 
     update = update_function if update_function is not None else _default_update(alpha)
 
     def solve_once(beta0):
-        pen = Penalty(labels, w1.copy(), w2.copy(), dl.copy())
-        return solve(Xsolve, yp, pen, tol=solver_tol, max_sweeps=max_sweeps, beta0=beta0)
+        pen = Penalty(labels, w1 * pen_scale, w2 * pen_scale, dl_solve.copy())
+        return solve(Xsolve, ysolve, pen, tol=solver_tol, max_sweeps=max_sweeps, beta0=beta0)
 
     details = {"passes": []}
     if not adaptive:
@@ -411,7 +428,7 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
         beta = fold_back(beta, beta_indices, p)
     intercept = float(y_off - X_off @ beta) if fit_intercept else 0.0
     details.update(n_iter=n_iter, w1=w1, w2=w2, labels=labels, delta=dl,
-                   beta_solve=gamma, X_solve=Xsolve, y_solve=yp)
+                   beta_solve=gamma, X_solve=Xsolve, y_solve=ysolve, pen_scale=pen_scale)
     if return_details:
         return beta, intercept, details
     return beta, intercept

@@ -84,6 +84,9 @@ SYMBOLS = {
     "slm_rowsparse_workspace": (c_sz, [c_i64, c_i64, ctypes.c_int]),
     "slm_gram_apply_rowsparse": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_sz, c_vp]),
     "slm_apply_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
+    "slm_group_whiten_factors": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "slm_gram_whiten": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp]),
+    "slm_coef_unwhiten": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

@@ -25,6 +25,7 @@
 #include "../../include/sparselm_b200.h"
 #include "gemm_f64.cuh"
 #include "solver_kernels.cuh"
+#include "whiten_kernels.cuh"
 
 using namespace slm;
 
@@ -1280,6 +1281,48 @@ int slm_intercepts(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const d
     if (K <= 0) return 0;
     intercept_kernel<<<(unsigned)((K + 7) / 8), 256, 0, (cudaStream_t)stream>>>(G, pa, (int)p, B, ldz, K, icpt);
     LAUNCH_OK("intercept_kernel");
+    return 0;
+}
+
+// ---- standardize=True: per-group whitening (whiten_kernels.cuh) -------------------
+int slm_group_whiten_factors(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const int32_t* gptr,
+                             const int64_t* wptr, int32_t n_groups, const double* shift, double* W,
+                             double* scratch, int32_t* info, void* stream) {
+    if (!ctx || !G || !gptr || !wptr || !W || !scratch || !info)
+        return fail(ctx, 1, "slm_group_whiten_factors: null argument");
+    (void)p;
+    if (n_groups <= 0) return 0;
+    group_chol_inv_kernel<<<(unsigned)n_groups, 256, 0, (cudaStream_t)stream>>>(
+        G, pa, gptr, (const long long*)wptr, shift, W, scratch, info);
+    LAUNCH_OK("group_chol_inv_kernel");
+    return 0;
+}
+
+int slm_gram_whiten(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const int32_t* gptr,
+                    const int64_t* wptr, int32_t n_groups, const double* W, const double* ridge,
+                    double ridge_scale, double* tmp, double* Gout, void* stream) {
+    if (!ctx || !G || !gptr || !wptr || !W || !tmp || !Gout) return fail(ctx, 1, "slm_gram_whiten: null argument");
+    if (G == Gout || tmp == Gout || tmp == G) return fail(ctx, 1, "slm_gram_whiten: buffers must be distinct");
+    if (n_groups <= 0 || p <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((unsigned)((pa + 255) / 256), (unsigned)pa);
+    whiten_left_kernel<<<grid, 256, 0, s>>>(G, pa, (int)p, gptr, (const long long*)wptr, n_groups, W, tmp);
+    LAUNCH_OK("whiten_left_kernel");
+    whiten_right_kernel<<<grid, 256, 0, s>>>(tmp, pa, (int)p, gptr, (const long long*)wptr, n_groups, W, ridge,
+                                            ridge_scale, Gout);
+    LAUNCH_OK("whiten_right_kernel");
+    return 0;
+}
+
+int slm_coef_unwhiten(slm_ctx* ctx, const double* Bg, int64_t p, int64_t ldz, int32_t K, const int32_t* gptr,
+                      const int64_t* wptr, int32_t n_groups, const double* W, double* B, void* stream) {
+    if (!ctx || !Bg || !gptr || !wptr || !W || !B) return fail(ctx, 1, "slm_coef_unwhiten: null argument");
+    if (Bg == B) return fail(ctx, 1, "slm_coef_unwhiten: in-place call not supported");
+    if (K <= 0 || p <= 0) return 0;
+    dim3 grid((unsigned)((K + 127) / 128), (unsigned)p);
+    unwhiten_coef_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(Bg, (int)p, ldz, K, gptr, (const long long*)wptr,
+                                                                n_groups, W, B);
+    LAUNCH_OK("unwhiten_coef_kernel");
     return 0;
 }
 

@@ -614,6 +614,56 @@ class Engine:
             W2.copy_(torch.from_numpy(W2h))
         dnorm.copy_(torch.from_numpy(dn))
 
+    # ---- standardize=True: per-group whitening -------------------------------------
+    def whiten(self, G, p, gptr, n_obs, shift=None, ridge=None):
+        """Whitened copies of the Grams G [F, pa, pa] for the group structure gptr:
+        Gw_f = W_f^T G_f W_f (+ n_f ridge_g W_g^T W_g on the diagonal blocks), W_f =
+        blockdiag(R_g^{-1}), R_g^T R_g = G_f[g, g] (+ shift_g I).  Returns (Gw, ctx) where ctx
+        carries the device-resident factors for `unwhiten`.  Raises ValueError if some
+        group's columns are linearly dependent on the rows of a Gram (its block is not
+        positive definite): ||X_g b_g|| is then only a semi-norm."""
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        gptr = np.asarray(gptr, dtype=np.int64)
+        Gn = len(gptr) - 1
+        sizes = np.diff(gptr)
+        wptr = np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)
+        wtot = int(wptr[-1])
+        gptr_dev = self.to_device(gptr.astype(np.int32))
+        wptr_dev = self.to_device(wptr)
+        shift_dev = None if shift is None else self.to_device(np.asarray(shift, dtype=np.float64))
+        ridge_dev = None if ridge is None else self.to_device(np.asarray(ridge, dtype=np.float64))
+        W = torch.empty((F, max(wtot, 1)), dtype=torch.float64, device=self.device)
+        scratch = torch.empty(max(wtot, 1), dtype=torch.float64, device=self.device)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        tmp = torch.empty((pa, pa), dtype=torch.float64, device=self.device)
+        Gw = torch.empty_like(Gs)
+        for f in range(F):
+            self._ck(self.lib.slm_group_whiten_factors(self.h, self._ptr(Gs[f]), pa, p, self._ptr(gptr_dev),
+                                                       self._ptr(wptr_dev), Gn, self._ptr(shift_dev), self._ptr(W[f]),
+                                                       self._ptr(scratch), self._ptr(info), self.stream),
+                     "slm_group_whiten_factors")
+            self._ck(self.lib.slm_gram_whiten(self.h, self._ptr(Gs[f]), pa, p, self._ptr(gptr_dev),
+                                              self._ptr(wptr_dev), Gn, self._ptr(W[f]), self._ptr(ridge_dev),
+                                              float(n_obs[f]), self._ptr(tmp), self._ptr(Gw[f]), self.stream),
+                     "slm_gram_whiten")
+        bad = int(info.item())
+        if bad:
+            raise ValueError(
+                f"standardize=True: {bad} (group, training set) blocks X_g^T X_g are not positive definite "
+                "(linearly dependent columns inside a group, or fewer rows than the group has features)")
+        return Gw, dict(W=W, gptr_dev=gptr_dev, wptr_dev=wptr_dev, Gn=Gn)
+
+    def unwhiten(self, Bg, wctx, f, p, K):
+        """Coefficients of Gram f back in the caller's variables: b_g = W_g gamma_g."""
+        out = self.torch.zeros_like(Bg)
+        self._ck(self.lib.slm_coef_unwhiten(self.h, self._ptr(Bg), p, Bg.shape[-1], int(K), self._ptr(wctx["gptr_dev"]),
+                                            self._ptr(wctx["wptr_dev"]), wctx["Gn"], self._ptr(wctx["W"][f]),
+                                            self._ptr(out), self.stream), "slm_coef_unwhiten")
+        return out
+
     # ---- K9 / K10 ---------------------------------------------------------------
     def fold_back(self, Bext, inv_ptr_dev, inv_idx_dev, p, K):
         torch = self.torch

@@ -108,11 +108,11 @@ class AdaptiveGroupLasso(AdaptiveLasso, GroupLasso):
         _warn_max_iter(self)
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         col_perm, gptr, gw = self._group_spec(n_features)
         a = float(self.alpha)
         return ProblemSpec(p=n_features, pe=n_features, lam1=0.0, col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=a + 0.0 * gw, adaptive=_adaptive(self, None, a),
+                           w2=a + 0.0 * gw, adaptive=_adaptive(self, None, a), standardize=std,
                            key=self._structure_key("AdaptiveGroupLasso", n_features) + (_fn_key(self),))
 
 
@@ -138,14 +138,14 @@ class AdaptiveOverlapGroupLasso(OverlapGroupLasso, AdaptiveGroupLasso):
         OverlapGroupLasso._validate_hyperparams(self, X, y)
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         ext_idx, gptr, n_groups = self._expansion(n_features)
         import numpy as np
 
         gw = np.ones(n_groups) if self.group_weights is None else np.asarray(self.group_weights, dtype=float)
         a = float(self.alpha)
         return ProblemSpec(p=n_features, pe=len(ext_idx), lam1=0.0, ext_idx=ext_idx, gptr=gptr, gw=gw,
-                           w2=a + 0.0 * gw, adaptive=_adaptive(self, None, a),
+                           w2=a + 0.0 * gw, adaptive=_adaptive(self, None, a), standardize=std,
                            key=self._structure_key("AdaptiveOverlapGroupLasso", n_features) + (_fn_key(self),))
 
 
@@ -171,7 +171,7 @@ class AdaptiveSparseGroupLasso(AdaptiveLasso, SparseGroupLasso):
         _warn_max_iter(self)
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        self._check_standardize(separable=False)
         col_perm, gptr, gw = self._group_spec(n_features)
         lam1, lam2 = (float(v) for v in self._lambdas())
         return ProblemSpec(p=n_features, pe=n_features, lam1=lam1, col_perm=col_perm, gptr=gptr, gw=gw,
@@ -201,9 +201,10 @@ class AdaptiveRidgedGroupLasso(AdaptiveGroupLasso, RidgedGroupLasso):
         _warn_max_iter(self)
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         col_perm, gptr, gw = self._group_spec(n_features)
         a = float(self.alpha)
+        ridge, rkey = self._ridge_fields(std, len(gw))
         return ProblemSpec(p=n_features, pe=n_features, lam1=0.0, col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=a + 0.0 * gw, d2=self._delta_vector(len(gw)), adaptive=_adaptive(self, None, a),
-                           key=self._structure_key("AdaptiveRidgedGroupLasso", n_features) + (_fn_key(self),))
+                           w2=a + 0.0 * gw, adaptive=_adaptive(self, None, a), standardize=std, **ridge,
+                           key=self._structure_key("AdaptiveRidgedGroupLasso", n_features) + rkey + (_fn_key(self),))

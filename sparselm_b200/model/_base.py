@@ -49,6 +49,8 @@ class ProblemSpec:
     w2: np.ndarray | None = None         # (G,)
     d2: np.ndarray | None = None         # (G,)
     adaptive: dict | None = None         # a1, a2, alpha, eps, tol, max_iter, update_function
+    standardize: bool = False            # group norms ||X_g b_g|| (solved in whitened variables)
+    std_delta: np.ndarray | None = None  # (G,) ridge of the standardized ridged variant (then d2 is None)
     key: tuple = field(default_factory=tuple)  # structure key: specs with equal keys can be batched
 
     @property
@@ -269,16 +271,25 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
     Ks = [g.K for g in grids]
     used = [i for i in range(F) if Ks[i] > 0]
     L = np.ones(F)
+    wctx = None
     if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
         idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))
         Gs = engine.gram_gather(G, p, idx_dev, s0.pe)
-        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / n_obs
     else:
         Gs = G
+    if s0.standardize:
+        # group norms ||X_g b_g|| (_lasso.py:249-252) / ||sqrtm(X_g^T X_g + sqrt(delta_g) I) b_g||
+        # (:776-789): solve in the whitened variables gamma_g = R_g b_g, ridge folded into the Gram
+        gptr = np.arange(s0.pe + 1) if s0.gptr is None else s0.gptr
+        dl = s0.std_delta
+        Gs, wctx = engine.whiten(Gs, s0.pe, gptr, n_obs, shift=None if dl is None else np.sqrt(dl), ridge=dl)
+    if Gs is not G:
+        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / n_obs
+    else:
         L[used] = fd.lipschitz(engine, [keys[i] for i in used])
     fd.check_finite()  # the Lipschitz estimate synchronised: deferred input validation is free here
     B_start = None
-    if B0 is not None and s0.adaptive is None:
+    if B0 is not None and s0.adaptive is None and not s0.standardize:
         ldz0 = max(8, (max(Ks) + 7) // 8 * 8)
         B_start = torch.zeros((F, s0.pe, ldz0), dtype=torch.float64, device=engine.device)
         B_start[0, :, 0] = B0
@@ -286,6 +297,8 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
                        check_every=check_every, floor_rel=floor_rel)
     B = res["B"]
     ldz = res["ldz"]
+    if wctx is not None:  # back to the caller's variables: b_g = R_g^{-1} gamma_g
+        B = torch.stack([engine.unwhiten(B[f], wctx, f, s0.pe, Ks[f]) for f in range(F)])
     if s0.ext_idx is not None:  # fold back (_lasso.py:492-501)
         idx = np.asarray(s0.ext_idx)
         order = np.argsort(idx, kind="stable").astype(np.int32)

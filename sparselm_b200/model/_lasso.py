@@ -97,12 +97,18 @@ class GroupLasso(Lasso):
         _check_group_weights(self.group_weights, self._n_groups(X.shape[1]))
 
     # -- problem description --
-    def _check_standardize(self):
-        if self.standardize:
+    def _check_standardize(self, separable=True):
+        """standardize=True (group norms ||X_g b_g||, reference _lasso.py:249-252) is solved in
+        per-group whitened variables.  That needs a penalty that is a function of the group
+        norms alone: the l1 term of the sparse-group estimators is not separable in the
+        whitened variables, so those raise (there is no CPU fallback)."""
+        if self.standardize and not separable:
             raise NotImplementedError(
-                "standardize=True (group norms ||X_g b_g||, reference _lasso.py:249-252) is not "
-                "implemented by the B200 engine yet; there is no CPU fallback"
+                f"{type(self).__name__}(standardize=True): the l1 term is not separable in the whitened "
+                "group variables the B200 engine solves standardize=True in; not implemented "
+                "(there is no CPU fallback)"
             )
+        return bool(self.standardize)
 
     def _group_spec(self, n_features):
         """(col_perm, gptr, gw) for the current groups (memoised on the identity of the
@@ -124,10 +130,11 @@ class GroupLasso(Lasso):
                 _arr_key(self.group_weights))
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         col_perm, gptr, gw = self._group_spec(n_features)
         return ProblemSpec(p=n_features, pe=n_features, lam1=0.0, col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=float(self.alpha) * gw, key=self._structure_key("GroupLasso", n_features))
+                           w2=float(self.alpha) * gw, standardize=std,
+                           key=self._structure_key("GroupLasso", n_features))
 
 
 class OverlapGroupLasso(GroupLasso):
@@ -188,11 +195,12 @@ class OverlapGroupLasso(GroupLasso):
         return (name, n_features, bool(self.fit_intercept), bool(self.standardize), gl, _arr_key(self.group_weights))
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         ext_idx, gptr, n_groups = self._expansion(n_features)
         gw = np.ones(n_groups) if self.group_weights is None else np.asarray(self.group_weights, dtype=float)
         return ProblemSpec(p=n_features, pe=len(ext_idx), lam1=0.0, ext_idx=ext_idx, gptr=gptr, gw=gw,
-                           w2=float(self.alpha) * gw, key=self._structure_key("OverlapGroupLasso", n_features))
+                           w2=float(self.alpha) * gw, standardize=std,
+                           key=self._structure_key("OverlapGroupLasso", n_features))
 
 
 class SparseGroupLasso(GroupLasso):
@@ -222,7 +230,7 @@ class SparseGroupLasso(GroupLasso):
         return self.l1_ratio * self.alpha, (1 - self.l1_ratio) * self.alpha  # _lasso.py:621-624
 
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        self._check_standardize(separable=False)
         col_perm, gptr, gw = self._group_spec(n_features)
         lam1, lam2 = self._lambdas()
         return ProblemSpec(p=n_features, pe=n_features, lam1=float(lam1), col_perm=col_perm, gptr=gptr, gw=gw,
@@ -255,9 +263,19 @@ class RidgedGroupLasso(GroupLasso):
         d = np.asarray(self.delta, dtype=float)
         return d * np.ones(n_groups) if len(d) != n_groups else d  # _lasso.py:762-764
 
+    def _ridge_fields(self, std, n_groups):
+        """ProblemSpec fields of the ridge: a prox-side weight normally; with standardize the
+        norm is ||sqrtm(X_g^T X_g + sqrt(delta_g) I) b_g|| (_lasso.py:779-786), the whitening then
+        depends on delta and the ridge is folded into the whitened Gram."""
+        dl = self._delta_vector(n_groups)
+        if std:
+            return dict(d2=None, std_delta=dl), (_arr_key(dl),)
+        return dict(d2=dl), ()
+
     def _problem_spec(self, n_features):
-        self._check_standardize()
+        std = self._check_standardize()
         col_perm, gptr, gw = self._group_spec(n_features)
+        ridge, rkey = self._ridge_fields(std, len(gw))
         return ProblemSpec(p=n_features, pe=n_features, lam1=0.0, col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=float(self.alpha) * gw, d2=self._delta_vector(len(gw)),
-                           key=self._structure_key("RidgedGroupLasso", n_features))
+                           w2=float(self.alpha) * gw, standardize=std, **ridge,
+                           key=self._structure_key("RidgedGroupLasso", n_features) + rkey)

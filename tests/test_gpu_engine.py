@@ -342,3 +342,65 @@ def test_overlap_gather_and_fold_back(engine):
                             torch.from_numpy(order.astype(np.int32)).cuda(), p, 3).cpu().numpy()
     for k in range(3):
         np.testing.assert_allclose(coef[:, k], R.fold_back(Be[:, k], idx, p), rtol=1e-14, atol=1e-15)
+
+
+# --------------------------------------------------------------------------- #
+# standardize=True: per-group whitening (slm_group_whiten_factors / slm_gram_whiten /
+# slm_coef_unwhiten) against numpy Cholesky
+# --------------------------------------------------------------------------- #
+@pytest.mark.parametrize("sizes", [[1, 1, 1, 1, 1], [3, 7, 1, 20, 5], [64, 2, 130]])
+@pytest.mark.parametrize("ridged", [False, True])
+def test_group_whitening_matches_numpy(engine, sizes, ridged):
+    torch = _torch()
+    rng = _rng(sum(sizes) + ridged)
+    p = int(sum(sizes))
+    n = 3 * p + 10
+    X = rng.standard_normal((n, p)) @ (np.eye(p) + 0.2 * rng.standard_normal((p, p)))
+    y = rng.standard_normal(n)
+    Xa = engine.pack(X, y)
+    pa = engine.padded_cols(p)
+    row_ptr = np.array([0, n // 2, n], dtype=np.int64)
+    G = engine.gram_blocks(Xa, row_ptr)
+    gptr = np.concatenate([[0], np.cumsum(sizes)])
+    Gn = len(sizes)
+    dl = 0.1 + rng.random(Gn) if ridged else None
+    n_obs = np.array([n // 2, n - n // 2], dtype=float)
+    Gw, wctx = engine.whiten(G, p, gptr, n_obs, shift=None if dl is None else np.sqrt(dl), ridge=dl)
+    torch.cuda.synchronize()
+    Gh, Gwh = G.cpu().numpy(), Gw.cpu().numpy()
+    for f in range(2):
+        W = np.zeros((pa, pa))
+        W[p:, p:] = np.eye(pa - p)
+        ridge = np.zeros((pa, pa))
+        for g in range(Gn):
+            a, b = gptr[g], gptr[g + 1]
+            A = Gh[f, a:b, a:b] + (np.sqrt(dl[g]) * np.eye(b - a) if ridged else 0.0)
+            Rg = np.linalg.cholesky(A).T  # A = R^T R, R upper
+            Wg = np.linalg.inv(Rg)
+            W[a:b, a:b] = Wg
+            if ridged:
+                ridge[a:b, a:b] = n_obs[f] * dl[g] * Wg.T @ Wg
+        ref = W.T @ Gh[f] @ W + ridge
+        np.testing.assert_allclose(Gwh[f], ref, rtol=1e-10, atol=1e-10 * np.abs(ref).max())
+        if not ridged:  # whitened groups are orthonormal
+            for g in range(Gn):
+                a, b = gptr[g], gptr[g + 1]
+                np.testing.assert_allclose(Gwh[f, a:b, a:b], np.eye(b - a), atol=1e-9)
+        # coefficients back: b = W gamma
+        ldz = 16
+        gam = torch.from_numpy(rng.standard_normal((p, ldz))).to(engine.device)
+        back = engine.unwhiten(gam, wctx, f, p, 11).cpu().numpy()
+        ref_b = W[:p, :p] @ gam.cpu().numpy()
+        np.testing.assert_allclose(back[:, :11], ref_b[:, :11], rtol=1e-11, atol=1e-12 * np.abs(ref_b).max())
+        assert np.all(back[:, 11:] == 0.0)
+
+
+def test_group_whitening_rejects_singular_block(engine):
+    rng = _rng(77)
+    n, p = 40, 6
+    X = rng.standard_normal((n, p))
+    X[:, 2] = X[:, 0] - X[:, 1]  # group 0 = columns 0..2 is rank deficient
+    Xa = engine.pack(X, rng.standard_normal(n))
+    G = engine.gram_blocks(Xa, np.array([0, n], dtype=np.int64))
+    with pytest.raises(ValueError, match="positive definite"):
+        engine.whiten(G, p, np.array([0, 3, 6]), np.array([float(n)]))

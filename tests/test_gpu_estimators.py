@@ -101,10 +101,99 @@ def test_group_lasso_all_or_nothing(random_model_with_groups):
             assert (c > m * THRESHOLD).all() or (c <= m * THRESHOLD).all()
 
 
-def test_standardize_fails_loudly(random_model_with_groups):
+# ---- reference tests/test_lasso.py:89-155 (standardize=True arm) -------------------
+def test_group_lasso_all_or_nothing_standardized(random_model_with_groups):
     X, y, _, groups = random_model_with_groups
+    gw = np.ones(len(np.unique(groups)))
+    for est in (AdaptiveGroupLasso(groups=groups, alpha=0.1, fit_intercept=True, standardize=True),
+                AdaptiveGroupLasso(groups=groups, alpha=0.1, group_weights=gw, fit_intercept=True,
+                                   standardize=True),
+                AdaptiveRidgedGroupLasso(groups=groups, alpha=0.1, group_weights=gw, fit_intercept=True,
+                                         standardize=True)):
+        est.fit(X, y)
+        m = np.max(abs(est.coef_))
+        for gid in np.unique(groups):
+            c = abs(est.coef_[groups == gid])
+            assert (c > m * THRESHOLD).all() or (c <= m * THRESHOLD).all()
+
+
+STD = [GroupLasso, OverlapGroupLasso, RidgedGroupLasso, AdaptiveGroupLasso, AdaptiveOverlapGroupLasso,
+       AdaptiveRidgedGroupLasso]
+
+
+@pytest.mark.parametrize("cls", STD)
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_standardized_estimator_matches_oracle(cls, fit_intercept):
+    """standardize=True (_lasso.py:249-252, 776-789): the engine whitens the Gram with Cholesky
+    factors, the oracle whitens X with symmetric square roots -- the coefficients agree."""
+    rng = np.random.default_rng(43)
+    n, p = 140, 30
+    X = rng.standard_normal((n, p)) @ (np.eye(p) + 0.3 * rng.standard_normal((p, p))) + (0.5 if fit_intercept else 0)
+    w = np.zeros(p)
+    w[rng.choice(p, 6, replace=False)] = 2 * rng.standard_normal(6)
+    y = X @ w + 0.3 * rng.standard_normal(n) + (1.0 if fit_intercept else 0.0)
+    groups = rng.integers(0, 6, size=p)
+    kw = _kwargs(cls, groups, rng, p)
+    extra = {}
+    if "Ridged" in cls.__name__:
+        extra["delta"] = tuple(0.2 + rng.random(len(np.unique(groups))))
+    ng = len(np.unique(groups)) if "groups" in kw else len(np.unique([g for gl in kw["group_list"] for g in gl]))
+    extra["group_weights"] = 0.5 + rng.random(ng)
+    alpha = 0.05  # ||X_g b_g|| ~ sqrt(n) ||b_g||: the standardized penalty is much stronger
+    est = cls(alpha=alpha, fit_intercept=fit_intercept, standardize=True, solver_options={"tol": 1e-12},
+              **kw, **extra).fit(X, y)
+    b_ref, i_ref, det = R.fit(cls.__name__, X, y, alpha=alpha, fit_intercept=fit_intercept, standardize=True,
+                              return_details=True, **kw, **extra)
+    scale = np.abs(b_ref).max()
+    assert scale > 0 and (np.abs(b_ref) <= 1e-6 * scale).any()  # a genuinely sparse, non-trivial solution
+    assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * scale, np.abs(est.coef_ - b_ref).max()
+    assert np.array_equal(np.abs(est.coef_) > 1e-6 * scale, np.abs(b_ref) > 1e-6 * scale)
+    assert abs(est.intercept_ - i_ref) <= 1e-6 * max(1.0, abs(i_ref))
+    if cls in ADAPTIVE:
+        assert est.n_iter_ == det["n_iter"]
+
+
+def test_standardized_grid_search_matches_per_fit_oracle():
+    """Every training fold has its own whitening (X_g^T X_g of the training rows)."""
+    rng = np.random.default_rng(44)
+    n, p = 160, 32
+    X = rng.standard_normal((n, p))
+    w = np.zeros(p)
+    w[:6] = [3, -2, 1.5, 1, -1, 0.5]
+    y = X @ w + 0.5 * rng.standard_normal(n) + 0.7
+    groups = rng.permutation(np.repeat(np.arange(8), 4))
+    alphas = np.logspace(-3.5, -1, 7)
+    for cls, kw in ((GroupLasso, {}), (RidgedGroupLasso, {"delta": (0.5,)})):
+        gs = GridSearchCV(cls(groups=groups, standardize=True, fit_intercept=True, solver_options={"tol": 1e-12},
+                              **kw), {"alpha": alphas}, cv=4).fit(X, y)
+        assert gs.batched_
+        ref = _cv_reference(cls.__name__, X, y, alphas, 4, groups=groups, standardize=True, fit_intercept=True, **kw)
+        got = np.stack([gs.cv_results_[f"split{i}_test_score"] for i in range(4)], axis=1)
+        npt.assert_allclose(got, ref, rtol=1e-7, atol=1e-10)
+        best = int(np.argmax(ref.mean(1)))
+        assert gs.best_index_ == best
+        b_ref, _ = R.fit(cls.__name__, X, y, alpha=alphas[best], groups=groups, standardize=True,
+                         fit_intercept=True, **kw)
+        assert np.abs(gs.best_estimator_.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+
+
+def test_standardize_error_contract(random_model_with_groups):
+    X, y, _, groups = random_model_with_groups
+    # the l1 term is not separable in the whitened variables: loud failure, no CPU fallback
     with pytest.raises(NotImplementedError):
-        GroupLasso(groups=groups, standardize=True).fit(X, y)
+        SparseGroupLasso(groups=groups, standardize=True).fit(X, y)
+    with pytest.raises(NotImplementedError):
+        AdaptiveSparseGroupLasso(groups=groups, standardize=True).fit(X, y)
+    # a group with linearly dependent columns: ||X_g b_g|| is only a semi-norm
+    Xd = X.copy()
+    idx = np.flatnonzero(groups == groups[0])
+    if len(idx) < 2:
+        idx = np.array([0, 1])
+        groups = groups.copy()
+        groups[1] = groups[0]
+    Xd[:, idx[1]] = 2.0 * Xd[:, idx[0]]
+    with pytest.raises(ValueError, match="positive definite"):
+        GroupLasso(groups=groups, standardize=True).fit(Xd, y)
 
 
 # ---- reference tests/test_lasso.py:203-260: warnings that need a completed fit -----

@@ -97,3 +97,47 @@ def test_oracle_preprocess_matches_weighted_least_squares():
     sol = np.linalg.solve(Xa.T @ W @ Xa, Xa.T @ W @ y)
     np.testing.assert_allclose(b, sol[:p], atol=1e-8)
     assert icpt == pytest.approx(sol[p], abs=1e-8)
+
+
+@pytest.mark.parametrize("name", ["GroupLasso", "RidgedGroupLasso"])
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_oracle_standardize_satisfies_kkt_in_original_variables(name, fit_intercept):
+    """standardize=True (_lasso.py:249-252, 776-789): the oracle solves in whitened variables;
+    its answer is checked here against the optimality conditions of the ORIGINAL problem
+    min 1/(2n)||y - X b||^2 + sum_g v_g ||M_g b_g|| + 1/2 sum_g delta_g ||b_g||^2,
+    M_g^2 = X_g^T X_g (+ sqrt(delta_g) I), computed in plain numpy."""
+    rng = np.random.default_rng(11)
+    n, p = 80, 18
+    X = rng.standard_normal((n, p)) @ (np.eye(p) + 0.3 * rng.standard_normal((p, p)))
+    y = X[:, :4] @ [2.0, -1.0, 0.5, 1.0] + 0.2 * rng.standard_normal(n) + (1.0 if fit_intercept else 0.0)
+    groups = rng.integers(0, 5, size=p)
+    G = len(np.unique(groups))
+    gw = 0.5 + rng.random(G)
+    kw = dict(groups=groups, group_weights=gw)
+    delta = np.zeros(G)
+    if name == "RidgedGroupLasso":
+        delta = 0.1 + rng.random(G)
+        kw["delta"] = delta
+    alpha = 0.01
+    b, icpt, det = R.fit(name, X, y, alpha=alpha, standardize=True, fit_intercept=fit_intercept,
+                         return_details=True, **kw)
+    Xp, yp, _, _ = R.preprocess(X, y, None, fit_intercept)
+    labels, _ = R.group_labels(groups, p)
+    v = det["w2"]
+    r = yp - Xp @ b
+    grad = -Xp.T @ r / n
+    n_active = 0
+    for g in range(G):
+        idx = np.flatnonzero(labels == g)
+        M2 = Xp[:, idx].T @ Xp[:, idx] + np.sqrt(delta[g]) * np.eye(len(idx))
+        bg = b[idx]
+        nrm = np.sqrt(bg @ M2 @ bg)
+        if nrm > 1e-9:
+            n_active += 1
+            res = grad[idx] + delta[g] * bg + v[g] * (M2 @ bg) / nrm
+            assert np.abs(res).max() <= 1e-8 * max(1.0, np.abs(grad).max())
+        else:
+            # 0 in grad_g + v_g M_g B(0,1)  <=>  ||M_g^{-1} grad_g|| <= v_g
+            L = np.linalg.cholesky(M2)
+            assert np.linalg.norm(np.linalg.solve(L, grad[idx])) <= v[g] * (1 + 1e-8)
+    assert 0 < n_active < G
