@@ -42,6 +42,10 @@ int slm_create(int device, slm_ctx** out);
 void slm_destroy(slm_ctx* ctx);
 const char* slm_last_error(const slm_ctx* ctx);
 int slm_sm_count(const slm_ctx* ctx);
+/* the persistent tensor-core grids leave n_sms SMs free from now on (0 = use all): a sharded
+ * Gram build keeps a few SMs for the NCCL all-reduce of the previous fold block, which runs
+ * concurrently on its own stream (SURVEY 8e, row sharding) */
+int slm_set_sm_reserve(slm_ctx* ctx, int n_sms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t slm_launch_count(const slm_ctx* ctx);
 /* average device time in ms of the `which` kernel family since the last reset,
@@ -91,6 +95,10 @@ int slm_gram_gather(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
  * largest Rayleigh quotient seen (a lower bound; callers add a margin).
  * work_dev: >= slm_lipschitz_workspace(p, n_grams) bytes. */
 size_t slm_lipschitz_workspace(int64_t p, int n_grams);
+/* same, result left on the device (lam_dev[n_grams]) and NO host synchronisation: the step
+ * sizes then reach slm_solve_batch through slm_batch.lipschitz_dev */
+int slm_lipschitz_dev(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p,
+                      int n_grams, int iters, void* work_dev, double* lam_dev, void* stream);
 int slm_lipschitz(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p,
                   int n_grams, int iters, void* work_dev, double* lam_host, void* stream);
 
@@ -129,6 +137,8 @@ typedef struct slm_batch {
     double* primal_dev;
     int32_t* n_iter_dev;
     int32_t* status_dev; /* 0 converged, 1 max_iter reached, 2 non-finite */
+    const double* lipschitz_dev; /* [n_folds] device array of L, or NULL; overrides lipschitz[]
+                                  * (lets the Lipschitz estimate feed the solve with no host sync) */
     /* host outputs */
     int32_t iters_run;     /* outer iterations executed */
     int32_t n_unconverged; /* columns that hit max_iter */

@@ -50,6 +50,7 @@ class SlmBatch(ctypes.Structure):
         ("primal_dev", c_vp),
         ("n_iter_dev", c_vp),
         ("status_dev", c_vp),
+        ("lipschitz_dev", c_vp),
         ("iters_run", c_i32),
         ("n_unconverged", c_i32),
     ]
@@ -62,6 +63,7 @@ SYMBOLS = {
     "slm_destroy": (None, [c_vp]),
     "slm_last_error": (ctypes.c_char_p, [c_vp]),
     "slm_sm_count": (ctypes.c_int, [c_vp]),
+    "slm_set_sm_reserve": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "slm_launch_count": (c_i64, [c_vp]),
     "slm_timing_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "slm_timing_read": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]),
@@ -74,6 +76,7 @@ SYMBOLS = {
     "slm_gram_gather": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "slm_lipschitz_workspace": (c_sz, [c_i64, ctypes.c_int]),
     "slm_lipschitz": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, ctypes.POINTER(c_dbl), c_vp]),
+    "slm_lipschitz_dev": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
     "slm_solve_workspace": (c_sz, [c_i64, c_i64, ctypes.c_int, ctypes.c_int]),
     "slm_solve_batch": (ctypes.c_int, [c_vp, ctypes.POINTER(SlmBatch), c_vp]),
     "slm_adaptive_update": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp, c_vp, c_vp]),

@@ -47,6 +47,7 @@ constexpr int kMaxScount = 4096;
 struct slm_ctx {
     int device = 0;
     int sm_count = 148;
+    int sm_reserve = 0;  // SMs the persistent GEMM grids leave free (for a concurrent NCCL kernel)
     std::string err;
     int64_t launches = 0;
     bool timing = false;
@@ -170,13 +171,14 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         occupancy = std::min(occ, MINB);
     }
-    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy);
+    const int sms = std::max(1, ctx->sm_count - ctx->sm_reserve);
+    fill_units(b, Cfg::BM, Cfg::BN, SYM, sms * occupancy);
     if (b.total_units <= 0) return cudaSuccess;
     if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
     b.flags = ctx->d_flags;
     int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
     // row-sparse: the k extents live on the device, the CTAs partition the units themselves
-    if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
+    if (KSP) grid = (int)std::min<long long>((long long)sms * occupancy, b.total_units);
     cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);
     if (e != cudaSuccess) return e;
     kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b);
@@ -744,6 +746,11 @@ void slm_destroy(slm_ctx* ctx) {
 
 const char* slm_last_error(const slm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int slm_sm_count(const slm_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+int slm_set_sm_reserve(slm_ctx* ctx, int n_sms) {
+    if (!ctx) return 1;
+    ctx->sm_reserve = std::max(0, std::min(n_sms, ctx->sm_count - 1));
+    return 0;
+}
 int64_t slm_launch_count(const slm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int slm_timing_enable(slm_ctx* ctx, int on) {
@@ -919,10 +926,9 @@ size_t slm_lipschitz_workspace(int64_t p, int n_grams) {
     return (size_t)(2 * (int64_t)n_grams * p * 8 + n_grams) * sizeof(double);
 }
 
-int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_grams,
-                  int iters, void* work, double* lam_host, void* stream) {
-    if (!ctx || !G || !work || !lam_host) return fail(ctx, 1, "slm_lipschitz: null argument");
-    cudaStream_t s = (cudaStream_t)stream;
+// block power iteration; leaves lam[n_grams] (largest Rayleigh quotient) in the workspace
+static int lipschitz_run(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_grams,
+                         int iters, void* work, double** lam_out, cudaStream_t s) {
     double* V = (double*)work;
     double* W = V + (int64_t)n_grams * p * 8;
     double* lam = W + (int64_t)n_grams * p * 8;
@@ -935,8 +941,30 @@ int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, i
         power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 0);
         LAUNCH_OK("power_norm_kernel");
     }
+    *lam_out = lam;
+    return 0;
+}
+
+int slm_lipschitz(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_grams,
+                  int iters, void* work, double* lam_host, void* stream) {
+    if (!ctx || !G || !work || !lam_host) return fail(ctx, 1, "slm_lipschitz: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* lam = nullptr;
+    int rc = lipschitz_run(ctx, G, g_stride, pa, p, n_grams, iters, work, &lam, s);
+    if (rc) return rc;
     CUDA_OK(cudaMemcpyAsync(lam_host, lam, sizeof(double) * n_grams, cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int slm_lipschitz_dev(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_grams,
+                      int iters, void* work, double* lam_dev, void* stream) {
+    if (!ctx || !G || !work || !lam_dev) return fail(ctx, 1, "slm_lipschitz_dev: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* lam = nullptr;
+    int rc = lipschitz_run(ctx, G, g_stride, pa, p, n_grams, iters, work, &lam, s);
+    if (rc) return rc;
+    CUDA_OK(cudaMemcpyAsync(lam_dev, lam, sizeof(double) * n_grams, cudaMemcpyDeviceToDevice, s));
     return 0;
 }
 
@@ -1035,12 +1063,13 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.nblk = (int)(ldz / SC);
     sp.tol = bt->tol;
     sp.floor_rel = bt->floor_rel;
+    sp.lips_dev = bt->lipschitz_dev;
     int Kcur[SLM_MAX_FOLDS];
     int Kmax0 = 0;
     long long Ktot = 0;
     for (int f = 0; f < F; ++f) {
         if (bt->K[f] < 0 || bt->K[f] > ldz) return fail(ctx, 1, "slm_solve_batch: K[f] out of range");
-        if (bt->K[f] > 0 && (!(bt->lipschitz[f] > 0.0) || !(bt->n_obs[f] > 0.0)))
+        if (bt->K[f] > 0 && ((!bt->lipschitz_dev && !(bt->lipschitz[f] > 0.0)) || !(bt->n_obs[f] > 0.0)))
             return fail(ctx, 1, "slm_solve_batch: lipschitz and n_obs must be positive");
         sp.K[f] = Kcur[f] = bt->K[f];
         sp.n_obs[f] = bt->n_obs[f] > 0.0 ? bt->n_obs[f] : 1.0;
@@ -1085,17 +1114,46 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     const bool can_adapt = sparse && cw < cw_wide && F * ncc <= kMaxScount;
     bool wide = false;
     int it = 0;
+    // chunk-width decision from the support-list lengths of a narrow iteration (host copy in
+    // ctx->h_scount): time of the narrow form (per-chunk supports, G re-read per chunk) against
+    // one wide chunk per fold contracting over the largest support
+    auto decide_width = [&]() {
+        double fw = 0.0, fn = 0.0, bw = 0.0, bn = 0.0;  // flops / G bytes, wide and narrow
+        for (int f = 0; f < F; ++f) {
+            const int Kp = (int)std::min<int64_t>(round_up(Kcur[f], 8), ldz);
+            int smax = 0;
+            for (int cc = 0; cc * cw < Kp; ++cc) {
+                const int sc = ctx->h_scount[f * ncc + cc];
+                smax = std::max(smax, sc);
+                fn += 2.0 * (double)p * sc * std::min(cw, Kp - cc * cw);
+                bn += 8.0 * (double)p * sc;
+            }
+            fw += 2.0 * (double)p * smax * std::min(Kp, cw_wide) * ((Kp + cw_wide - 1) / cw_wide);
+            bw += 8.0 * (double)p * smax * ((Kp + cw_wide - 1) / cw_wide);
+        }
+        const double tn = std::max(fn / (0.84 * 35e12), bn / 6.0e12);
+        const double tw = std::max(fw / (0.776 * 35e12), bw / 6.0e12);
+        wide = (fn == 0.0) || (tw < tn);
+    };
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
         const bool check = (it % check_every == 0);
         double algo = 2.0 * (double)p * (double)p * (double)n_active;
-        const int cw_now = (wide && !check) ? cw_wide : cw;
+        // the supports change fastest in the first iterations (a cold start is all-zero, then
+        // every weakly penalised column fills up): re-decide the width there without waiting
+        // for the next convergence check
+        const bool probe = can_adapt && !check && (it == 1 || it == 3 || it == 6);
+        const int cw_now = (wide && !check && !probe) ? cw_wide : cw;
         int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
                                           scount, s, algo)
                         : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
         if (rc) return rc;
-        if (check && can_adapt)
+        if ((check || probe) && can_adapt)
             CUDA_OK(cudaMemcpyAsync(ctx->h_scount, scount, sizeof(int) * (size_t)F * ncc, cudaMemcpyDeviceToHost, s));
+        if (probe) {
+            CUDA_OK(cudaStreamSynchronize(s));
+            decide_width();
+        }
         if (check) {
             CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
             {
@@ -1120,25 +1178,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             }
             if (n_active == 0) break;
             do_compact = shrink;
-            if (can_adapt) {
-                double fw = 0.0, fn = 0.0, bw = 0.0, bn = 0.0;  // flops / G bytes, wide and narrow
-                for (int f = 0; f < F; ++f) {
-                    const int Kp = (int)std::min<int64_t>(round_up(Kcur[f], 8), ldz);
-                    int smax = 0;
-                    for (int cc = 0; cc * cw < Kp; ++cc) {
-                        const int sc = ctx->h_scount[f * ncc + cc];
-                        smax = std::max(smax, sc);
-                        fn += 2.0 * (double)p * sc * std::min(cw, Kp - cc * cw);
-                        bn += 8.0 * (double)p * sc;
-                    }
-                    // after this iteration's compaction the fold keeps n_active_f columns
-                    fw += 2.0 * (double)p * smax * std::min(Kp, cw_wide) * ((Kp + cw_wide - 1) / cw_wide);
-                    bw += 8.0 * (double)p * smax * ((Kp + cw_wide - 1) / cw_wide);
-                }
-                const double tn = std::max(fn / (0.84 * 35e12), bn / 6.0e12);
-                const double tw = std::max(fw / (0.776 * 35e12), bw / 6.0e12);
-                wide = (fn == 0.0) || (tw < tn);
-            }
+            if (can_adapt) decide_width();
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);

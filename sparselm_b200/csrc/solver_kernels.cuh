@@ -54,6 +54,7 @@ struct SolveDev {
     int K[SLM_MAX_FOLDS];
     double n_obs[SLM_MAX_FOLDS];
     double step[SLM_MAX_FOLDS];
+    const double* lips_dev;  // [F] Lipschitz constants on the device (overrides step[]) or NULL
 };
 
 __device__ __forceinline__ double softt(double v, double t) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
     const double theta = active ? sp.theta[par][colbase] : 0.0;
     const double inv1pt = 1.0 / (1.0 + theta);
     const double* __restrict__ cvec = sp.G + (long long)f * sp.g_stride + (long long)sp.p * sp.pa;
-    const double n = sp.n_obs[f], step = sp.step[f];
+    const double n = sp.n_obs[f], step = sp.lips_dev ? 1.0 / sp.lips_dev[f] : sp.step[f];
     const double son = step / n;
     const long long ldz = sp.ldz;
     const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;  // original column (penalty arrays)

@@ -69,6 +69,7 @@ class FoldData:
     row_perm: np.ndarray | None = None
     extra: dict = field(default_factory=dict)
     _lam: dict = field(default_factory=dict)   # fold index (or "full") -> lambda_max estimate
+    _lam_dev: dict = field(default_factory=dict)  # same, as 0-d device tensors (no host sync)
     G_all: object = None       # torch [F+1, pa, pa]: G_train followed by G_full (same storage)
     _finite: object = None     # device flag of the deferred input check (None once checked)
 
@@ -128,6 +129,51 @@ class FoldData:
         out = np.array([max(self._lam[k], 1e-300) * engine.LIPSCHITZ_MARGIN / self.n_obs(k) for k in keys])
         return out if isinstance(which, (list, tuple, np.ndarray)) else float(out[0])
 
+    def lipschitz_dev(self, engine, keys, used):
+        """Device tensor [len(keys)] of L >= lambda_max(G_k)/n_k for the Grams `keys`
+        (training folds or "full"); entries of keys not listed in `used` are 1.  Nothing
+        here synchronises the host: the power iterations are only enqueued and their
+        results stay on the device (cached per Gram for later searches on the same data)."""
+        torch = engine.torch
+        need = [keys[i] for i in used if keys[i] not in self._lam_dev]
+        ints = sorted(k for k in need if k != "full")
+        F = self.n_folds
+        runs, start = [], None
+        for k in ints:
+            if start is None:
+                start = prev = k
+            elif k == prev + 1:
+                prev = k
+            else:
+                runs.append((start, prev))
+                start = prev = k
+        if start is not None:
+            runs.append((start, prev))
+        want_full = "full" in need
+        for a, b in runs:
+            if b == F - 1 and self.G_all is not None and "full" not in self._lam_dev:
+                lam = engine.lipschitz_device(self.G_all[a:F + 1], self.p)  # the refit Gram rides along
+                self._lam_dev["full"] = lam[-1]
+                want_full = False
+            else:
+                lam = engine.lipschitz_device(self.G_train[a:b + 1], self.p)
+            for j, k in enumerate(range(a, b + 1)):
+                self._lam_dev[k] = lam[j]
+        if want_full:
+            self._lam_dev["full"] = engine.lipschitz_device(self.G_full[None], self.p)[0]
+        scale = np.ones(len(keys))
+        parts = []
+        one = None
+        for i, k in enumerate(keys):
+            if i in used:
+                parts.append(self._lam_dev[k])
+                scale[i] = engine.LIPSCHITZ_MARGIN / self.n_obs(k)
+            else:
+                if one is None:
+                    one = torch.ones((), dtype=torch.float64, device=engine.device)
+                parts.append(one)
+        return torch.stack(parts).clamp_min(1e-300) * engine.to_device(scale)
+
 
 class Engine:
     # 12 block power iterations reach >= 0.93 lambda_max on flat (Marchenko-Pastur) spectra;
@@ -182,6 +228,13 @@ class Engine:
             t = a
         else:
             t = torch.from_numpy(np.ascontiguousarray(a))
+            if t.numel() * t.element_size() <= (8 << 20):
+                # small host arrays (penalty tables, y, index lists) are staged through torch's
+                # cached pinned pool so that the upload is asynchronous: a pageable H2D copy
+                # would stall the host until the GPU has drained the stream
+                if dtype is not None and t.dtype != dtype:
+                    t = t.to(dtype)
+                t = t.pin_memory()
         if dtype is not None and t.dtype != dtype:
             t = t.to(dtype)
         if t.device != self.device:
@@ -284,6 +337,23 @@ class Engine:
             out[f0:f0 + nf] = np.frombuffer(lam, dtype=np.float64, count=nf)
         return out
 
+    def lipschitz_device(self, G, p, iters=None):
+        """Same estimate, left on the device ([F] tensor) without synchronising the host."""
+        torch = self.torch
+        pa = G.shape[-1]
+        Gs = G.reshape(-1, pa, pa)
+        F = Gs.shape[0]
+        out = torch.empty(F, dtype=torch.float64, device=self.device)
+        iters = self.LIPSCHITZ_ITERS if iters is None else iters
+        for f0 in range(0, F, _lib.SLM_MAX_FOLDS):
+            nf = min(F - f0, _lib.SLM_MAX_FOLDS)
+            nbytes = self.lib.slm_lipschitz_workspace(p, nf)
+            work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._ck(self.lib.slm_lipschitz_dev(self.h, self._ptr(Gs[f0]), pa * pa, pa, p, nf, iters,
+                                                self._ptr(work), ctypes.c_void_p(out.data_ptr() + 8 * f0),
+                                                self.stream), "slm_lipschitz_dev")
+        return out
+
     def gram_apply(self, G, p, K, Z):
         """GZ_f = G_f Z_f (tests / roofline)."""
         torch = self.torch
@@ -347,28 +417,24 @@ class Engine:
         if sample_weight is not None:
             sw = np.asarray(sample_weight, dtype=np.float64)
         F = len(row_ptr) - 1
-        build_ptr = row_ptr
         sharded = shard is not None and shard.world > 1
-        if sharded:
-            # row-sharded build: this rank contributes the Gram of its own rows only
-            r0, r1 = shard.row_range(n)
-            build_ptr = np.clip(row_ptr, r0, r1)
         on_host = not (isinstance(X, self.torch.Tensor) and X.is_cuda)
+        # rows of every test fold whose Gram block this rank builds (all of them unless sharded)
+        fold_rows = shard.fold_row_ranges(row_ptr) if sharded else \
+            [(int(row_ptr[f]), int(row_ptr[f + 1])) for f in range(F)]
         if on_host and row_perm is None and n >= 4096:
-            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, build_ptr, sharded)
+            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows, shard if sharded else None)
+        elif sharded:
+            Xa, allG = self._prepare_sharded(X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard)
         else:
             Xa = self.pack(X, y, sw, col_perm, row_perm)
-            allG = self.gram_blocks(Xa, build_ptr, extra=1 if F > 1 else 0, zero=sharded)
+            allG = self.gram_blocks(Xa, row_ptr, extra=1 if F > 1 else 0)
         pa = Xa.shape[1]
         if F > 1:
-            if sharded:
-                shard.allreduce_sum_(allG[:F])  # NCCL all-reduce of the partial Gram blocks
             G_train, G_full = allG[:F], allG[F]
             self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
             n_train = (n - np.diff(row_ptr)).astype(np.float64)
         else:
-            if sharded:
-                shard.allreduce_sum_(allG)
             G_full = allG[0]
             G_train = allG[:0]
             n_train = np.zeros(0)
@@ -391,11 +457,47 @@ class Engine:
                         n_train=n_train, fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra,
                         G_all=allG if F > 1 else None, _finite=finite)
 
-    def _prepare_pipelined(self, X, y, sw, col_perm, row_ptr, build_ptr, zero):
+    SHARD_SM_RESERVE = 16  # SMs left to the NCCL kernel while a sharded Gram build runs
+
+    def _gram_block_into(self, Xa, lo, hi, out):
+        """out = Xa[lo:hi]^T Xa[lo:hi] (out untouched when the range is empty)."""
+        if hi <= lo:
+            return
+        ptr = np.array([lo, hi], dtype=np.int64)
+        self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), Xa.shape[1],
+                                          ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
+                                          ctypes.c_void_p(out.data_ptr()), self.stream), "slm_gram_blocks")
+
+    def _prepare_sharded(self, X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard):
+        """Row-sharded Gram build: this rank contributes, for every test fold, the
+        Gram of its own 1/world slice of that fold's rows.  The block of fold f is all-reduced
+        on NCCL's stream while the tensor cores build the block of fold f+1 (the persistent
+        GEMM grid leaves SHARD_SM_RESERVE SMs to the NCCL kernel)."""
+        torch = self.torch
+        Xa = self.pack(X, y, sw, col_perm, row_perm)
+        pa = Xa.shape[1]
+        F = len(row_ptr) - 1
+        allG = torch.zeros((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=self.device)
+        works = []
+        self.lib.slm_set_sm_reserve(self.h, self.SHARD_SM_RESERVE)
+        try:
+            for f, (lo, hi) in enumerate(fold_rows):
+                self._gram_block_into(Xa, lo, hi, allG[f])
+                works.append(shard.allreduce_sum_async(allG[f]))
+        finally:
+            self.lib.slm_set_sm_reserve(self.h, 0)
+        for w in works:
+            if w is not None:
+                w.wait()
+        return Xa, allG
+
+    def _prepare_pipelined(self, X, y, sw, col_perm, row_ptr, fold_rows, shard=None):
         """Host-resident X: the rows of one test fold at a time are copied to the device on a
         copy stream while the previous fold is packed and its Gram block is built, so the
         H2D transfer hides behind the FP64 tensor work (needs pinned memory to be truly
-        asynchronous; pageable arrays still overlap chunk by chunk)."""
+        asynchronous; pageable arrays still overlap chunk by chunk).  fold_rows[f] = the rows
+        of fold f whose Gram this rank builds; with `shard` the blocks are summed over the
+        ranks, fold by fold, on NCCL's stream while the next block is being built."""
         torch = self.torch
         Xt = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
         if Xt.dtype != torch.float64:
@@ -408,8 +510,11 @@ class Engine:
         swd = None if sw is None else self.to_device(sw, torch.float64)
         cp = None if col_perm is None else self.to_device(np.asarray(col_perm, dtype=np.int32))
         Xa = torch.empty((n, pa), dtype=torch.float64, device=dev)
-        alloc = torch.zeros if zero else torch.empty
+        alloc = torch.zeros if shard is not None else torch.empty
         allG = alloc((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=dev)
+        works = []
+        if shard is not None:
+            self.lib.slm_set_sm_reserve(self.h, self.SHARD_SM_RESERVE)
         # row blocks: the test folds, split further so that a block stays <= 64 MiB
         blocks = []
         max_rows = max(1024, (64 << 20) // (8 * p))
@@ -439,17 +544,18 @@ class Engine:
                      "slm_pack_design")
             if F > 1:  # one Gram block per test fold, as soon as its rows are packed
                 f = int(np.searchsorted(row_ptr, a, side="right") - 1)
-                ptr = np.array([max(a, int(build_ptr[f])), min(b, int(build_ptr[f + 1]))], dtype=np.int64)
-                if ptr[1] > ptr[0]:
-                    self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
-                                                      ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
-                                                      ctypes.c_void_p(allG[f].data_ptr()), self.stream),
-                             "slm_gram_blocks")
+                self._gram_block_into(Xa, max(a, fold_rows[f][0]), min(b, fold_rows[f][1]), allG[f])
+                if shard is not None:
+                    works.append(shard.allreduce_sum_async(allG[f]))
         if F == 1:  # single fit: one Gram over all (of this rank's) rows once everything is packed
-            ptr = np.ascontiguousarray(build_ptr, dtype=np.int64)
-            self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), pa,
-                                              ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
-                                              self._ptr(allG), self.stream), "slm_gram_blocks")
+            self._gram_block_into(Xa, fold_rows[0][0], fold_rows[0][1], allG[0])
+            if shard is not None:
+                works.append(shard.allreduce_sum_async(allG[0]))
+        if shard is not None:
+            self.lib.slm_set_sm_reserve(self.h, 0)
+        for w in works:
+            if w is not None:
+                w.wait()
         return Xa, allG
 
     # ---- K5-K8: batched solve ------------------------------------------------
@@ -493,19 +599,25 @@ class Engine:
             B.copy_(B0)
         nbytes = self.lib.slm_solve_workspace(p, ldz, F, Gn)
         work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        gap = torch.zeros((F, ldz), dtype=torch.float64, device=dev)
-        primal = torch.zeros((F, ldz), dtype=torch.float64, device=dev)
-        n_iter = torch.zeros((F, ldz), dtype=torch.int32, device=dev)
-        status = torch.full((F, ldz), -1, dtype=torch.int32, device=dev)
+        # per-column results share one buffer so that they come back in a single D2H copy
+        ncol = F * ldz
+        rbuf = torch.zeros(24 * ncol, dtype=torch.uint8, device=dev)
+        gap = rbuf[: 8 * ncol].view(torch.float64).view(F, ldz)
+        primal = rbuf[8 * ncol: 16 * ncol].view(torch.float64).view(F, ldz)
+        n_iter = rbuf[16 * ncol: 20 * ncol].view(torch.int32).view(F, ldz)
+        status = rbuf[20 * ncol:].view(torch.int32).view(F, ldz)
+        status.fill_(-1)
 
         bt = _lib.SlmBatch()
         bt.n_folds, bt.n_groups, bt.p, bt.pa, bt.ldz = F, Gn, p, pa, ldz
         bt.G_dev, bt.g_stride = Gs.data_ptr(), pa * pa
         bt.gptr_dev = 0 if gptr_dev is None else gptr_dev.data_ptr()
+        lips_dev = lipschitz if isinstance(lipschitz, torch.Tensor) else None
+        bt.lipschitz_dev = 0 if lips_dev is None else lips_dev.data_ptr()
         for f in range(F):
             bt.K[f] = Ks[f]
             bt.n_obs[f] = float(n_obs[f])
-            bt.lipschitz[f] = float(lipschitz[f])
+            bt.lipschitz[f] = 1.0 if lips_dev is not None else float(lipschitz[f])
         bt.lam1_dev = lam1.data_ptr()
         bt.W2_dev = 0 if W2 is None else W2.data_ptr()
         bt.D2_dev = 0 if D2 is None else D2.data_ptr()
@@ -572,10 +684,13 @@ class Engine:
                     break
                 skip.copy_(torch.from_numpy(conv.astype(np.int32)))
 
+        rh = rbuf.cpu().numpy()
         res = {
             "B": B, "ldz": ldz, "K": Ks,
-            "gap": gap.cpu().numpy(), "primal": primal.cpu().numpy(),
-            "n_iter": n_iter.cpu().numpy(), "status": status.cpu().numpy(),
+            "gap": rh[: 8 * ncol].view(np.float64).reshape(F, ldz),
+            "primal": rh[8 * ncol: 16 * ncol].view(np.float64).reshape(F, ldz),
+            "n_iter": rh[16 * ncol: 20 * ncol].view(np.int32).reshape(F, ldz),
+            "status": rh[20 * ncol:].view(np.int32).reshape(F, ldz),
             "n_pass": n_pass, "iters_run": int(total_iters), "n_unconverged": int(bt.n_unconverged),
             "W1": W1, "W2": W2,
         }

@@ -267,10 +267,14 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
     fold_specs = specs if (len(specs) and isinstance(specs[0], (list, tuple))) else [specs] * F
     assert len(fold_specs) == F
     s0 = next(fs[0] for fs in fold_specs if len(fs))
-    grids = [stack_specs(fs) if len(fs) else _empty_like_grid(s0) for fs in fold_specs]
+    memo = {}  # an unsharded search solves the same candidate list on every fold
+    grids = []
+    for fs in fold_specs:
+        if id(fs) not in memo:
+            memo[id(fs)] = stack_specs(fs) if len(fs) else _empty_like_grid(s0)
+        grids.append(memo[id(fs)])
     Ks = [g.K for g in grids]
     used = [i for i in range(F) if Ks[i] > 0]
-    L = np.ones(F)
     wctx = None
     if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
         idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))
@@ -283,11 +287,12 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
         gptr = np.arange(s0.pe + 1) if s0.gptr is None else s0.gptr
         dl = s0.std_delta
         Gs, wctx = engine.whiten(Gs, s0.pe, gptr, n_obs, shift=None if dl is None else np.sqrt(dl), ridge=dl)
+    # step sizes stay on the device: nothing before the solver's first convergence check
+    # synchronises the host, so packing, Gram build and power iterations are enqueued back to back
     if Gs is not G:
-        L = engine.lipschitz(Gs, s0.pe) * engine.LIPSCHITZ_MARGIN / n_obs
+        L = engine.lipschitz_device(Gs, s0.pe).clamp_min(1e-300) * engine.to_device(engine.LIPSCHITZ_MARGIN / n_obs)
     else:
-        L[used] = fd.lipschitz(engine, [keys[i] for i in used])
-    fd.check_finite()  # the Lipschitz estimate synchronised: deferred input validation is free here
+        L = fd.lipschitz_dev(engine, keys, used)
     B_start = None
     if B0 is not None and s0.adaptive is None and not s0.standardize:
         ldz0 = max(8, (max(Ks) + 7) // 8 * 8)
@@ -295,6 +300,7 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
         B_start[0, :, 0] = B0
     res = engine.solve(Gs, s0.pe, n_obs, L, grids, B0=B_start, tol=tol, max_iter=max_iter,
                        check_every=check_every, floor_rel=floor_rel)
+    fd.check_finite()  # the solve synchronised: the deferred input validation is free here
     B = res["B"]
     ldz = res["ldz"]
     if wctx is not None:  # back to the caller's variables: b_g = R_g^{-1} gamma_g

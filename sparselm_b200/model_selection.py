@@ -194,14 +194,23 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         n_unconverged += int(out["n_unconverged"])
         iters_run += int(out["iters_run"])
     if shard is not None and shard.world > 1:
-        # the only data-path exchange of the sharded grid: sum the zero-padded tables
-        dev = engine.device
-        test_scores = shard.allreduce_sum_numpy(np.nan_to_num(test_scores, nan=0.0), dev)
+        # the only data-path exchange of the sharded grid: one sum of the zero-padded tables
+        tabs = [np.nan_to_num(test_scores, nan=0.0)]
         if train_scores is not None:
-            train_scores = shard.allreduce_sum_numpy(np.nan_to_num(train_scores, nan=0.0), dev)
-        for k in list(info):
-            info[k] = shard.allreduce_sum_numpy(info[k].astype(np.float64), dev).astype(info[k].dtype)
-        n_unconverged = int(shard.allreduce_sum_numpy(np.array([float(n_unconverged)]), dev)[0])
+            tabs.append(np.nan_to_num(train_scores, nan=0.0))
+        keys = list(info)
+        tabs += [info[k].astype(np.float64) for k in keys] + [np.array([[float(n_unconverged)]])]
+        flat = shard.allreduce_sum_numpy(np.concatenate([t.ravel() for t in tabs]), engine.device)
+        parts, o = [], 0
+        for t in tabs:
+            parts.append(flat[o:o + t.size].reshape(t.shape))
+            o += t.size
+        test_scores = parts.pop(0)
+        if train_scores is not None:
+            train_scores = parts.pop(0)
+        for k in keys:
+            info[k] = parts.pop(0).astype(info[k].dtype)
+        n_unconverged = int(round(float(parts.pop(0)[0, 0])))
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
                 info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm)
 

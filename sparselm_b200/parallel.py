@@ -2,9 +2,10 @@
 
 Two independent shardings compose:
 
-* rows    : every rank builds the per-fold Gram blocks of its own contiguous row
-            range only; one all-reduce(sum) of the [F, pa, pa] block array gives every
-            rank the complete test-fold Grams (NCCL over NVLink / NVSwitch).
+* rows    : every rank builds, for every test fold, the Gram block of its own 1/world
+            slice of that fold's rows; the block of fold f is all-reduced (NCCL over
+            NVLink / NVSwitch, asynchronously on NCCL's stream) while the tensor cores
+            build the block of fold f+1.
 * grid    : the (fold, alpha) problems are independent (the reference treats them as
             independent joblib tasks, model_selection.py:304-323).  Each rank solves a
             subset chosen so that it touches as few Grams as possible (fold-major
@@ -15,12 +16,25 @@ Two independent shardings compose:
 
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 __all__ = ["GridShard", "assign_columns"]
 
 
+@functools.lru_cache(maxsize=64)
+def _assign_columns_cached(n_folds: int, n_cols: int, world: int):
+    owner = _assign_columns(n_folds, n_cols, world)
+    owner.setflags(write=False)
+    return owner
+
+
 def assign_columns(n_folds: int, n_cols: int, world: int):
+    return _assign_columns_cached(int(n_folds), int(n_cols), int(world))
+
+
+def _assign_columns(n_folds: int, n_cols: int, world: int):
     """owner[f][k] in [0, world): rank that solves column k of fold f.
 
     Fold-major capacity ranges give the quota q[f][r] of fold f's columns owned by rank
@@ -50,8 +64,13 @@ class GridShard:
     def __init__(self, rank: int, world: int, group=None):
         self.rank, self.world, self.group = int(rank), int(world), group
 
-    def row_range(self, n: int):
-        return (self.rank * n) // self.world, ((self.rank + 1) * n) // self.world
+    def row_range(self, n: int, start: int = 0):
+        """This rank's contiguous slice of the rows [start, start + n)."""
+        return start + (self.rank * n) // self.world, start + ((self.rank + 1) * n) // self.world
+
+    def fold_row_ranges(self, row_ptr):
+        """Per test fold f (rows row_ptr[f]..row_ptr[f+1]) the slice this rank builds."""
+        return [self.row_range(int(row_ptr[f + 1] - row_ptr[f]), int(row_ptr[f])) for f in range(len(row_ptr) - 1)]
 
     def my_columns(self, n_folds: int, n_cols: int):
         """list over folds of the column indices this rank solves."""
@@ -66,6 +85,15 @@ class GridShard:
 
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
+
+    def allreduce_sum_async(self, tensor):
+        """Start an in-place sum over ranks; returns a handle whose wait() orders the current
+        stream after the collective (None when there is nothing to do)."""
+        if self.world == 1:
+            return None
+        import torch.distributed as dist
+
+        return dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def allreduce_sum_numpy(self, arr, device=None):
         """Sum over ranks of a (small) numpy array, returned as numpy."""

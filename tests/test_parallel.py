@@ -36,14 +36,20 @@ def test_row_ranges_partition_rows():
     ranges = [GridShard(r, 8).row_range(n) for r in range(8)]
     assert ranges[0][0] == 0 and ranges[-1][1] == n
     assert all(ranges[i][1] == ranges[i + 1][0] for i in range(7))
+    # what engine.prepare builds on every rank: its 1/world slice of EVERY test fold's rows
     row_ptr = np.array([0, 4001, 8001, 12002, 16002, 20003])
     covered = np.zeros(n, dtype=int)
-    for r0, r1 in ranges:
-        b = np.clip(row_ptr, r0, r1)  # what engine.prepare uses as the rank-local fold blocks
-        for f in range(5):
-            covered[b[f]:b[f + 1]] += 1
-            assert row_ptr[f] <= b[f] <= b[f + 1] <= row_ptr[f + 1] or b[f] == b[f + 1]
+    for r in range(8):
+        fr = GridShard(r, 8).fold_row_ranges(row_ptr)
+        assert len(fr) == 5
+        for f, (lo, hi) in enumerate(fr):
+            assert row_ptr[f] <= lo <= hi <= row_ptr[f + 1]
+            assert abs((hi - lo) - (row_ptr[f + 1] - row_ptr[f]) / 8) < 1  # balanced per fold
+            covered[lo:hi] += 1
     assert np.all(covered == 1)
+    # more ranks than rows in a fold: empty slices are fine
+    fr = [GridShard(r, 8).fold_row_ranges(np.array([0, 3, 5])) for r in range(8)]
+    assert sum(hi - lo for ranges_ in fr for lo, hi in ranges_) == 5
 
 
 def _free_port():

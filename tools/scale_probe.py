@@ -96,6 +96,14 @@ for _ in range(reps):
 out = {"rank": rank, "world": world, "plain_step_ms": plain_ms, "instrumented_step_ms": float(np.mean(tot)),
        "phases_ms": {k: v / reps for k, v in acc.items()}, "iters": int(res["iters_run"])}
 out["phases_ms"]["other(host+unwrapped)"] = out["instrumented_step_ms"] - sum(out["phases_ms"].values())
+if world > 1:
+    # the sharded search must reproduce the single-process score table
+    for nm in ("pack", "gram_blocks", "gram_complement", "gram_center", "lipschitz", "solve", "cv_score"):
+        pass
+    ref = batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error")
+    err = float(np.abs(ref["test_scores"] - res["test_scores"]).max() / np.abs(ref["test_scores"]).max())
+    out["sharded_vs_single_rel_err"] = err
+    assert err < 1e-8, err
 for r in range(world):
     barrier()
     if r == rank:
