@@ -1,7 +1,7 @@
 """Benchmark of the hot path: CV grid fits/sec (alpha x fold), device-timed.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
-                    [--workload c3|c2|c1|c4]
+                    [--workload c3|c2|c1|c4|c5]
 
 One "step" = one full cross-validated grid search of the workload (every
 (alpha, fold) problem solved to the duality-gap tolerance and scored).
@@ -91,6 +91,18 @@ def workload(name):
         est = AdaptiveOverlapGroupLasso(group_list=group_list, solver_options={"tol": TOL, "max_iter": 50000})
         desc = "AdaptiveOverlapGroupLasso, 30% overlap, 3 reweight passes, 20 alphas x 5 folds, n=5000 p=1500 (configs[3])"
         oracle = dict(name="AdaptiveOverlapGroupLasso", group_list=group_list)
+    elif name == "c5":
+        # tall design: X (25.6 GB) is generated on the device of every rank from the same seed
+        from sparselm_b200.model import RidgedGroupLasso
+
+        n, p, G, K, F = 400000, 8000, 400, 100, 5
+        rng = np.random.default_rng(3)
+        groups = rng.permutation(np.repeat(np.arange(G), p // G))
+        est = RidgedGroupLasso(groups=groups, delta=(1.0,), solver_options=opts)
+        desc = ("RidgedGroupLasso tall design, 400 groups, delta=1, 100 alphas x 5 folds, n=400000 p=8000, "
+                "X row-sharded with an NCCL Gram all-reduce (BASELINE configs[4])")
+        return dict(X=None, y=None, est=est, alphas=None, F=F, desc=desc, name=name, n=n, p=p, K=K,
+                    device_gen=True, oracle=dict(name="RidgedGroupLasso", groups=groups, delta=(1.0,)))
     else:
         raise SystemExit(f"unknown workload {name}")
     alpha_max = np.abs(X.T @ y).max() / n
@@ -151,10 +163,32 @@ class ClockSampler:
 # --------------------------------------------------------------------------- #
 # CPU baseline: the oracle on a bounded sample, all host threads
 # --------------------------------------------------------------------------- #
+def device_data(wl, torch, dev):
+    """make_regression-style data generated on the device (same seed on every rank => the
+    same matrix): X ~ N(0,1), p/10 informative coefficients 100 U(0,1), noise 10."""
+    n, p, K = wl["n"], wl["p"], wl["K"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)
+    X = torch.empty((n, p), dtype=torch.float64, device=dev)
+    step = 1 << 15
+    for r in range(0, n, step):  # row chunks keep the generator's scratch small
+        X[r:r + step].normal_(generator=g)
+    w = torch.zeros(p, dtype=torch.float64, device=dev)
+    idx = torch.randperm(p, generator=g, device=dev)[: p // 10]
+    w[idx] = 100.0 * torch.rand(p // 10, generator=g, device=dev, dtype=torch.float64)
+    y = X @ w + 10.0 * torch.randn(n, generator=g, device=dev, dtype=torch.float64)
+    alpha_max = float((X.T @ y).abs().max().item()) / n
+    wl["X"], wl["y"] = X, y.cpu().numpy()
+    wl["alphas"] = alpha_max * np.logspace(0, -3, K)
+    return wl
+
+
 def cpu_sample_problem(wl, n_fits):
     """One training fold + n_fits alphas spread over the grid, as inputs of slmo_bcd_many."""
     import oracle.reference as R
 
+    if wl.get("device_gen"):
+        return None
     X, y, o = wl["X"], wl["y"], wl["oracle"]
     n, p = X.shape
     te = np.arange(0, n // wl["F"])  # fold 0 of KFold(F)
@@ -297,11 +331,13 @@ def run_engine(args):
     from sparselm_b200.model_selection import GridSearchCV, batched_cv
 
     wl = workload(args.workload)
+    engine = get_engine(local)
+    dev = engine.device
+    if wl.get("device_gen"):
+        wl = device_data(wl, torch, dev)
     X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
     n, p = X.shape
     n_fits = len(alphas) * F
-    engine = get_engine(local)
-    dev = engine.device
     shard = None
     if world > 1:
         from sparselm_b200.parallel import GridShard
@@ -311,8 +347,8 @@ def run_engine(args):
     peak = measure_fp64_peak(torch, dev)
 
     # ---- device-resident arm ------------------------------------------------------
-    Xd = torch.from_numpy(X).to(dev)
-    folds = [te for _, te in KFold(F).split(X)]
+    Xd = X if isinstance(X, torch.Tensor) else torch.from_numpy(X).to(dev)
+    folds = [te for _, te in KFold(F).split(np.empty((n, 1)))]
     ests = [clone(est).set_params(alpha=a) for a in alphas]
     specs = [e._problem_spec(p) for e in ests]
     opts = est._engine_options()
@@ -363,6 +399,21 @@ def run_engine(args):
     value = n_fits / (ms / 1e3)
 
     # ---- end-to-end arm: public API on host (pinned) arrays --------------------------
+    if wl.get("device_gen"):
+        e2e = None  # 25.6 GB design generated on the device: no host copy to start from
+    else:
+        e2e = run_e2e(args, torch, wl, shard, barrier, world, dev)
+    finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank)
+
+
+def run_e2e(args, torch, wl, shard, barrier, world, dev):
+    from sklearn.base import clone
+
+    from sparselm_b200.model_selection import GridSearchCV
+
+    X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
+    n, p = X.shape
+    n_fits = len(alphas) * F
     Xp = torch.from_numpy(X).pin_memory()
     Xh = Xp.numpy()
     grid = {"alpha": list(alphas)}
@@ -392,9 +443,18 @@ def run_engine(args):
         e2e_ms = float(t.item())
     h2d = X.nbytes + y.nbytes
     d2h = 8 * (n_fits * 2 + n_fits + p + 1)  # residual sums, per-fit info, refit coefficients
+    return {"value": n_fits / (e2e_ms / 1e3), "unit": "fits/s", "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "api": "sparselm_b200.model_selection.GridSearchCV.fit (pinned host X, refit included)"}
 
+
+def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank):
     if rank != 0:
         return
+    X, alphas, F = wl["X"], wl["alphas"], wl["F"]
+    n, p = X.shape
+    n_fits = len(alphas) * F
+    xbytes = n * p * 8
     ap = tim["gram_apply"]
     apply_ms = ap["ms"] / max(ap["launches"], 1)
     # the row-sparse apply contracts only over the support rows of each column chunk:
@@ -408,6 +468,23 @@ def run_engine(args):
         traffic = json.load(open(tpath)).get(args.workload, {}).get("gram_apply_dram_bytes_per_launch")
     step_ms = {k: v["ms"] / args.steps for k, v in tim.items()}
     info = res["info"]
+    gb = tim["gram_build"]
+    build_tf = gb["flops"] / (gb["ms"] * 1e-3) / 1e12 if gb["ms"] > 0 else None
+    src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
+    if gb["ms"] > ap["ms"]:
+        # tall designs: the dominant kernel is the Gram build (SYRK count n pa (pa+1))
+        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel<SYM> (Gram build, FP64 DMMA, SYRK flop count)",
+                "achieved": build_tf, "peak": peak, "unit": "TFLOP/s", "frac": build_tf / peak if build_tf else None,
+                "peak_source": src, "avg_launch_ms": gb["ms"] / max(gb["launches"], 1),
+                "launches_per_step": gb["launches"] / args.steps, "traffic": None,
+                "gram_apply_tflops": achieved, "step_ms_by_kernel_family": step_ms}
+    else:
+        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (row-sparse Gram apply, FP64 DMMA)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "peak_source": src, "dense_equivalent_tflops": dense_equiv,
+                "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
+                "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
+                "traffic": traffic, "gram_build_tflops": build_tf, "step_ms_by_kernel_family": step_ms}
     line = {
         "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
@@ -416,18 +493,10 @@ def run_engine(args):
                    "iterations_per_step": int(res["iters_run"]), "mean_iterations_per_fit": float(info["n_iter"].mean()),
                    "unconverged": int(res["n_unconverged"]),
                    "l2": "inputs larger than L2 between iterations (X %.0f MB, fold Grams %.0f MB vs 126 MB L2)"
-                         % (X.nbytes / 1e6, (F + 1) * (p + 8) ** 2 * 8 / 1e6),
-                   "parallelism": f"grid-sharded x{world}" if world > 1 else "single GPU"},
-        "roofline": {"bound": "tensor", "kernel": "gemm_f64_kernel (row-sparse Gram apply, FP64 DMMA)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                     "dense_equivalent_tflops": dense_equiv,
-                     "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
-                     "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
-                     "traffic": traffic, "step_ms_by_kernel_family": step_ms},
-        "e2e": {"value": n_fits / (e2e_ms / 1e3), "unit": "fits/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "sparselm_b200.model_selection.GridSearchCV.fit (pinned host X, refit included)"},
+                         % (xbytes / 1e6, (F + 1) * (p + 8) ** 2 * 8 / 1e6),
+                   "parallelism": f"rows (Gram build) + grid (solve) sharded x{world}" if world > 1 else "single GPU"},
+        "roofline": roof,
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -442,7 +511,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup

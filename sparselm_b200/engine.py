@@ -409,9 +409,12 @@ class Engine:
             sizes = [len(t) for t in test_folds]
             row_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
             perm = np.concatenate([np.asarray(t, dtype=np.int64) for t in test_folds])
-            if len(perm) != n or not np.array_equal(np.sort(perm), np.arange(n)):
+            ident = np.arange(n)
+            if len(perm) != n:
                 raise ValueError("test_folds must partition the rows")
-            if not np.array_equal(perm, np.arange(n)):
+            if not np.array_equal(perm, ident):  # KFold without shuffling is the identity: no sort needed
+                if not np.array_equal(np.sort(perm), ident):
+                    raise ValueError("test_folds must partition the rows")
                 row_perm = perm
         sw = None
         if sample_weight is not None:

@@ -62,11 +62,14 @@ class ProblemSpec:
         """Scalar penalty strength used to order the columns of a batch: weakly penalised
         problems have the densest iterates, and the row-sparse Gram apply works on chunks of
         adjacent columns, so columns of similar strength should sit together."""
-        s = float(self.lam1)
-        if self.w2 is not None and len(self.w2):
-            s += float(np.mean(self.w2))
-        if self.adaptive is not None:
-            s += float(self.adaptive["alpha"])
+        s = self.__dict__.get("_strength")
+        if s is None:
+            s = float(self.lam1)
+            if self.w2 is not None and len(self.w2):
+                s += float(self.w2.sum()) / len(self.w2)
+            if self.adaptive is not None:
+                s += float(self.adaptive["alpha"])
+            self.__dict__["_strength"] = s
         return s
 
 

@@ -31,6 +31,7 @@ def _assign_columns_cached(n_folds: int, n_cols: int, world: int):
 
 
 def assign_columns(n_folds: int, n_cols: int, world: int):
+    """owner[f][k] in [0, world): rank that solves column k of fold f (read-only, cached)."""
     return _assign_columns_cached(int(n_folds), int(n_cols), int(world))
 
 
