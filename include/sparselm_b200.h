@@ -169,10 +169,14 @@ int slm_fold_back(slm_ctx* ctx, const double* Bext_dev, const int32_t* inv_ptr_d
 /* ---- K10: CV scoring (sklearn scorer inside _fit_and_score, model_selection.py:305)
  * rows [r0, r1) of Xa are the test fold; B [p][ldz]; intercept[k] may be NULL.
  * out_dev[0][k] = sum (y - yhat)^2, out_dev[1][k] = sum |y - yhat|  (ldz stride).
+ * rows_scaled != 0: the rows were packed with sample weights (sqrt(sw_i) [x_i, y_i, 1]) and the
+ * scorer is unweighted, as sklearn's is for fit_params (model_selection.py:266): residuals are
+ * divided by the row's sqrt(sw_i) column (all weights must be > 0).
  * yhat_dev: scratch [(r1-r0) + 256][ldz] (predictions, then partial sums). */
 int slm_cv_score(slm_ctx* ctx, const double* Xa_dev, int64_t lda, int64_t p, int64_t r0,
                  int64_t r1, const double* B_dev, int64_t ldz, int32_t K,
-                 const double* intercept_dev, double* yhat_dev, double* out_dev, void* stream);
+                 const double* intercept_dev, int32_t rows_scaled, double* yhat_dev,
+                 double* out_dev, void* stream);
 
 /* intercept[k] = ybar - mu^T B[:,k] from the (uncentred) training Gram's ones row
  * (LinearModel._set_intercept, _base.py:202). */

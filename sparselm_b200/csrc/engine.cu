@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const double* __rest
                                                             long long r0, long long m,
                                                             const double* __restrict__ yhat, long long ldz,
                                                             int K, const double* __restrict__ icpt,
-                                                            double* __restrict__ part) {
+                                                            int rows_scaled, double* __restrict__ part) {
     // block = 8 columns x 32 row lanes; grid = (ceil(K/8), SCORE_RB)
     const int c = threadIdx.x & 7, r = threadIdx.x >> 3;
     const int k = blockIdx.x * 8 + c;
@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(256) score_partial_kernel(const double* __rest
         const double b0 = icpt ? icpt[k] : 0.0;
         for (long long i = (long long)blockIdx.y * 32 + r; i < m; i += (long long)SCORE_RB * 32) {
             const double* row = Xa + (r0 + i) * lda;
-            const double d = row[p] - yhat[i * ldz + k] - b0 * row[p + 1];
+            double d = row[p] - yhat[i * ldz + k] - b0 * row[p + 1];
+            // rows packed as sqrt(sw_i) [x_i, y_i, 1]: the scorer wants the unweighted residual
+            if (rows_scaled) d /= row[p + 1];
             sse += d * d;
             sae += fabs(d);
         }
@@ -1278,8 +1280,8 @@ int slm_fold_back(slm_ctx* ctx, const double* Be, const int32_t* inv_ptr, const 
 }
 
 int slm_cv_score(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int64_t r0, int64_t r1,
-                 const double* B, int64_t ldz, int32_t K, const double* icpt, double* yhat, double* out,
-                 void* stream) {
+                 const double* B, int64_t ldz, int32_t K, const double* icpt, int32_t rows_scaled, double* yhat,
+                 double* out, void* stream) {
     if (!ctx || !Xa || !B || !yhat || !out) return fail(ctx, 1, "slm_cv_score: null argument");
     if (ldz % 8) return fail(ctx, 1, "slm_cv_score: ldz must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
@@ -1308,7 +1310,7 @@ int slm_cv_score(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int64_t
     }
     double* part = yhat + m * ldz;
     dim3 grid((unsigned)((K + 7) / 8), SCORE_RB);
-    score_partial_kernel<<<grid, 256, 0, s>>>(Xa, lda, (int)p, r0, m, yhat, ldz, K, icpt, part);
+    score_partial_kernel<<<grid, 256, 0, s>>>(Xa, lda, (int)p, r0, m, yhat, ldz, K, icpt, rows_scaled, part);
     LAUNCH_OK("score_partial_kernel");
     score_final_kernel<<<(unsigned)((K + 127) / 128), 128, 0, s>>>(part, ldz, K, out);
     LAUNCH_OK("score_final_kernel");

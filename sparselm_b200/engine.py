@@ -799,15 +799,17 @@ class Engine:
                                          self._ptr(out), self.stream), "slm_intercepts")
         return out
 
-    def cv_score(self, Xa, p, r0, r1, B, K, intercept=None):
-        """(sse[K], sae[K]) of the rows [r0, r1) of Xa for the K columns of B."""
+    def cv_score(self, Xa, p, r0, r1, B, K, intercept=None, rows_scaled=False):
+        """(sse[K], sae[K]) of the rows [r0, r1) of Xa for the K columns of B (unweighted
+        residuals; rows_scaled: Xa was packed with sample weights)."""
         torch = self.torch
         ldz = B.shape[-1]
         m = int(r1 - r0)
         yhat = torch.empty((m + 256, ldz), dtype=torch.float64, device=self.device)
         out = torch.zeros((2, ldz), dtype=torch.float64, device=self.device)
         self._ck(self.lib.slm_cv_score(self.h, self._ptr(Xa), Xa.shape[1], p, int(r0), int(r1), self._ptr(B), ldz,
-                                       K, self._ptr(intercept), self._ptr(yhat), self._ptr(out), self.stream),
+                                       K, self._ptr(intercept), 1 if rows_scaled else 0, self._ptr(yhat),
+                                       self._ptr(out), self.stream),
                  "slm_cv_score")
         return out
 

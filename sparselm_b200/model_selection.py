@@ -95,7 +95,7 @@ def _fold_key(est, spec):
     return (bool(est.fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
 
 
-def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=None, shard=None):
+def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=None, shard=None, sample_weight=None):
     """Device-resident design + Grams for (fit_intercept, column order) of `est`/`spec`,
     through the FoldData cache of a LineSearchCV when there is one.  Only enqueues GPU
     work (H2D copies, packing, Gram build): the caller can keep working on the host."""
@@ -105,14 +105,14 @@ def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=No
               tuple(int(t[0]) for t in test_folds))
         if ck in cache:
             return cache[ck]
-    fd = engine.prepare(X, yv, test_folds, est.fit_intercept, None, col_perm=spec.col_perm, shard=shard)
+    fd = engine.prepare(X, yv, test_folds, est.fit_intercept, sample_weight, col_perm=spec.col_perm, shard=shard)
     if ck is not None:
         cache[ck] = fd
     return fd
 
 
 def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_train_score=False, cache=None,
-               cache_key=None, shard=None, fds=None):
+               cache_key=None, shard=None, fds=None, sample_weight=None):
     """Solve every (candidate, fold) problem as device batches and score them.
 
     X: (n, p) numpy array or torch tensor (host, pinned or already on the device);
@@ -120,6 +120,8 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     ests/specs: one configured estimator and its ProblemSpec per candidate.
     shard: optional parallel.GridShard -- this rank builds the Gram of its rows, solves
     its share of the (fold, candidate) grid, and the score tables are summed over ranks.
+    sample_weight: optional (n,) strictly positive fit weights, split per fold like the
+    reference's fit_params (model_selection.py:266); the scores stay unweighted.
     Returns test_scores [n_cand, n_splits] (+ train scores, timings, solver info and
     the device-resident FoldData objects keyed by (fit_intercept, column order)).
     """
@@ -147,7 +149,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         s0, e0 = specs[idxs[0]], ests[idxs[0]]
         fkey = _fold_key(e0, s0)
         if fkey not in fds:
-            fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard)
+            fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard, sample_weight)
         fd = fds[fkey]
         t0 = time.perf_counter()
         # batch columns in order of increasing penalty strength (dense iterates first): the
@@ -164,7 +166,9 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
                 warm.setdefault(int(idxs[k]), out["B"][f, :, pos])
         K = len(idxs)
         icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
-        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f))
+        wtd = bool(fd.extra.get("weighted"))
+        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f),
+                                  rows_scaled=wtd)
                   for f in range(n_splits)]
         sc = engine.torch.stack(sc_dev).cpu().numpy()  # one D2H for all folds
         if train_scores is not None:
@@ -173,7 +177,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
                 for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
                     if r1 > r0 and len(mine[f]):
                         tsc[f] += engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], len(mine[f]),
-                                                  icpt(f)).cpu().numpy()
+                                                  icpt(f), rows_scaled=wtd).cpu().numpy()
         t2 = time.perf_counter()
         for f in range(n_splits):
             nt = len(test_folds[f])
@@ -261,8 +265,15 @@ class GridSearchCV(_SkGridSearchCV):
         est = self.estimator
         if not isinstance(est, EngineRegressor) or y is None:
             return None
-        if any(v is not None for v in params.values()):
-            return None
+        # fit params: only sample_weight is understood by the batched seam (strictly positive:
+        # the unweighted CV scores are recovered from the sqrt(sw)-scaled rows)
+        sw = None
+        for k, v in params.items():
+            if v is None:
+                continue
+            if k != "sample_weight":
+                return None
+            sw = v
         if not (self.scoring is None or (isinstance(self.scoring, str) and self.scoring in _DEVICE_SCORERS)):
             return None
         if callable(self.refit) or hasattr(X, "columns"):
@@ -276,6 +287,13 @@ class GridSearchCV(_SkGridSearchCV):
         except Exception:
             return None
         n, p = Xv.shape
+        if sw is not None:
+            try:
+                sw = np.asarray(sw, dtype=np.float64).reshape(-1)
+            except Exception:
+                return None
+            if sw.shape[0] != n or not np.all(np.isfinite(sw)) or not np.all(sw > 0):
+                return None
         cv = check_cv(self.cv, yv, classifier=False)
         splits = list(cv.split(Xv, yv, None))
         if len(splits) < 2 or len(splits) > 15 or not _is_partition(splits, n):
@@ -309,13 +327,14 @@ class GridSearchCV(_SkGridSearchCV):
                     cache = getattr(self, "_fd_cache", None)
                     pre_fds[_fold_key(ests[0], specs[0])] = prepare_folds(
                         engine, Xv, yv, [np.asarray(test) for _, test in splits], ests[0], specs[0], cache,
-                        None if cache is None else (id(Xv), id(yv)), getattr(self, "_shard", None))
+                        None if cache is None else (id(Xv), id(yv), None if sw is None else sw.tobytes()),
+                        getattr(self, "_shard", None), sw)
         except (NotImplementedError, EngineError):
             raise
         except Exception:
             return None  # sklearn's loop applies error_score semantics per candidate
         return dict(X=Xv, y=yv, n=n, p=p, splits=splits, candidates=candidates, ests=ests, specs=specs,
-                    fds=pre_fds)
+                    fds=pre_fds, sample_weight=sw)
 
     def _fit_batched(self, plan):
         Xv, yv, n, p = plan["X"], plan["y"], plan["n"], plan["p"]
@@ -327,10 +346,11 @@ class GridSearchCV(_SkGridSearchCV):
         scoring = self.scoring if self.scoring is not None else "r2"
         test_folds = [np.asarray(test) for _, test in splits]
         cache = getattr(self, "_fd_cache", None)
-        cache_key = None if cache is None else (id(plan["X"]), id(plan["y"]))
+        sw = plan.get("sample_weight")
+        cache_key = None if cache is None else (id(plan["X"]), id(plan["y"]), None if sw is None else sw.tobytes())
         res = batched_cv(engine, Xv, yv, test_folds, ests, specs, opts, scoring,
                          return_train_score=self.return_train_score, cache=cache, cache_key=cache_key,
-                         shard=getattr(self, "_shard", None), fds=plan.get("fds"))
+                         shard=getattr(self, "_shard", None), fds=plan.get("fds"), sample_weight=sw)
         test_scores, train_scores = res["test_scores"], res["train_scores"]
         fit_time, score_time, info, fds = res["fit_time"], res["score_time"], res["info"], res["fds"]
         if res["n_unconverged"]:

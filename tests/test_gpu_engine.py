@@ -315,6 +315,12 @@ def test_cv_score_and_intercepts(engine):
     resid = y[r0:r1, None] - X[r0:r1] @ Bh[:, :K] - ref_icpt[None, :]
     np.testing.assert_allclose(out[0, :K], (resid ** 2).sum(0), rtol=1e-11)
     np.testing.assert_allclose(out[1, :K], np.abs(resid).sum(0), rtol=1e-11)
+    # rows packed with sample weights: the scorer still sees unweighted residuals
+    sw = 0.3 + rng.random(n)
+    Xw = engine.pack(X, y, sample_weight=sw)
+    outw = engine.cv_score(Xw, p, r0, r1, B, K, icpt, rows_scaled=True).cpu().numpy()
+    np.testing.assert_allclose(outw[0, :K], (resid ** 2).sum(0), rtol=1e-11)
+    np.testing.assert_allclose(outw[1, :K], np.abs(resid).sum(0), rtol=1e-11)
 
 
 def test_overlap_gather_and_fold_back(engine):

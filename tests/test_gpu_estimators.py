@@ -338,6 +338,47 @@ def test_grid_search_matches_per_fit_oracle(fit_intercept):
     npt.assert_allclose(sk.cv_results_["mean_test_score"], ref.mean(1)[:3], rtol=1e-8)
 
 
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_grid_search_with_sample_weight_is_batched_and_matches_oracle(fit_intercept):
+    """fit_params are split per fold and reach fit only; scores stay unweighted
+    (reference model_selection.py:266, sklearn _fit_and_score)."""
+    from sklearn.model_selection import KFold
+
+    rng = np.random.default_rng(12)
+    n, p = 140, 24
+    X = rng.standard_normal((n, p))
+    y = X[:, :4] @ [2.0, -1.0, 1.0, 0.5] + 0.4 * rng.standard_normal(n) + (0.8 if fit_intercept else 0.0)
+    sw = 0.2 + 2.0 * rng.random(n)
+    groups = rng.permutation(np.repeat(np.arange(6), 4))
+    alphas = np.logspace(-2.5, -0.3, 6)
+    est = SparseGroupLasso(groups=groups, l1_ratio=0.4, fit_intercept=fit_intercept, solver_options={"tol": 1e-12})
+    gs = GridSearchCV(est, {"alpha": alphas}, cv=4, return_train_score=True).fit(X, y, sample_weight=sw)
+    assert gs.batched_
+    ref = np.zeros((len(alphas), 4))
+    ref_tr = np.zeros((len(alphas), 4))
+    for f, (tr, te) in enumerate(KFold(4).split(X)):
+        for i, a in enumerate(alphas):
+            b, icpt = R.fit("SparseGroupLasso", X[tr], y[tr], alpha=a, groups=groups, l1_ratio=0.4,
+                            fit_intercept=fit_intercept, sample_weight=sw[tr])
+            ref[i, f] = -np.sqrt(np.mean((y[te] - X[te] @ b - icpt) ** 2))
+            ref_tr[i, f] = -np.sqrt(np.mean((y[tr] - X[tr] @ b - icpt) ** 2))
+    got = np.stack([gs.cv_results_[f"split{i}_test_score"] for i in range(4)], axis=1)
+    got_tr = np.stack([gs.cv_results_[f"split{i}_train_score"] for i in range(4)], axis=1)
+    npt.assert_allclose(got, ref, rtol=1e-8, atol=1e-10)
+    npt.assert_allclose(got_tr, ref_tr, rtol=1e-8, atol=1e-10)
+    best = int(np.argmax(ref.mean(1)))
+    assert gs.best_index_ == best
+    b_ref, i_ref = R.fit("SparseGroupLasso", X, y, alpha=alphas[best], groups=groups, l1_ratio=0.4,
+                         fit_intercept=fit_intercept, sample_weight=sw)
+    assert np.abs(gs.best_estimator_.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+    assert abs(gs.best_estimator_.intercept_ - i_ref) <= 1e-7 * max(1.0, abs(i_ref))
+    # zero weights cannot be un-scaled on the device: sklearn's per-fit path takes over
+    sw0 = sw.copy()
+    sw0[::7] = 0.0
+    g0 = GridSearchCV(est, {"alpha": alphas[:2]}, cv=4).fit(X, y, sample_weight=sw0)
+    assert not g0.batched_
+
+
 def test_grid_search_two_parameters_and_r2_default_scoring():
     rng = np.random.default_rng(9)
     X = rng.standard_normal((100, 20))
