@@ -63,6 +63,7 @@ struct slm_ctx {
     double apply_dense_flops = 0.0;  // 2 p^2 K_active of the same applies
     int chunk_w = 32;                // columns per support chunk (SLM_CHUNK_W)
     bool dense_apply = false;        // SLM_DENSE_APPLY=1: solver uses the dense apply (A/B runs)
+    bool small_fused = true;         // SLM_SMALL_FUSED=0: never use the fused small-design iterations
     int force_sparse_shape = -1;     // SLM_FORCE_SPARSE_SHAPE
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
@@ -716,6 +717,7 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_FORCE_SPARSE_SHAPE")) ctx->force_sparse_shape = atoi(e);
     if (const char* e = getenv("SLM_CHUNK_W")) ctx->chunk_w = std::max(8, atoi(e) / 8 * 8);
     if (const char* e = getenv("SLM_DENSE_APPLY")) ctx->dense_apply = atoi(e) != 0;
+    if (const char* e = getenv("SLM_SMALL_FUSED")) ctx->small_fused = atoi(e) != 0;
     ctx->n_flags_cap = 1 << 20;
     if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
@@ -1022,7 +1024,10 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     int* sidx = newK + 64;                  // [F][ncc][p]
     int* scount = sidx + (size_t)F * ncc * p;  // [F][ncc]
     unsigned char* zflag = (unsigned char*)(newK + 64 + (size_t)F * (ldz / 8) * (p + 1));
-    const bool sparse = !ctx->dense_apply;
+    // small designs: the iterations between two convergence checks run inside one kernel
+    // (fista_small_kernel, Gram in shared memory); the checks use the regular dense path
+    const bool small = ctx->small_fused && p <= kSmallPMax;
+    const bool sparse = !ctx->dense_apply && !small;
 
     SolveDev sp;
     memset(&sp, 0, sizeof(sp));
@@ -1137,9 +1142,32 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         const double tw = std::max(fw / (0.776 * 35e12), bw / 6.0e12);
         wide = (fn == 0.0) || (tw < tn);
     };
+    int next_check = 0, interval = check_every;  // small mode: checks get rarer while nothing converges
+    const int p32 = (int)round_up(p, 32);
+    const int nsplit = std::max(1, std::min(8, 256 / p32));
+    const size_t small_smem = fista_small_smem((int)p, p32, nsplit);
+    if (small) {
+        CUDA_OK(cudaFuncSetAttribute(fista_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)small_smem));
+        CUDA_OK(cudaFuncSetAttribute(fista_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)small_smem));
+    }
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
-        const bool check = (it % check_every == 0);
+        const bool check = small ? (it == next_check) : (it % check_every == 0);
+        if (small && !check) {
+            // every iteration up to the next check (or max_iter) in one launch
+            const int n_inner = std::min(next_check, (int)bt->max_iter) - it;
+            FamTimer tm(ctx, FAM_PROX, s, 0.0);
+            const dim3 sgrid((unsigned)Kmax, (unsigned)F);
+            if (grouped)
+                fista_small_kernel<true><<<sgrid, p32 * nsplit, small_smem, s>>>(sp, par, n_inner, p32, nsplit);
+            else
+                fista_small_kernel<false><<<sgrid, p32 * nsplit, small_smem, s>>>(sp, par, n_inner, p32, nsplit);
+            LAUNCH_OK("fista_small_kernel");
+            it += n_inner - 1;
+            continue;
+        }
         double algo = 2.0 * (double)p * (double)p * (double)n_active;
         // the supports change fastest in the first iterations (a cold start is all-zero, then
         // every weakly penalised column fills up): re-decide the width there without waiting
@@ -1179,7 +1207,11 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
                 if (round_up(n_active_f[f], 8) < round_up(Kcur[f], 8)) shrink = true;
             }
             if (n_active == 0) break;
-            do_compact = shrink;
+            do_compact = shrink && !small;  // idle CTAs of the fused kernel exit at once: no compaction
+            if (small) {  // checks at 0, c, 3c, 7c, ... (c = check_every), at most 2048 apart
+                next_check = it + interval;
+                interval = std::min(interval * 2, 2048);
+            }
             if (can_adapt) decide_width();
         }
         {

@@ -252,7 +252,10 @@ def _empty_like_grid(s0):
                        D2=None if s0.d2 is None else np.zeros((G, 0)), adaptive=ad)
 
 
-def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, check_every=10,
+SMALL_P = 160  # designs up to this many (expanded) features iterate inside one fused kernel
+
+
+def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, check_every=10,
                 floor_rel=1e-14, B0=None):
     """Solve problems (equal structure keys) on every training Gram of `fd` (or on its
     full Gram when use_full) as one engine batch.  `specs` is either one list (the same
@@ -301,6 +304,10 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=20000, ch
         ldz0 = max(8, (max(Ks) + 7) // 8 * 8)
         B_start = torch.zeros((F, s0.pe, ldz0), dtype=torch.float64, device=engine.device)
         B_start[0, :, 0] = B0
+    if max_iter is None:
+        # fused small-design iterations cost ~0.3 us each: ill-conditioned small problems (p > n,
+        # vanishing penalties) get the iterations plain accelerated proximal gradient needs
+        max_iter = 1000000 if s0.pe <= SMALL_P else 20000
     res = engine.solve(Gs, s0.pe, n_obs, L, grids, B0=B_start, tol=tol, max_iter=max_iter,
                        check_every=check_every, floor_rel=floor_rel)
     fd.check_finite()  # the solve synchronised: the deferred input validation is free here

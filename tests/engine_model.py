@@ -110,7 +110,7 @@ def solve(pb: BatchProblem, tol=1e-10, floor_rel=1e-14, max_iter=20000, check_ev
     tmom = np.ones(K)
     done = np.zeros(K, bool)
     iters = np.zeros(K, int)
-    floor = floor_rel * pb.yty / (2 * pb.n)
+    floor = max(floor_rel, 4e-15 / tol) * pb.yty / (2 * pb.n)  # rounding floor of the Gram-form gap
     gap = np.full(K, np.inf)
     for it in range(max_iter):
         GZ = pb.G @ Z

@@ -255,9 +255,13 @@ def test_solve_multi_fold_batch_and_model_iterations(engine):
         pb = M.BatchProblem(G, Xt.T @ yt, yt @ yt, len(tr), gptr, np.tile(grid.lam1, (p, 1)), grid.W2,
                             np.zeros_like(grid.W2), L=fd.lipschitz(engine, f))
         Bm, info = M.solve(pb, tol=1e-11)
-        # same algorithm => same iteration counts (up to reduction-order ties) and same answer
-        assert np.abs(B[f][:, :20] - Bm).max() <= 1e-8 * np.abs(Bm).max()
-        assert np.abs(res["n_iter"][f, :20] - info["iters"]).max() <= 10
+        # same algorithm => same answer; p <= 160 runs the fused small-design kernel, whose
+        # convergence checks sit at iterations 0, 10, 30, 70, 150, ...: a column is flagged at the
+        # first check at or after the model's (which checks every 10 iterations)
+        assert np.abs(B[f][:, :20] - Bm).max() <= 1e-7 * np.abs(Bm).max()
+        checks = np.array([0, 10, 30, 70, 150, 310, 630])
+        expect = checks[np.searchsorted(checks, info["iters"] - 10)]
+        assert (res["n_iter"][f, :20] >= expect).all() and (res["n_iter"][f, :20] <= 2 * info["iters"] + 20).all()
         for k in (0, 10, 19):
             b_ref, _ = R.solve(Xt, yt, _oracle_pen(grid, k), tol=1e-14)
             assert np.abs(B[f][:, k] - b_ref).max() <= 1e-6 * max(np.abs(b_ref).max(), 1e-12)

@@ -430,9 +430,12 @@ def test_readme_example_adaptive_lasso_grid():
 
     X, y = make_regression(n_samples=100, n_features=80, n_informative=10, random_state=0)
     alphas = np.logspace(-8, 2, 10)
-    opts = {"tol": 1e-10, "max_iter": 200000}
-    gs = GridSearchCV(AdaptiveLasso(fit_intercept=False, solver_options=opts), {"alpha": alphas}, scoring=None,
-                      cv=5).fit(X, y)
+    opts = {"tol": 1e-10}
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # in particular: no ConvergenceWarning on the README grid
+        gs = GridSearchCV(AdaptiveLasso(fit_intercept=False, solver_options=opts), {"alpha": alphas}, scoring=None,
+                          cv=5).fit(X, y)
+    assert (gs.solver_info_["status"] == 0).all()
     mean = gs.cv_results_["mean_test_score"]
     # oracle per cell
     ref = _cv_reference("AdaptiveLasso", X, y, alphas, 5, scoring="r2")
