@@ -75,7 +75,7 @@ def workload(name):
 
         n, p, K, F = 100, 80, 10, 5
         X, y = make_regression(n_samples=100, n_features=80, n_informative=10, random_state=0)
-        est = AdaptiveLasso(solver_options={"tol": TOL, "max_iter": 100000})
+        est = AdaptiveLasso(solver_options={"tol": TOL})
         alphas = np.logspace(-8, 2, 10)
         desc = "AdaptiveLasso GridSearchCV, 10 alphas x 5 folds, make_regression n=100 p=80 (README, configs[0])"
         return dict(X=X, y=y, est=est, alphas=alphas, F=F, desc=desc, name=name,
@@ -349,8 +349,16 @@ def run_engine(args):
     # ---- device-resident arm ------------------------------------------------------
     Xd = X if isinstance(X, torch.Tensor) else torch.from_numpy(X).to(dev)
     folds = [te for _, te in KFold(F).split(np.empty((n, 1)))]
-    ests = [clone(est).set_params(alpha=a) for a in alphas]
-    specs = [e._problem_spec(p) for e in ests]
+    # candidates described the way GridSearchCV._batch_plan does it: one working estimator
+    # re-parametrised per alpha
+    from types import SimpleNamespace
+
+    work = clone(est)
+    ests, specs = [], []
+    for a in alphas:
+        work.set_params(alpha=a)
+        specs.append(work._problem_spec(p))
+        ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
     opts = est._engine_options()
 
     def step_device():

@@ -42,10 +42,6 @@ int slm_create(int device, slm_ctx** out);
 void slm_destroy(slm_ctx* ctx);
 const char* slm_last_error(const slm_ctx* ctx);
 int slm_sm_count(const slm_ctx* ctx);
-/* the persistent tensor-core grids leave n_sms SMs free from now on (0 = use all): a sharded
- * Gram build keeps a few SMs for the NCCL all-reduce of the previous fold block, which runs
- * concurrently on its own stream (SURVEY 8e, row sharding) */
-int slm_set_sm_reserve(slm_ctx* ctx, int n_sms);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t slm_launch_count(const slm_ctx* ctx);
 /* average device time in ms of the `which` kernel family since the last reset,
@@ -79,6 +75,17 @@ int slm_gram_blocks(slm_ctx* ctx, const double* Xa_dev, int64_t lda, const int64
  * when the blocks are the CV test folds, model_selection.py:304-323). */
 int slm_gram_complement(slm_ctx* ctx, double* Gblk_dev, int n_blocks, int64_t pa,
                         double* Gtot_dev, void* stream);
+
+/* Row-sharded build: every rank builds the Gram blocks of its own rows and the
+ * blocks are summed over the ranks with one NCCL all-reduce.  A Gram is symmetric, so only its
+ * upper triangle travels: slm_tri_pack copies n_grams Grams (stride g_stride doubles) into
+ * buf_dev[n_grams][slm_tri_size(pa)] (row i = columns i..pa-1), slm_tri_unpack restores the full
+ * matrices (upper part + mirror) from the reduced buffer. */
+int64_t slm_tri_size(int64_t pa);
+int slm_tri_pack(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int n_grams,
+                 double* buf_dev, void* stream);
+int slm_tri_unpack(slm_ctx* ctx, const double* buf_dev, int64_t pa, int n_grams, double* G_dev,
+                   int64_t g_stride, void* stream);
 
 /* in-place centering of one augmented Gram using its ones row/column
  * (fit_intercept=True, _base.py:216-222): G <- G - s s^T / n on the [0,p] block. */

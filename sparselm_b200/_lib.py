@@ -63,7 +63,6 @@ SYMBOLS = {
     "slm_destroy": (None, [c_vp]),
     "slm_last_error": (ctypes.c_char_p, [c_vp]),
     "slm_sm_count": (ctypes.c_int, [c_vp]),
-    "slm_set_sm_reserve": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "slm_launch_count": (c_i64, [c_vp]),
     "slm_timing_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "slm_timing_read": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]),
@@ -72,6 +71,9 @@ SYMBOLS = {
     "slm_pack_design": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "slm_gram_blocks": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.c_int, c_vp, c_vp]),
     "slm_gram_complement": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp]),
+    "slm_tri_size": (c_i64, [c_i64]),
+    "slm_tri_pack": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_vp]),
+    "slm_tri_unpack": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp]),
     "slm_gram_center": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "slm_gram_gather": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "slm_lipschitz_workspace": (c_sz, [c_i64, ctypes.c_int]),

@@ -47,7 +47,6 @@ constexpr int kMaxScount = 4096;
 struct slm_ctx {
     int device = 0;
     int sm_count = 148;
-    int sm_reserve = 0;  // SMs the persistent GEMM grids leave free (for a concurrent NCCL kernel)
     std::string err;
     int64_t launches = 0;
     bool timing = false;
@@ -172,14 +171,13 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         occupancy = std::min(occ, MINB);
     }
-    const int sms = std::max(1, ctx->sm_count - ctx->sm_reserve);
-    fill_units(b, Cfg::BM, Cfg::BN, SYM, sms * occupancy);
+    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy);
     if (b.total_units <= 0) return cudaSuccess;
     if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
     b.flags = ctx->d_flags;
     int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
     // row-sparse: the k extents live on the device, the CTAs partition the units themselves
-    if (KSP) grid = (int)std::min<long long>((long long)sms * occupancy, b.total_units);
+    if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
     cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);
     if (e != cudaSuccess) return e;
     kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b);
@@ -442,6 +440,26 @@ __global__ void gram_complement_kernel(double* __restrict__ Gblk, int nb, long l
     }
 }
 
+// symmetric Gram <-> packed upper triangle (row i holds columns i..pa-1): the row-sharded
+// build only sends the upper triangles through the all-reduce
+__device__ __forceinline__ long long tri_off(long long i, long long pa) { return i * pa - i * (i - 1) / 2; }
+__global__ void tri_pack_kernel(const double* __restrict__ G, long long g_stride, long long pa,
+                                double* __restrict__ buf, long long b_stride) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= pa || j < i) return;
+    buf[(long long)blockIdx.z * b_stride + tri_off(i, pa) + (j - i)] = G[(long long)blockIdx.z * g_stride + i * pa + j];
+}
+__global__ void tri_unpack_kernel(const double* __restrict__ buf, long long b_stride, long long pa,
+                                  double* __restrict__ G, long long g_stride) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= pa) return;
+    const double* b = buf + (long long)blockIdx.z * b_stride;
+    const double v = j >= i ? b[tri_off(i, pa) + (j - i)] : b[tri_off(j, pa) + (i - j)];
+    G[(long long)blockIdx.z * g_stride + i * pa + j] = v;
+}
+
 __global__ void gram_center_kernel(double* __restrict__ G, long long pa, int p) {
     // rows/cols 0..p (features and y); ones row p+1 kept intact
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -505,15 +523,18 @@ __global__ void init_cols_kernel(double* theta, double* tmom, int* flag, int* co
 }
 
 // K4 helper: V <- W/||W|| per column, tracks the largest Rayleigh quotient.
-__global__ void __launch_bounds__(256) power_norm_kernel(double* __restrict__ V, const double* __restrict__ W,
-                                                         int p, double* __restrict__ lam, int init) {
+// One CTA per Gram, 8 columns x PN_LANES row lanes (a sharded rank holds one or two Grams, so
+// the kernel is latency-bound: many lanes, independent loads).
+constexpr int PN_LANES = 128;
+__global__ void __launch_bounds__(8 * PN_LANES) power_norm_kernel(double* __restrict__ V, const double* __restrict__ W,
+                                                                  int p, double* __restrict__ lam, int init) {
     const int f = blockIdx.x;
-    const int c = threadIdx.x & 7, r = threadIdx.x >> 3;  // 8 columns x 32 row lanes
+    const int c = threadIdx.x & 7, r = threadIdx.x >> 3;  // 8 columns x PN_LANES row lanes
     double* Vf = V + (long long)f * p * 8;
     const double* Wf = W + (long long)f * p * 8;
-    __shared__ double red[3][32][8];
+    __shared__ double red[3][PN_LANES][8];
     if (init) {
-        for (int j = r; j < p; j += 32) {
+        for (int j = r; j < p; j += PN_LANES) {
             unsigned h = (unsigned)(j * 8 + c) * 2654435761u + 12345u * (unsigned)(f + 1);
             h ^= h >> 15;
             h *= 2246822519u;
@@ -524,7 +545,7 @@ __global__ void __launch_bounds__(256) power_norm_kernel(double* __restrict__ V,
         return;
     }
     double vw = 0.0, ww = 0.0, vv = 0.0;
-    for (int j = r; j < p; j += 32) {
+    for (int j = r; j < p; j += PN_LANES) {
         double v = Vf[(long long)j * 8 + c], w = Wf[(long long)j * 8 + c];
         vw += v * w;
         ww += w * w;
@@ -534,7 +555,7 @@ __global__ void __launch_bounds__(256) power_norm_kernel(double* __restrict__ V,
     red[1][r][c] = ww;
     red[2][r][c] = vv;
     __syncthreads();
-    for (int s = 16; s > 0; s >>= 1) {
+    for (int s = PN_LANES / 2; s > 0; s >>= 1) {
         if (r < s) {
             red[0][r][c] += red[0][r + s][c];
             red[1][r][c] += red[1][r + s][c];
@@ -554,7 +575,7 @@ __global__ void __launch_bounds__(256) power_norm_kernel(double* __restrict__ V,
         lam[f] = best;
     }
     const double inv = ww > 0.0 ? rsqrt(ww) : 0.0;
-    for (int j = r; j < p; j += 32) Vf[(long long)j * 8 + c] = Wf[(long long)j * 8 + c] * inv;
+    for (int j = r; j < p; j += PN_LANES) Vf[(long long)j * 8 + c] = Wf[(long long)j * 8 + c] * inv;
 }
 
 // K8: adaptive reweighting.
@@ -750,11 +771,6 @@ void slm_destroy(slm_ctx* ctx) {
 
 const char* slm_last_error(const slm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int slm_sm_count(const slm_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
-int slm_set_sm_reserve(slm_ctx* ctx, int n_sms) {
-    if (!ctx) return 1;
-    ctx->sm_reserve = std::max(0, std::min(n_sms, ctx->sm_count - 1));
-    return 0;
-}
 int64_t slm_launch_count(const slm_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int slm_timing_enable(slm_ctx* ctx, int on) {
@@ -862,6 +878,28 @@ int slm_gram_complement(slm_ctx* ctx, double* Gblk, int n_blocks, int64_t pa, do
     return 0;
 }
 
+int64_t slm_tri_size(int64_t pa) { return pa * (pa + 1) / 2; }
+
+int slm_tri_pack(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int n_grams, double* buf,
+                 void* stream) {
+    if (!ctx || !G || !buf) return fail(ctx, 1, "slm_tri_pack: null argument");
+    if (n_grams <= 0 || pa <= 0) return 0;
+    dim3 grid((unsigned)((pa + 255) / 256), (unsigned)pa, (unsigned)n_grams);
+    tri_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(G, g_stride, pa, buf, slm_tri_size(pa));
+    LAUNCH_OK("tri_pack_kernel");
+    return 0;
+}
+
+int slm_tri_unpack(slm_ctx* ctx, const double* buf, int64_t pa, int n_grams, double* G, int64_t g_stride,
+                   void* stream) {
+    if (!ctx || !G || !buf) return fail(ctx, 1, "slm_tri_unpack: null argument");
+    if (n_grams <= 0 || pa <= 0) return 0;
+    dim3 grid((unsigned)((pa + 255) / 256), (unsigned)pa, (unsigned)n_grams);
+    tri_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(buf, slm_tri_size(pa), pa, G, g_stride);
+    LAUNCH_OK("tri_unpack_kernel");
+    return 0;
+}
+
 int slm_gram_center(slm_ctx* ctx, double* G, int64_t pa, int64_t p, void* stream) {
     if (!ctx || !G) return fail(ctx, 1, "slm_gram_center: null argument");
     // NOTE: every thread reads the (unmodified) ones row; rows 0..p are updated
@@ -937,12 +975,12 @@ static int lipschitz_run(slm_ctx* ctx, const double* G, int64_t g_stride, int64_
     double* W = V + (int64_t)n_grams * p * 8;
     double* lam = W + (int64_t)n_grams * p * 8;
     std::vector<int32_t> K(n_grams, 8);
-    power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 1);
+    power_norm_kernel<<<n_grams, 8 * PN_LANES, 0, s>>>(V, W, (int)p, lam, 1);
     LAUNCH_OK("power_norm_kernel(init)");
     for (int it = 0; it < iters; ++it) {
         int rc = apply_batched(ctx, G, g_stride, pa, p, n_grams, K.data(), V, 8, W, s, -1.0, FAM_LIPS);
         if (rc) return rc;
-        power_norm_kernel<<<n_grams, 256, 0, s>>>(V, W, (int)p, lam, 0);
+        power_norm_kernel<<<n_grams, 8 * PN_LANES, 0, s>>>(V, W, (int)p, lam, 0);
         LAUNCH_OK("power_norm_kernel");
     }
     *lam_out = lam;

@@ -391,11 +391,15 @@ class Engine:
         return ex.value, de.value
 
     # ---- data preparation for a CV search / a plain fit --------------------
-    def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None, shard=None):
+    def prepare(self, X, y, test_folds=None, fit_intercept=False, sample_weight=None, col_perm=None, shard=None,
+                score_folds=None):
         """Pack the design, build per-fold training Grams + the full Gram.
 
         test_folds: list of index arrays forming a partition of range(n) (the CV
         test sets), or None for a single fit on all rows.
+        score_folds: (sharded searches on a host-resident X) the test folds this rank will
+        score; rows of other folds are only brought to the device as far as this rank's
+        share of the Gram build needs them.  None = every row.
         """
         if isinstance(X, self.torch.Tensor):
             n, p = X.shape
@@ -426,9 +430,10 @@ class Engine:
         fold_rows = shard.fold_row_ranges(row_ptr) if sharded else \
             [(int(row_ptr[f]), int(row_ptr[f + 1])) for f in range(F)]
         if on_host and row_perm is None and n >= 4096:
-            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows, shard if sharded else None)
+            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows, shard if sharded else None,
+                                               score_folds if sharded else None)
         elif sharded:
-            Xa, allG = self._prepare_sharded(X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard)
+            Xa, allG = self._prepare_sharded(X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard, score_folds)
         else:
             Xa = self.pack(X, y, sw, col_perm, row_perm)
             allG = self.gram_blocks(Xa, row_ptr, extra=1 if F > 1 else 0)
@@ -455,12 +460,34 @@ class Engine:
             self.gram_center(G_full, p)
             if F > 1:
                 self.gram_center(G_train, p)
+        if sharded and score_folds is not None and row_perm is None and F > 1 and (not on_host or n >= 4096):
+            # rows of the other folds reached the device only as far as the Gram build needed
+            extra["partial_folds"] = {f for f in range(F) if f not in score_folds}
+            extra["pack_args"] = (sw, col_perm)
         finite = self.torch.isfinite(G_full[p + 1]).all()  # checked at the next host sync
         return FoldData(n=n, p=p, pa=pa, Xa=Xa, row_ptr=row_ptr, G_train=G_train, G_full=G_full,
                         n_train=n_train, fit_intercept=bool(fit_intercept), row_perm=row_perm, extra=extra,
                         G_all=allG if F > 1 else None, _finite=finite)
 
-    SHARD_SM_RESERVE = 16  # SMs left to the NCCL kernel while a sharded Gram build runs
+    def ensure_fold_rows(self, fd, X, y, f):
+        """Make every row of test fold f resident in fd.Xa (a sharded prepare only uploads the
+        folds it expects to score; anything else is fetched on demand here)."""
+        part = fd.extra.get("partial_folds")
+        if not part or f not in part:
+            return
+        torch = self.torch
+        sw, col_perm = fd.extra["pack_args"]
+        a, b = int(fd.row_ptr[f]), int(fd.row_ptr[f + 1])
+        Xt = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
+        blk = self.to_device(Xt[a:b], torch.float64)
+        yd = self.to_device(np.asarray(y, dtype=np.float64)[a:b])
+        swd = None if sw is None else self.to_device(np.asarray(sw, dtype=np.float64)[a:b])
+        cp = None if col_perm is None else self.to_device(np.asarray(col_perm, dtype=np.int32))
+        self._ck(self.lib.slm_pack_design(self.h, self._ptr(blk), blk.stride(0), self._ptr(yd), self._ptr(swd),
+                                          self._ptr(cp), ctypes.c_void_p(0), b - a, fd.p,
+                                          ctypes.c_void_p(fd.Xa.data_ptr() + 8 * a * fd.pa), fd.pa, self.stream),
+                 "slm_pack_design")
+        part.discard(f)
 
     def _gram_block_into(self, Xa, lo, hi, out):
         """out = Xa[lo:hi]^T Xa[lo:hi] (out untouched when the range is empty)."""
@@ -471,36 +498,67 @@ class Engine:
                                           ptr.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), 1,
                                           ctypes.c_void_p(out.data_ptr()), self.stream), "slm_gram_blocks")
 
-    def _prepare_sharded(self, X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard):
+    def _prepare_sharded(self, X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard, score_folds=None):
         """Row-sharded Gram build: this rank contributes, for every test fold, the
-        Gram of its own 1/world slice of that fold's rows.  The block of fold f is all-reduced
-        on NCCL's stream while the tensor cores build the block of fold f+1 (the persistent
-        GEMM grid leaves SHARD_SM_RESERVE SMs to the NCCL kernel)."""
+        Gram of its own 1/world slice of that fold's rows; the blocks are then summed over the
+        ranks.  Only the rows this rank needs are packed: its slices, plus the whole test folds
+        in `score_folds` (None = everything)."""
         torch = self.torch
-        Xa = self.pack(X, y, sw, col_perm, row_perm)
-        pa = Xa.shape[1]
         F = len(row_ptr) - 1
+        if score_folds is None or row_perm is not None or F == 1:
+            Xa = self.pack(X, y, sw, col_perm, row_perm)
+        else:
+            Xd = self.to_device(X, torch.float64)
+            yd = self.to_device(y, torch.float64).reshape(-1)
+            swd = None if sw is None else self.to_device(sw, torch.float64)
+            cp = None if col_perm is None else self.to_device(np.asarray(col_perm, dtype=np.int32))
+            n, p = Xd.shape
+            Xa = torch.empty((n, self.padded_cols(p)), dtype=torch.float64, device=self.device)
+            for f in range(F):
+                a, b = (int(row_ptr[f]), int(row_ptr[f + 1])) if f in score_folds else fold_rows[f]
+                self._pack_rows(Xd, yd, swd, cp, a, b, Xa)
+        pa = Xa.shape[1]
         allG = torch.zeros((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=self.device)
-        works = []
-        self.lib.slm_set_sm_reserve(self.h, self.SHARD_SM_RESERVE)
-        try:
-            for f, (lo, hi) in enumerate(fold_rows):
-                self._gram_block_into(Xa, lo, hi, allG[f])
-                works.append(shard.allreduce_sum_async(allG[f]))
-        finally:
-            self.lib.slm_set_sm_reserve(self.h, 0)
-        for w in works:
-            if w is not None:
-                w.wait()
+        for f, (lo, hi) in enumerate(fold_rows):
+            self._gram_block_into(Xa, lo, hi, allG[f])
+        self._allreduce_grams(allG[:F], shard)
         return Xa, allG
 
-    def _prepare_pipelined(self, X, y, sw, col_perm, row_ptr, fold_rows, shard=None):
+    def _allreduce_grams(self, G, shard):
+        """Sum the partial Gram blocks G [F, pa, pa] over the ranks: upper triangles packed into
+        one buffer, ONE NCCL all-reduce, unpack + mirror.  (Measured on B200/NVLink: NCCL's
+        bandwidth is bound by the CTAs it gets -- about 20 GB/s each, 24 to saturate -- and the
+        FP64 build wants every SM, so overlapping the two only slows both; half the bytes in one
+        full-speed collective after the builds is faster at every rank count.)"""
+        torch = self.torch
+        F, pa = G.shape[0], G.shape[-1]
+        tri = int(self.lib.slm_tri_size(pa))
+        buf = torch.empty((F, tri), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.slm_tri_pack(self.h, self._ptr(G), pa * pa, pa, F, self._ptr(buf), self.stream),
+                 "slm_tri_pack")
+        shard.allreduce_sum_(buf)
+        self._ck(self.lib.slm_tri_unpack(self.h, self._ptr(buf), pa, F, self._ptr(G), pa * pa, self.stream),
+                 "slm_tri_unpack")
+
+    def _pack_rows(self, Xd, yd, swd, cp, a, b, Xa):
+        """Xa[a:b] = [X | y | 1 | 0] of the device-resident rows a..b (identity row order)."""
+        if b <= a:
+            return
+        pa = Xa.shape[1]
+        self._ck(self.lib.slm_pack_design(self.h, ctypes.c_void_p(Xd.data_ptr() + 8 * a * Xd.stride(0)), Xd.stride(0),
+                                          ctypes.c_void_p(yd.data_ptr() + 8 * a),
+                                          ctypes.c_void_p(0 if swd is None else swd.data_ptr() + 8 * a),
+                                          self._ptr(cp), ctypes.c_void_p(0), b - a, Xd.shape[1],
+                                          ctypes.c_void_p(Xa.data_ptr() + 8 * a * pa), pa, self.stream),
+                 "slm_pack_design")
+
+    def _prepare_pipelined(self, X, y, sw, col_perm, row_ptr, fold_rows, shard=None, score_folds=None):
         """Host-resident X: the rows of one test fold at a time are copied to the device on a
         copy stream while the previous fold is packed and its Gram block is built, so the
         H2D transfer hides behind the FP64 tensor work (needs pinned memory to be truly
         asynchronous; pageable arrays still overlap chunk by chunk).  fold_rows[f] = the rows
-        of fold f whose Gram this rank builds; with `shard` the blocks are summed over the
-        ranks, fold by fold, on NCCL's stream while the next block is being built."""
+        of fold f whose Gram this rank builds; with `shard` the blocks are then summed over the
+        ranks (one all-reduce of the packed upper triangles)."""
         torch = self.torch
         Xt = X if isinstance(X, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
         if Xt.dtype != torch.float64:
@@ -515,17 +573,21 @@ class Engine:
         Xa = torch.empty((n, pa), dtype=torch.float64, device=dev)
         alloc = torch.zeros if shard is not None else torch.empty
         allG = alloc((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=dev)
-        works = []
-        if shard is not None:
-            self.lib.slm_set_sm_reserve(self.h, self.SHARD_SM_RESERVE)
+
         # row blocks: the test folds, split further so that a block stays <= 64 MiB
         blocks = []
         max_rows = max(1024, (64 << 20) // (8 * p))
         for f in range(F):
             a, b = int(row_ptr[f]), int(row_ptr[f + 1])
+            if F > 1 and score_folds is not None and f not in score_folds:
+                a, b = fold_rows[f]  # not scored here: only this rank's slice of the fold travels
+                if b <= a:
+                    if shard is not None:
+                        blocks.append((a, a))  # nothing to build, but the collective still runs
+                    continue
             nb = max(1, -(-(b - a) // max_rows)) if F == 1 else 1
             edges = np.linspace(a, b, nb + 1).astype(np.int64)
-            blocks += [(int(edges[i]), int(edges[i + 1])) for i in range(nb) if edges[i + 1] > edges[i]]
+            blocks += [(int(edges[i]), int(edges[i + 1])) for i in range(nb) if edges[i + 1] > edges[i] or b == a]
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
@@ -548,17 +610,10 @@ class Engine:
             if F > 1:  # one Gram block per test fold, as soon as its rows are packed
                 f = int(np.searchsorted(row_ptr, a, side="right") - 1)
                 self._gram_block_into(Xa, max(a, fold_rows[f][0]), min(b, fold_rows[f][1]), allG[f])
-                if shard is not None:
-                    works.append(shard.allreduce_sum_async(allG[f]))
         if F == 1:  # single fit: one Gram over all (of this rank's) rows once everything is packed
             self._gram_block_into(Xa, fold_rows[0][0], fold_rows[0][1], allG[0])
-            if shard is not None:
-                works.append(shard.allreduce_sum_async(allG[0]))
         if shard is not None:
-            self.lib.slm_set_sm_reserve(self.h, 0)
-        for w in works:
-            if w is not None:
-                w.wait()
+            self._allreduce_grams(allG[:max(F, 1)] if F > 1 else allG[:1], shard)
         return Xa, allG
 
     # ---- K5-K8: batched solve ------------------------------------------------

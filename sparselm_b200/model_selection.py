@@ -95,7 +95,8 @@ def _fold_key(est, spec):
     return (bool(est.fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
 
 
-def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=None, shard=None, sample_weight=None):
+def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=None, shard=None, sample_weight=None,
+                  score_folds=None):
     """Device-resident design + Grams for (fit_intercept, column order) of `est`/`spec`,
     through the FoldData cache of a LineSearchCV when there is one.  Only enqueues GPU
     work (H2D copies, packing, Gram build): the caller can keep working on the host."""
@@ -105,7 +106,8 @@ def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=No
               tuple(int(t[0]) for t in test_folds))
         if ck in cache:
             return cache[ck]
-    fd = engine.prepare(X, yv, test_folds, est.fit_intercept, sample_weight, col_perm=spec.col_perm, shard=shard)
+    fd = engine.prepare(X, yv, test_folds, est.fit_intercept, sample_weight, col_perm=spec.col_perm, shard=shard,
+                        score_folds=score_folds)
     if ck is not None:
         cache[ck] = fd
     return fd
@@ -148,10 +150,6 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     for key, idxs in batches.items():
         s0, e0 = specs[idxs[0]], ests[idxs[0]]
         fkey = _fold_key(e0, s0)
-        if fkey not in fds:
-            fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard, sample_weight)
-        fd = fds[fkey]
-        t0 = time.perf_counter()
         # batch columns in order of increasing penalty strength (dense iterates first): the
         # row-sparse apply shares one support list per chunk of adjacent columns
         idxs = np.asarray(sorted(idxs, key=lambda ci: (specs[ci].strength, ci)))
@@ -159,6 +157,14 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             mine = shard.my_columns(n_splits, len(idxs))  # per fold: positions in idxs this rank solves
         else:
             mine = [np.arange(len(idxs))] * n_splits
+        if fkey not in fds:
+            score_folds = None
+            if shard is not None and shard.world > 1 and train_scores is None and cache is None:
+                score_folds = {f for f in range(n_splits) if len(mine[f])}  # rows this rank has to hold
+            fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard, sample_weight,
+                                      score_folds)
+        fd = fds[fkey]
+        t0 = time.perf_counter()
         out = solve_specs(engine, fd, [[specs[idxs[k]] for k in mine[f]] for f in range(n_splits)], **opts)
         t1 = time.perf_counter()
         for f in range(n_splits):
@@ -167,6 +173,12 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         K = len(idxs)
         icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
         wtd = bool(fd.extra.get("weighted"))
+        for f in range(n_splits):  # rows a sharded prepare did not expect to need
+            if len(mine[f]) or train_scores is not None:
+                engine.ensure_fold_rows(fd, X, yv, f)
+        if train_scores is not None:
+            for f in range(n_splits):
+                engine.ensure_fold_rows(fd, X, yv, f)
         sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f),
                                   rows_scaled=wtd)
                   for f in range(n_splits)]
@@ -325,10 +337,17 @@ class GridSearchCV(_SkGridSearchCV):
                     opts0 = est._engine_options()
                     engine = get_engine(opts0.pop("device", None))
                     cache = getattr(self, "_fd_cache", None)
+                    shard = getattr(self, "_shard", None)
+                    score_folds = None
+                    if shard is not None and shard.world > 1 and not self.return_train_score and cache is None:
+                        # host rows this rank needs: its slices for the Gram build + the test
+                        # folds of the columns it will solve (anything else is fetched on demand)
+                        mine = shard.my_columns(len(splits), len(candidates))
+                        score_folds = {f for f in range(len(splits)) if len(mine[f])}
                     pre_fds[_fold_key(ests[0], specs[0])] = prepare_folds(
                         engine, Xv, yv, [np.asarray(test) for _, test in splits], ests[0], specs[0], cache,
                         None if cache is None else (id(Xv), id(yv), None if sw is None else sw.tobytes()),
-                        getattr(self, "_shard", None), sw)
+                        shard, sw, score_folds)
         except (NotImplementedError, EngineError):
             raise
         except Exception:

@@ -3,9 +3,8 @@
 Two independent shardings compose:
 
 * rows    : every rank builds, for every test fold, the Gram block of its own 1/world
-            slice of that fold's rows; the block of fold f is all-reduced (NCCL over
-            NVLink / NVSwitch, asynchronously on NCCL's stream) while the tensor cores
-            build the block of fold f+1.
+            slice of that fold's rows; the upper triangles of all blocks are packed into one
+            buffer and summed with ONE all-reduce (NCCL over NVLink / NVSwitch).
 * grid    : the (fold, alpha) problems are independent (the reference treats them as
             independent joblib tasks, model_selection.py:304-323).  Each rank solves a
             subset chosen so that it touches as few Grams as possible (fold-major
@@ -86,15 +85,6 @@ class GridShard:
 
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group)
         return tensor
-
-    def allreduce_sum_async(self, tensor):
-        """Start an in-place sum over ranks; returns a handle whose wait() orders the current
-        stream after the collective (None when there is nothing to do)."""
-        if self.world == 1:
-            return None
-        import torch.distributed as dist
-
-        return dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def allreduce_sum_numpy(self, arr, device=None):
         """Sum over ranks of a (small) numpy array, returned as numpy."""

@@ -414,3 +414,31 @@ def test_group_whitening_rejects_singular_block(engine):
     G = engine.gram_blocks(Xa, np.array([0, n], dtype=np.int64))
     with pytest.raises(ValueError, match="positive definite"):
         engine.whiten(G, p, np.array([0, 3, 6]), np.array([float(n)]))
+
+
+def test_tri_pack_roundtrip(engine):
+    """Upper-triangle packing of the row-sharded Gram all-reduce: pack -> unpack restores a
+    symmetric matrix exactly, and summing packed buffers equals summing the matrices."""
+    import ctypes
+
+    torch = _torch()
+    rng = _rng(21)
+    pa, F = 40, 3
+    A = rng.standard_normal((2, F, pa, pa))
+    A = A + A.transpose(0, 1, 3, 2)
+    tri = int(engine.lib.slm_tri_size(pa))
+    assert tri == pa * (pa + 1) // 2
+    bufs = []
+    for r in range(2):
+        G = torch.from_numpy(A[r].copy()).to(engine.device)
+        buf = torch.empty((F, tri), dtype=torch.float64, device=engine.device)
+        engine._ck(engine.lib.slm_tri_pack(engine.h, engine._ptr(G), pa * pa, pa, F, engine._ptr(buf), engine.stream),
+                   "slm_tri_pack")
+        bufs.append(buf)
+    iu = np.triu_indices(pa)
+    np.testing.assert_array_equal(bufs[0].cpu().numpy()[1], A[0, 1][iu])
+    total = bufs[0] + bufs[1]
+    out = torch.full((F, pa, pa), np.nan, dtype=torch.float64, device=engine.device)
+    engine._ck(engine.lib.slm_tri_unpack(engine.h, engine._ptr(total), pa, F, engine._ptr(out), pa * pa, engine.stream),
+               "slm_tri_unpack")
+    np.testing.assert_array_equal(out.cpu().numpy(), A[0] + A[1])

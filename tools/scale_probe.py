@@ -104,6 +104,16 @@ if world > 1:
     err = float(np.abs(ref["test_scores"] - res["test_scores"]).max() / np.abs(ref["test_scores"]).max())
     out["sharded_vs_single_rel_err"] = err
     assert err < 1e-8, err
+    # the same through the public API on a host-resident X (rows travel only as far as needed)
+    from sparselm_b200.model_selection import GridSearchCV
+
+    gs = GridSearchCV(clone(est), {"alpha": list(alphas)}, cv=F)
+    gs._shard = shard
+    gs.fit(X, y)
+    ms = gs.cv_results_["mean_test_score"]
+    err2 = float(np.abs(ms - ref["test_scores"].mean(1)).max() / np.abs(ms).max())
+    out["sharded_api_vs_single_rel_err"] = err2
+    assert err2 < 1e-8, err2
 for r in range(world):
     barrier()
     if r == rank:
