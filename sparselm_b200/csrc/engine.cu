@@ -133,7 +133,7 @@ struct Shape {
     double eff; // measured fraction of the per-SM DMMA peak this warp layout reaches
 };
 
-static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
+static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas, int bk = kBK) {
     long long u = 0;
     int nflags = 0;
     for (int i = 0; i < b.n_problems; ++i) {
@@ -141,7 +141,7 @@ static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
         if (pr.qlim <= 0) pr.qlim = (int)pr.ldq;
         pr.tiles_m = (pr.M + bm - 1) / bm;
         pr.tiles_n = (pr.N + bn - 1) / bn;
-        pr.kt = std::max(1, (pr.Kd + kBK - 1) / kBK);
+        pr.kt = std::max(1, (pr.Kd + bk - 1) / bk);
         if (pr.N <= 0 || pr.M <= 0 || pr.Kd <= 0) pr.tiles_m = pr.tiles_n = 0;
         pr.n_tiles = sym ? pr.tiles_n * (pr.tiles_n + 1) / 2 : pr.tiles_m * pr.tiles_n;
         pr.unit_begin = (int)u;
@@ -156,10 +156,11 @@ static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas) {
     b.units_per_cta = (int)((u + n_cta - 1) / n_cta);
 }
 
-template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB, bool KSP = false>
+template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB, bool KSP = false, int BK = kBK,
+          int STAGES = kStages>
 static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
-    using Cfg = GemmCfg<WM, WN, MI, NI, kBK, kStages, AM>;
-    auto kern = gemm_f64_kernel<WM, WN, MI, NI, kBK, kStages, AM, SYM, MINB, KSP>;
+    using Cfg = GemmCfg<WM, WN, MI, NI, BK, STAGES, AM>;
+    auto kern = gemm_f64_kernel<WM, WN, MI, NI, BK, STAGES, AM, SYM, MINB, KSP>;
     static int occupancy = 0;  // resident CTAs per SM (the spin-wait fix-up needs co-residency)
     if (occupancy == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -171,7 +172,7 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         occupancy = std::min(occ, MINB);
     }
-    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy);
+    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy, BK);
     if (b.total_units <= 0) return cudaSuccess;
     if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
     b.flags = ctx->d_flags;
@@ -222,13 +223,16 @@ static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
     return cudaErrorInvalidValue;
 }
 // row-sparse apply menu (one tile column per support chunk): id, WM, WN, MI, NI, MINB, eff
+// narrow tiles run 3 CTAs (24 warps) per SM with a 3-stage pipeline: measured 6.6 % faster than
+// 2 CTAs x 4 stages on the mid-solve scenario of tools/apply_probe.py (more warps hide the
+// gather latency; 80 registers, no spills)
 #define SLM_SPARSE_SHAPES(X)      \
-    X(0, 8, 1, 2, 1, 2, 0.55)     \
-    X(1, 8, 1, 2, 2, 2, 0.70)     \
-    X(2, 8, 1, 2, 3, 2, 0.78)     \
-    X(3, 8, 1, 2, 4, 2, 0.84)     \
-    X(4, 8, 1, 2, 5, 2, 0.80)     \
-    X(5, 8, 1, 2, 6, 2, 0.79)     \
+    X(0, 8, 1, 2, 1, 3, 0.55)     \
+    X(1, 8, 1, 2, 2, 3, 0.70)     \
+    X(2, 8, 1, 2, 3, 3, 0.78)     \
+    X(3, 8, 1, 2, 4, 3, 0.84)     \
+    X(4, 8, 1, 2, 5, 3, 0.80)     \
+    X(5, 8, 1, 2, 6, 3, 0.79)     \
     X(6, 8, 1, 2, 7, 2, 0.765)    \
     X(7, 4, 2, 4, 4, 2, 0.78)     \
     X(8, 16, 1, 1, 9, 1, 0.775)   \
@@ -244,9 +248,12 @@ constexpr int kNumSparseShapes = sizeof(kSparseShapes) / sizeof(Shape);
 static cudaError_t launch_sparse_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
 #define X(id_, wm, wn, mi, ni, minb, eff) \
-    case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb, true>(ctx, b, s);
+    case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb, true, kBK, (minb >= 3 ? 3 : kStages)>(ctx, b, s);
         SLM_SPARSE_SHAPES(X)
 #undef X
+        // experimental 128x32 variants (SLM_FORCE_SPARSE_SHAPE only)
+        case 12: return launch_gemm_t<8, 1, 2, 4, false, false, 2, true>(ctx, b, s);
+        case 13: return launch_gemm_t<8, 1, 2, 4, false, false, 4, true, 16, 2>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -263,15 +270,19 @@ static cudaError_t launch_score_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
     }
     return cudaErrorInvalidValue;
 }
-// symmetric (Gram build) menu
-static const Shape kSyrkShapes[] = {{128, 128, 1, 0.84}, {128, 128, 1, 0.85}};
+// symmetric (Gram build) menu: 128x128 tiles.  Measured at the C3 shape (tools/syrk_probe.py):
+// a 32-deep k-slab (half as many CTA-wide barriers per flop) with 3 stages beats 16-deep x 4
+// stages by 9 % (11.25 vs 12.26 ms); more warps or other warp tiles change little.
 static cudaError_t launch_syrk_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
     switch (id) {
-        case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
-        case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1>(ctx, b, s);
+        case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1, false, 32, 3>(ctx, b, s);
+        case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1, false, 32, 3>(ctx, b, s);
+        case 2: return launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
+        case 3: return launch_gemm_t<4, 4, 4, 4, false, true, 1>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
+constexpr int kNumSyrkShapes = 4;
 
 struct ProblemDims {
     int M, N;
@@ -353,7 +364,7 @@ static int apply_rowsparse(slm_ctx* ctx, const SolveDev& sp, const int32_t* K, c
         if (np == 0) return 0;
         b.n_problems = np;
         int sid = pick_shape(kSparseShapes, kNumSparseShapes, pd, np, ctx->sm_count);
-        if (ctx->force_sparse_shape >= 0 && ctx->force_sparse_shape < kNumSparseShapes) sid = ctx->force_sparse_shape;
+        if (ctx->force_sparse_shape >= 0 && ctx->force_sparse_shape < 14) sid = ctx->force_sparse_shape;
         FamTimer tm(ctx, FAM_APPLY, s, first ? std::max(algo_flops, 0.0) : 0.0);
         first = false;
         cudaError_t e = launch_sparse_shape(ctx, sid, b, s);
@@ -842,7 +853,7 @@ int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* 
     if (!ctx || !Xa || !row_ptr || !Gblk) return fail(ctx, 1, "slm_gram_blocks: null argument");
     if (lda % 8) return fail(ctx, 1, "slm_gram_blocks: lda must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
-    int sid = ctx->force_syrk_shape >= 0 && ctx->force_syrk_shape < 2 ? ctx->force_syrk_shape : 0;
+    int sid = ctx->force_syrk_shape >= 0 && ctx->force_syrk_shape < kNumSyrkShapes ? ctx->force_syrk_shape : 0;
     for (int f0 = 0; f0 < n_blocks; f0 += kMaxGemmProblems) {
         int nf = std::min(n_blocks - f0, (int)kMaxGemmProblems);
         GemmBatch b;
