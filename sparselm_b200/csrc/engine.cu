@@ -133,7 +133,7 @@ struct Shape {
     double eff; // measured fraction of the per-SM DMMA peak this warp layout reaches
 };
 
-static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas, int bk = kBK) {
+static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas, int bk = kBK, bool waves = true) {
     long long u = 0;
     int nflags = 0;
     for (int i = 0; i < b.n_problems; ++i) {
@@ -146,14 +146,31 @@ static void fill_units(GemmBatch& b, int bm, int bn, bool sym, int max_ctas, int
         pr.n_tiles = sym ? pr.tiles_n * (pr.tiles_n + 1) / 2 : pr.tiles_m * pr.tiles_n;
         pr.unit_begin = (int)u;
         pr.flag_begin = nflags;
+        pr.tile_begin = nflags;
         nflags += pr.n_tiles;
         u += (long long)pr.n_tiles * pr.kt;
     }
     b.total_units = (int)u;
     b.n_flags = nflags;
-    // persistent grid: every CTA is resident, ranges are equal => SMs finish together
+    // persistent grid: every CTA is resident.  Whole waves of tiles are data-parallel (one tile
+    // per CTA, the CTAs of a wave sweep k together and share operand panels in L2); the units of
+    // the partial last wave are cut into equal ranges => the SMs still finish together
     long long n_cta = std::min<long long>(max_ctas, std::max<long long>(1, u));
-    b.units_per_cta = (int)((u + n_cta - 1) / n_cta);
+    b.full_waves = 0;
+    b.rem_unit_begin = 0;
+    if (waves && nflags >= n_cta && n_cta == max_ctas) {
+        b.full_waves = (int)(nflags / n_cta);
+        const int t0 = b.full_waves * (int)n_cta;  // first tile of the stream-K remainder
+        long long u0 = u;
+        for (int i = 0; i < b.n_problems; ++i) {
+            const GemmProblem& pr = b.pr[i];
+            if (t0 >= pr.tile_begin && t0 < pr.tile_begin + pr.n_tiles)
+                u0 = pr.unit_begin + (long long)(t0 - pr.tile_begin) * pr.kt;
+        }
+        b.rem_unit_begin = (int)u0;
+    }
+    const long long rem = u - b.rem_unit_begin;
+    b.units_per_cta = (int)std::max<long long>(1, (rem + n_cta - 1) / n_cta);
 }
 
 template <int WM, int WN, int MI, int NI, bool AM, bool SYM, int MINB, bool KSP = false, int BK = kBK,
@@ -176,7 +193,7 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     if (b.total_units <= 0) return cudaSuccess;
     if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
     b.flags = ctx->d_flags;
-    int grid = (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
+    int grid = b.full_waves > 0 ? ctx->sm_count * occupancy : (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
     // row-sparse: the k extents live on the device, the CTAs partition the units themselves
     if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
     cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);

@@ -11,10 +11,12 @@
 // i.e. C[M x N] = A[M x Kd] * B[Kd x N] with B row-major [Kd][ldq] and A given
 // either as its transpose (row-major [Kd][ldp], "K-major") or row-major [M][ldp].
 //
-// Scheduling is stream-K: the (tile, k-slab) work units of all problems of a
-// batch are laid out on one line and cut into equal contiguous ranges, one per
-// persistent CTA (grid = SMs x CTAs/SM), so that the 148 SMs finish together
-// whatever the tile count.  A CTA whose range covers a whole tile stores it.  A
+// Scheduling is data-parallel waves + stream-K over a persistent grid (SMs x CTAs/SM): as
+// long as whole waves of tiles remain, CTA c takes tile c of the wave and runs its full
+// contraction (all CTAs of a wave then sweep k in step and share operand panels through
+// L2: one DRAM read of the operands per wave instead of one per tile); the (tile, k-slab)
+// units of the partial last wave are laid out on one line and cut into equal contiguous
+// ranges, one per CTA, so that the 148 SMs finish together whatever the tile count.  A CTA whose range covers a whole tile stores it.  A
 // tile cut into several chunks is combined in a FIXED order (descending k: the
 // chunk holding the tile's last slab stores, every earlier chunk waits on the
 // tile's flag for the chunks after it and then adds), so results are
@@ -55,12 +57,20 @@ struct GemmProblem {
     int kt;          // k-slabs per tile
     int unit_begin;  // first linear work unit (tile * kt + slab) of this problem
     int flag_begin;  // first per-tile flag of this problem
+    int tile_begin;  // first global tile index of this problem
 };
 
 struct GemmBatch {
     int n_problems;
     int total_units;
     int units_per_cta;
+    // hybrid schedule (host-partitioned batches): CTA c first computes the whole tiles
+    // c, c + grid, ..., c + (full_waves-1)*grid ("data-parallel waves": every CTA walks the
+    // contraction in step, so the operand panels of a wave are read from DRAM once and shared
+    // through L2), then its stream-K share of the units from rem_unit_begin on (the partial
+    // last wave, cut evenly so that all SMs finish together)
+    int full_waves;
+    int rem_unit_begin;
     int* flags;  // one int per tile, zero on entry
     int n_flags;
     GemmProblem pr[kMaxGemmProblems];
@@ -133,26 +143,43 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         total_units = s_ub[batch.n_problems];
         upc = (total_units + (int)gridDim.x - 1) / (int)gridDim.x;
     }
-    int u = blockIdx.x * upc;
+    const int rem0 = KSPARSE ? 0 : batch.rem_unit_begin;  // first unit of the stream-K part
+    int u = rem0 + blockIdx.x * upc;
     const int u_end = min(total_units, u + upc);
+    int wave = 0;
+    const int full_waves = KSPARSE ? 0 : batch.full_waves;
 
 #pragma unroll 1
-    while (u < u_end) {
+    while (wave < full_waves || u < u_end) {
         // ---- locate (problem, tile, slab range) of this segment ------------------
-        int pi = 0;
+        int pi = 0, tl, kt0, kt1, KT, Kd, unit_begin;
+        if (wave < full_waves) {  // a whole tile of a data-parallel wave
+            const int tg = wave * (int)gridDim.x + (int)blockIdx.x;
+            ++wave;
 #pragma unroll 1
-        for (int i = 1; i < batch.n_problems; ++i)
-            if (u >= (KSPARSE ? s_ub[i] : batch.pr[i].unit_begin)) pi = i;
+            for (int i = 1; i < batch.n_problems; ++i)
+                if (tg >= batch.pr[i].tile_begin) pi = i;
+            Kd = batch.pr[pi].Kd;
+            KT = batch.pr[pi].kt;
+            unit_begin = batch.pr[pi].unit_begin;
+            tl = tg - batch.pr[pi].tile_begin;
+            kt0 = 0;
+            kt1 = KT;
+        } else {
+#pragma unroll 1
+            for (int i = 1; i < batch.n_problems; ++i)
+                if (u >= (KSPARSE ? s_ub[i] : batch.pr[i].unit_begin)) pi = i;
+            Kd = KSPARSE ? s_kd[pi] : batch.pr[pi].Kd;
+            KT = KSPARSE ? max(1, (Kd + BK - 1) / BK) : batch.pr[pi].kt;
+            unit_begin = KSPARSE ? s_ub[pi] : batch.pr[pi].unit_begin;
+            const int local = u - unit_begin;
+            tl = local / KT;
+            kt0 = local - tl * KT;
+            kt1 = min(KT, kt0 + (u_end - u));
+            u += kt1 - kt0;
+        }
         const GemmProblem& pr = batch.pr[pi];
-        const int Kd = KSPARSE ? s_kd[pi] : pr.Kd;
-        const int KT = KSPARSE ? max(1, (Kd + BK - 1) / BK) : pr.kt;
-        const int unit_begin = KSPARSE ? s_ub[pi] : pr.unit_begin;
-        const int local = u - unit_begin;
-        int tl = local / KT;
         const int tile_lin = tl;
-        const int kt0 = local - tl * KT;
-        const int kt1 = min(KT, kt0 + (u_end - u));
-        u += kt1 - kt0;
         int tm, tn;
         if (SYM) {
             tm = 0;
@@ -329,7 +356,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         if (!whole && !first_writer) {
             // chunks after mine = CTAs between me and the one owning the tile's last unit
             const int tile_last_unit = unit_begin + tile_lin * KT + KT - 1;
-            const int after = tile_last_unit / upc - (int)blockIdx.x;
+            const int after = (tile_last_unit - rem0) / upc - (int)blockIdx.x;
             if (tid == 0) {
                 while (atomicAdd(flag, 0) < after) __nanosleep(64);
                 __threadfence();
