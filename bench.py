@@ -56,6 +56,7 @@ def workload(name):
     from sparselm_b200.model import AdaptiveLasso, AdaptiveOverlapGroupLasso, Lasso, SparseGroupLasso
 
     opts = {"tol": TOL}
+    opts.update(json.loads(os.environ.get("BENCH_SOLVER_OPTIONS", "{}")))  # experiments: check_every, ...
     if name == "c3":
         n, p, G, K, F = 20000, 4000, 200, 100, 5
         X, y = make_data(n, p)

@@ -191,6 +191,18 @@ int slm_intercepts(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
                    const double* B_dev, int64_t ldz, int32_t K, double* intercept_dev,
                    void* stream);
 
+/* Unpenalised least squares on a Gram (OrdinaryLeastSquares, reference model/_ols.py:57-65:
+ * argmin 1/(2n) ||X b - y||^2): conjugate gradients on G b = c, c = row p of the Gram, every
+ * product G d through the tensor-core apply.  From b = 0 the iterates stay in range(G), so a
+ * rank-deficient (p > n) consistent system converges to its minimum-norm solution.  Stops on
+ * ||c - G b|| <= tol ||c|| (checked against the recomputed residual) or after max_iter products.
+ * X8_dev: [p][8] out, the solution is column 0 (stride 8: the layout slm_intercepts and
+ * slm_cv_score take with ldz = 8).  iters_host / relres_host may be NULL.  Synchronises. */
+size_t slm_gram_cg_workspace(int64_t p);
+int slm_gram_cg(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p, double tol,
+                int32_t max_iter, void* work_dev, size_t work_bytes, double* X8_dev,
+                int32_t* iters_host, double* relres_host, void* stream);
+
 /* plain batched tensor-core apply GZ_f = G_f Z_f (exposed for tests / roofline runs) */
 int slm_gram_apply(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p,
                    int n_folds, const int32_t* K, const double* Z_dev, int64_t ldz,

@@ -86,6 +86,8 @@ SYMBOLS = {
     "slm_cv_score": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "slm_intercepts": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "slm_gram_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_i64, c_vp, c_vp]),
+    "slm_gram_cg_workspace": (c_sz, [c_i64]),
+    "slm_gram_cg": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_dbl, c_i32, c_vp, c_sz, c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp]),
     "slm_rowsparse_workspace": (c_sz, [c_i64, c_i64, ctypes.c_int]),
     "slm_gram_apply_rowsparse": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_sz, c_vp]),
     "slm_apply_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),

@@ -26,6 +26,7 @@
 #include "gemm_f64.cuh"
 #include "solver_kernels.cuh"
 #include "whiten_kernels.cuh"
+#include "cg_kernels.cuh"
 
 using namespace slm;
 
@@ -58,6 +59,7 @@ struct slm_ctx {
     unsigned long long* d_stat = nullptr;  // executed contraction length of the row-sparse applies
     unsigned long long* h_stat = nullptr;
     int* h_scount = nullptr;         // pinned copy of the support-list lengths (chunk-width choice)
+    double* h_scal = nullptr;        // pinned scalars of the conjugate-gradient loop
     double apply_exec_flops = 0.0;   // flops the row-sparse applies executed (useful, unpadded)
     double apply_dense_flops = 0.0;  // 2 p^2 K_active of the same applies
     int chunk_w = 32;                // columns per support chunk (SLM_CHUNK_W)
@@ -773,6 +775,7 @@ int slm_create(int device, slm_ctx** out) {
         cudaMalloc(&ctx->d_stat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_stat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scount, sizeof(int) * kMaxScount) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_scal, sizeof(double) * 8) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess) {
         delete ctx;
         return 6;
@@ -792,6 +795,7 @@ void slm_destroy(slm_ctx* ctx) {
     if (ctx->d_stat) cudaFree(ctx->d_stat);
     if (ctx->h_stat) cudaFreeHost(ctx->h_stat);
     if (ctx->h_scount) cudaFreeHost(ctx->h_scount);
+    if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
     delete ctx;
@@ -952,6 +956,67 @@ int slm_gram_apply(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, 
     if (!ctx || !G || !K || !Z || !GZ) return fail(ctx, 1, "slm_gram_apply: null argument");
     if (ldz % 8 || pa % 2) return fail(ctx, 1, "slm_gram_apply: ldz must be a multiple of 8, pa even");
     return apply_batched(ctx, G, g_stride, pa, p, n_folds, K, Z, ldz, GZ, (cudaStream_t)stream);
+}
+
+// ---- unpenalised least squares: conjugate gradients on the Gram ------------------------
+size_t slm_gram_cg_workspace(int64_t p) { return (size_t)(3 * 8 * p + p + 8) * sizeof(double); }
+
+int slm_gram_cg(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, double tol, int32_t max_iter, void* work,
+                size_t work_bytes, double* X8, int32_t* iters_host, double* relres_host, void* stream) {
+    if (!ctx || !G || !work || !X8) return fail(ctx, 1, "slm_gram_cg: null argument");
+    if (pa % 2 || pa < p + 1) return fail(ctx, 1, "slm_gram_cg: pa must be even and hold the X^T y row");
+    if (work_bytes < slm_gram_cg_workspace(p)) return fail(ctx, 1, "slm_gram_cg: workspace too small");
+    if (!(tol > 0.0)) return fail(ctx, 1, "slm_gram_cg: tol must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* D8 = (double*)work;
+    double* GD8 = D8 + 8 * p;
+    double* GX8 = GD8 + 8 * p;
+    double* R = GX8 + 8 * p;
+    double* sc = R + p;
+    const int32_t K1 = 1;
+    CUDA_OK(cudaMemsetAsync(work, 0, slm_gram_cg_workspace(p), s));
+    CUDA_OK(cudaMemsetAsync(X8, 0, sizeof(double) * 8 * (size_t)p, s));
+    cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, nullptr, R, D8, sc);
+    LAUNCH_OK("cg_start_kernel");
+    auto scalars = [&]() -> int {  // sc -> host
+        CUDA_OK(cudaMemcpyAsync(ctx->h_scal, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaStreamSynchronize(s));
+        return 0;
+    };
+    int it = 0, restarts = 0;
+    double rel = 0.0;
+    const int check = 8;
+    while (true) {
+        bool conv = false;
+        for (; it < max_iter; ++it) {
+            if (it % check == 0) {
+                if (int rc = scalars()) return rc;
+                const double rs = ctx->h_scal[0], cc = ctx->h_scal[1];
+                if (!(rs == rs)) return fail(ctx, 7, "slm_gram_cg: non-finite residual");
+                rel = cc > 0.0 ? sqrt(rs / cc) : 0.0;
+                if (rel <= tol) {
+                    conv = true;
+                    break;
+                }
+            }
+            int rc = apply_batched(ctx, G, pa * pa, pa, p, 1, &K1, D8, 8, GD8, s, -1.0, FAM_LIPS);
+            if (rc) return rc;
+            cg_step_kernel<<<1, CG_T, 0, s>>>((int)p, X8, R, D8, GD8, sc);
+            LAUNCH_OK("cg_step_kernel");
+        }
+        // the recurrence drifts from the true residual: recompute c - G x and, if it is not
+        // there yet, restart the recurrence from x (residual replacement)
+        int rc = apply_batched(ctx, G, pa * pa, pa, p, 1, &K1, X8, 8, GX8, s, -1.0, FAM_LIPS);
+        if (rc) return rc;
+        cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, GX8, R, D8, sc);
+        LAUNCH_OK("cg_start_kernel");
+        if (int rc2 = scalars()) return rc2;
+        rel = ctx->h_scal[1] > 0.0 ? sqrt(ctx->h_scal[0] / ctx->h_scal[1]) : 0.0;
+        if (rel <= 4.0 * tol || it >= max_iter || (conv && ++restarts > 3)) break;
+    }
+    if (iters_host) *iters_host = it;
+    if (relres_host) *relres_host = rel;
+    return 0;
 }
 
 size_t slm_rowsparse_workspace(int64_t p, int64_t ldz, int n_folds) {

@@ -367,6 +367,23 @@ class Engine:
                                          self._ptr(GZ), self.stream), "slm_gram_apply")
         return GZ
 
+    def gram_cg(self, G, p, tol=1e-13, max_iter=None):
+        """Least-squares coefficients of ONE Gram G [pa, pa]: conjugate gradients on
+        G b = c (c = row p), products on the tensor-core apply.  Returns (X8, iters, relres):
+        X8 is [p, 8] with the solution in column 0."""
+        torch = self.torch
+        pa = G.shape[-1]
+        if max_iter is None:
+            max_iter = 10 * int(p) + 100
+        nbytes = self.lib.slm_gram_cg_workspace(p)
+        work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        X8 = torch.empty((p, 8), dtype=torch.float64, device=self.device)
+        iters, rel = ctypes.c_int32(0), ctypes.c_double(0.0)
+        self._ck(self.lib.slm_gram_cg(self.h, self._ptr(G), pa, p, float(tol), int(max_iter), self._ptr(work), nbytes,
+                                      self._ptr(X8), ctypes.byref(iters), ctypes.byref(rel), self.stream),
+                 "slm_gram_cg")
+        return X8, int(iters.value), float(rel.value)
+
     def gram_apply_rowsparse(self, G, p, K, Z, chunk_w=32):
         """The same product through the solver's row-sparse path (support lists per chunk of
         `chunk_w` columns are built on the device from Z)."""

@@ -19,6 +19,7 @@ from ._lasso import (
     RidgedGroupLasso,
     SparseGroupLasso,
 )
+from ._ols import OrdinaryLeastSquares
 from ._miqp import (
     L1L0,
     L2L0,
@@ -28,6 +29,7 @@ from ._miqp import (
 )
 
 __all__ = [
+    "OrdinaryLeastSquares",
     "Lasso",
     "BestSubsetSelection",
     "RidgedBestSubsetSelection",

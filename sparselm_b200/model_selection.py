@@ -91,6 +91,32 @@ def _metric(scoring, sse, sae, n_rows, sst):
     return 1.0 - sse / sst
 
 
+class _WarmStarts:
+    """candidate index -> device view [pe] of its solution on the first training fold that
+    solved it (start point of the refit).  The views are made on demand: building one per
+    (fold, candidate) eagerly costs more host time than the scoring kernels it delays."""
+
+    def __init__(self):
+        self._batches = []
+
+    def add(self, B, idxs, mine):
+        self._batches.append((B, np.asarray(idxs), [np.asarray(m) for m in mine]))
+
+    def get(self, ci, default=None):
+        for B, idxs, mine in self._batches:
+            for f, m in enumerate(mine):
+                pos = np.nonzero(idxs[m] == ci)[0] if len(m) else ()
+                if len(pos):
+                    return B[f, :, int(pos[0])]
+        return default
+
+    def __getitem__(self, ci):
+        v = self.get(ci)
+        if v is None:
+            raise KeyError(ci)
+        return v
+
+
 def _fold_key(est, spec):
     return (bool(est.fit_intercept), None if spec.col_perm is None else spec.col_perm.tobytes())
 
@@ -143,7 +169,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     iters_run = 0
 
     fds = {} if fds is None else dict(fds)  # may arrive pre-populated (prepare started early)
-    warm = {}  # candidate -> device view [pe] of its solution on some training fold (refit start)
+    warm = _WarmStarts()  # candidate -> device view [pe] of its solution on some training fold (refit start)
     batches = {}
     for ci, s in enumerate(specs):
         batches.setdefault(s.key, []).append(ci)
@@ -167,9 +193,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         t0 = time.perf_counter()
         out = solve_specs(engine, fd, [[specs[idxs[k]] for k in mine[f]] for f in range(n_splits)], **opts)
         t1 = time.perf_counter()
-        for f in range(n_splits):
-            for pos, k in enumerate(mine[f]):
-                warm.setdefault(int(idxs[k]), out["B"][f, :, pos])
+        warm.add(out["B"], idxs, mine)
         K = len(idxs)
         icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
         wtd = bool(fd.extra.get("weighted"))
@@ -275,7 +299,7 @@ class GridSearchCV(_SkGridSearchCV):
     # ------------------------------------------------------------------ #
     def _batch_plan(self, X, y, params):
         est = self.estimator
-        if not isinstance(est, EngineRegressor) or y is None:
+        if not isinstance(est, EngineRegressor) or y is None or not getattr(est, "_batchable", True):
             return None
         # fit params: only sample_weight is understood by the batched seam (strictly positive:
         # the unweighted CV scores are recovered from the sqrt(sw)-scaled rows)

@@ -38,7 +38,20 @@ specs = [e._problem_spec(p) for e in ests]
 opts = est._engine_options()
 
 
+E2E = len(sys.argv) > 2 and sys.argv[2] == "e2e"  # public API on pinned host arrays (refit included)
+if E2E:
+    from sparselm_b200.model_selection import GridSearchCV  # noqa: E402
+
+    Xh = torch.from_numpy(X).pin_memory().numpy()
+    grid = {"alpha": list(alphas)}
+
+
 def step():
+    if E2E:
+        gs = GridSearchCV(clone(est), grid, cv=F)
+        if shard is not None:
+            gs._shard = shard
+        return gs.fit(Xh, y)
     return batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error", shard=shard)
 
 
@@ -61,7 +74,7 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
 os.makedirs("gpurun_out", exist_ok=True)
-path = f"gpurun_out/timeline_w{world}_r{rank}.json"
+path = f"gpurun_out/timeline{'_e2e' if E2E else ''}_w{world}_r{rank}.json"
 prof.export_chrome_trace(path)
 ev = json.load(open(path))["traceEvents"]
 ks = sorted([e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e],
