@@ -36,6 +36,25 @@ _DEVICE_SCORERS = {None, "r2", "neg_root_mean_squared_error", "neg_mean_squared_
                    "neg_mean_absolute_error"}
 
 
+def _device_metrics(scoring):
+    """`scoring` as the batched seam understands it: one device scorer name, or a dict
+    {metric name: device scorer name} for sklearn's list / tuple / dict multi-metric forms;
+    None when some scorer has to run on the host (callables, other metrics)."""
+    if scoring is None:
+        return "r2"
+    if isinstance(scoring, str):
+        return scoring if scoring in _DEVICE_SCORERS else None
+    if isinstance(scoring, (list, tuple, set)):
+        names = list(scoring)
+        if not names or len(set(names)) != len(names):
+            return None
+        scoring = {nm: nm for nm in names}
+    if isinstance(scoring, dict) and scoring and all(
+            isinstance(k, str) and isinstance(v, str) and v in _DEVICE_SCORERS for k, v in scoring.items()):
+        return dict(scoring)
+    return None
+
+
 def _select_best_index_onestd(refit, refit_metric, results):
     """One-standard-error rule (reference model_selection.py:190-223): among the
     candidates whose summed non-negative numeric hyper-parameters are at least those
@@ -156,13 +175,18 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     n, p = X.shape
     n_splits, n_cand = len(test_folds), len(specs)
     yv = np.asarray(y, dtype=np.float64)
-    test_scores = np.full((n_cand, n_splits), np.nan)
-    train_scores = np.full((n_cand, n_splits), np.nan) if return_train_score else None
+    # one scorer name, or {metric name: scorer name}: every device scorer derives from the same
+    # two residual sums, so a multi-metric search costs nothing extra on the GPU
+    multi = not isinstance(scoring, str)
+    metrics = dict(scoring) if multi else {"score": scoring}
+    test_tabs = {m: np.full((n_cand, n_splits), np.nan) for m in metrics}
+    train_tabs = {m: np.full((n_cand, n_splits), np.nan) for m in metrics} if return_train_score else None
+    train_scores = train_tabs  # (None check below)
     fit_time = np.zeros(n_cand)
     score_time = np.zeros(n_cand)
     info = dict(n_iter=np.zeros((n_cand, n_splits), dtype=int), status=np.zeros((n_cand, n_splits), dtype=int),
                 gap=np.zeros((n_cand, n_splits)), n_pass=np.zeros((n_cand, n_splits), dtype=int))
-    need_r2 = scoring == "r2"
+    need_r2 = "r2" in metrics.values()
     sst_test = np.array([float(((yv[t] - yv[t].mean()) ** 2).sum()) if need_r2 else 0.0 for t in test_folds])
     tot_sum, tot_sq = float(yv.sum()), float((yv * yv).sum())
     n_unconverged = 0
@@ -219,12 +243,15 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             nt = len(test_folds[f])
             kf = len(mine[f])
             ci = idxs[mine[f]]
-            test_scores[ci, f] = _metric(scoring, sc[f, 0, :kf], sc[f, 1, :kf], nt, sst_test[f])
+            for m, scorer in metrics.items():
+                test_tabs[m][ci, f] = _metric(scorer, sc[f, 0, :kf], sc[f, 1, :kf], nt, sst_test[f])
             if train_scores is not None:
                 ntr = n - nt
                 s_tr = tot_sum - float(yv[test_folds[f]].sum())
                 q_tr = tot_sq - float((yv[test_folds[f]] ** 2).sum())
-                train_scores[ci, f] = _metric(scoring, tsc[f, 0, :kf], tsc[f, 1, :kf], ntr, q_tr - s_tr * s_tr / ntr)
+                for m, scorer in metrics.items():
+                    train_tabs[m][ci, f] = _metric(scorer, tsc[f, 0, :kf], tsc[f, 1, :kf], ntr,
+                                                   q_tr - s_tr * s_tr / ntr)
             info["n_iter"][ci, f] = out["n_iter"][f, :kf]
             info["status"][ci, f] = out["status"][f, :kf]
             info["gap"][ci, f] = out["gap"][f, :kf]
@@ -235,9 +262,9 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         iters_run += int(out["iters_run"])
     if shard is not None and shard.world > 1:
         # the only data-path exchange of the sharded grid: one sum of the zero-padded tables
-        tabs = [np.nan_to_num(test_scores, nan=0.0)]
+        tabs = [np.nan_to_num(test_tabs[m], nan=0.0) for m in metrics]
         if train_scores is not None:
-            tabs.append(np.nan_to_num(train_scores, nan=0.0))
+            tabs += [np.nan_to_num(train_tabs[m], nan=0.0) for m in metrics]
         keys = list(info)
         tabs += [info[k].astype(np.float64) for k in keys] + [np.array([[float(n_unconverged)]])]
         flat = shard.allreduce_sum_numpy(np.concatenate([t.ravel() for t in tabs]), engine.device)
@@ -245,12 +272,17 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         for t in tabs:
             parts.append(flat[o:o + t.size].reshape(t.shape))
             o += t.size
-        test_scores = parts.pop(0)
+        for m in metrics:
+            test_tabs[m] = parts.pop(0)
         if train_scores is not None:
-            train_scores = parts.pop(0)
+            for m in metrics:
+                train_tabs[m] = parts.pop(0)
         for k in keys:
             info[k] = parts.pop(0).astype(info[k].dtype)
         n_unconverged = int(round(float(parts.pop(0)[0, 0])))
+    test_scores = test_tabs if multi else test_tabs["score"]
+    if train_scores is not None:
+        train_scores = train_tabs if multi else train_tabs["score"]
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
                 info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm)
 
@@ -310,10 +342,13 @@ class GridSearchCV(_SkGridSearchCV):
             if k != "sample_weight":
                 return None
             sw = v
-        if not (self.scoring is None or (isinstance(self.scoring, str) and self.scoring in _DEVICE_SCORERS)):
+        if _device_metrics(self.scoring) is None:
             return None
         if callable(self.refit) or hasattr(X, "columns"):
             return None
+        if not isinstance(_device_metrics(self.scoring), str) and self.refit is not False and (
+                not isinstance(self.refit, str) or self.refit not in _device_metrics(self.scoring)):
+            return None  # sklearn's own loop raises its multi-metric refit error
         if self.opt_selection_method not in ("max_score", "one_std_score"):
             raise NotImplementedError(f"Method {self.opt_selection_method} not implemented!")
         try:
@@ -386,7 +421,8 @@ class GridSearchCV(_SkGridSearchCV):
         base = self.estimator
         opts = base._engine_options()
         engine = get_engine(opts.pop("device", None))
-        scoring = self.scoring if self.scoring is not None else "r2"
+        scoring = _device_metrics(self.scoring)
+        multi = not isinstance(scoring, str)
         test_folds = [np.asarray(test) for _, test in splits]
         cache = getattr(self, "_fd_cache", None)
         sw = plan.get("sample_weight")
@@ -438,16 +474,17 @@ class GridSearchCV(_SkGridSearchCV):
                     ma[i] = v
             results[f"param_{name}"] = ma
         results["params"] = candidates
-        _store("test_score", test_scores, splits_=True, rank=True)
-        if train_scores is not None:
-            _store("train_score", train_scores, splits_=True)
+        for m in (scoring if multi else ["score"]):
+            _store(f"test_{m}", test_scores[m] if multi else test_scores, splits_=True, rank=True)
+            if train_scores is not None:
+                _store(f"train_{m}", train_scores[m] if multi else train_scores, splits_=True)
 
-        self.multimetric_ = False
-        refit_metric = "score"
+        self.multimetric_ = multi
+        refit_metric = self.refit if multi else "score"
         if self.refit or not self.multimetric_:
             self.best_index_ = int(self._select_best_index(self.refit, refit_metric, results))
-            self.best_score_ = results["mean_test_score"][self.best_index_]
-            self.best_score_std_ = results["std_test_score"][self.best_index_]
+            self.best_score_ = results[f"mean_test_{refit_metric}"][self.best_index_]
+            self.best_score_std_ = results[f"std_test_{refit_metric}"][self.best_index_]
             self.best_params_ = results["params"][self.best_index_]
         if self.refit:
             bi = self.best_index_
@@ -458,9 +495,10 @@ class GridSearchCV(_SkGridSearchCV):
             self.best_estimator_.n_features_in_ = p
             self.best_estimator_._fit_prepared(engine, fds[fkey], spec, dict(opts), B0=res["warm"].get(bi))
             self.refit_time_ = time.time() - t0
-        from sklearn.metrics import check_scoring
+        from sklearn.metrics import check_scoring, get_scorer
 
-        self.scorer_ = check_scoring(base, scoring=self.scoring)
+        self.scorer_ = {m: get_scorer(v) for m, v in scoring.items()} if multi else \
+            check_scoring(base, scoring=self.scoring)
         self.cv_results_ = results
         self.n_splits_ = n_splits
         self.solver_info_ = info

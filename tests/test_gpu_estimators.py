@@ -393,6 +393,40 @@ def test_grid_search_two_parameters_and_r2_default_scoring():
         assert gs.cv_results_["mean_test_score"][i] == pytest.approx(ref.mean(), rel=1e-7)
 
 
+def test_multi_metric_search_is_batched_and_matches_sklearn_loop():
+    """Several device scorers in one search: same tables as sklearn's
+    per-fit multi-metric loop over the same engine-backed estimator."""
+    from sklearn.model_selection import GridSearchCV as SkGS
+
+    rng = np.random.default_rng(12)
+    X = rng.standard_normal((90, 16))
+    y = X[:, :3] @ [1.5, -1.0, 0.7] + 0.3 * rng.standard_normal(90) + 1.0
+    groups = np.repeat(np.arange(4), 4)
+    grid = {"alpha": [0.01, 0.05, 0.2, 0.8]}
+    scoring = {"rmse": "neg_root_mean_squared_error", "mae": "neg_mean_absolute_error", "r2": "r2"}
+    est = GroupLasso(groups=groups, fit_intercept=True, solver_options={"tol": 1e-12})
+    gs = GridSearchCV(est, grid, cv=3, scoring=scoring, refit="mae", return_train_score=True).fit(X, y)
+    sk = SkGS(est, grid, cv=3, scoring=scoring, refit="mae", return_train_score=True).fit(X, y)
+    assert gs.batched_ and gs.multimetric_
+    for m in scoring:
+        for key in (f"mean_test_{m}", f"std_test_{m}", f"mean_train_{m}", f"split1_test_{m}"):
+            npt.assert_allclose(gs.cv_results_[key], sk.cv_results_[key], rtol=1e-7, atol=1e-9)
+        npt.assert_array_equal(gs.cv_results_[f"rank_test_{m}"], sk.cv_results_[f"rank_test_{m}"])
+    assert gs.best_index_ == sk.best_index_ and gs.best_params_ == sk.best_params_
+    assert gs.best_score_ == pytest.approx(sk.best_score_, rel=1e-7)
+    npt.assert_allclose(gs.best_estimator_.coef_, sk.best_estimator_.coef_, atol=1e-7)
+    assert set(gs.scorer_) == set(scoring)
+    # list form, no refit
+    g2 = GridSearchCV(est, grid, cv=3, scoring=["r2", "neg_mean_squared_error"], refit=False).fit(X, y)
+    assert g2.batched_ and not hasattr(g2, "best_index_")
+    npt.assert_allclose(g2.cv_results_["mean_test_neg_mean_squared_error"],
+                        -(gs.cv_results_["split0_test_rmse"] ** 2 + gs.cv_results_["split1_test_rmse"] ** 2
+                          + gs.cv_results_["split2_test_rmse"] ** 2) / 3, rtol=1e-9)
+    # a host-side scorer in the mix falls back to sklearn's loop (still engine fits)
+    g3 = GridSearchCV(est, {"alpha": [0.05, 0.2]}, cv=3, scoring=["r2", "explained_variance"], refit="r2").fit(X, y)
+    assert not g3.batched_ and "mean_test_explained_variance" in g3.cv_results_
+
+
 # ---- reference tests/test_model_selection.py:122-167 (one-std rule) -----------------------
 def test_onestd_selects_larger_alpha_and_sparser_model():
     success = 0
