@@ -407,12 +407,54 @@ def run_engine(args):
         ms = float(t.item())
     value = n_fits / (ms / 1e3)
 
+    # ---- weak-scaling companion (N > 1): the grid grows with the GPUs -------------------
+    # the named config is a FIXED 100 x 5 grid (strong scaling, the headline `value`); the
+    # usual way such a search grows is a second hyper-parameter (sparse-lm's own SGL example
+    # sweeps alpha x l1_ratio), so next to it: N l1_ratio values x 100 alphas x 5 folds on N GPUs
+    weak = None
+    if world > 1 and args.workload == "c3" and not args.no_weak:
+        ratios = np.linspace(0.2, 0.8, world)
+        w_ests, w_specs = [], []
+        for r in ratios:
+            work.set_params(l1_ratio=float(r))
+            for a in alphas:
+                work.set_params(alpha=a)
+                w_specs.append(work._problem_spec(p))
+                w_ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
+
+        def step_weak():
+            return batched_cv(engine, Xd, y, folds, w_ests, w_specs, dict(opts), "neg_root_mean_squared_error",
+                              shard=shard)
+
+        for _ in range(2):
+            wres = step_weak()
+        wt = []
+        for _ in range(args.steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            wres = step_weak()
+            e1.record()
+            barrier()
+            wt.append(e0.elapsed_time(e1))
+        wms = float(np.mean(wt))
+        import torch.distributed as dist
+
+        t = torch.tensor([wms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wms = float(t.item())
+        weak = {"value": len(w_specs) * F / (wms / 1e3), "unit": "fits/s", "ms_per_step": wms,
+                "n_fits_per_step": len(w_specs) * F, "unconverged": int(wres["n_unconverged"]),
+                "grid": f"{world} l1_ratio values x {len(alphas)} alphas x {F} folds "
+                        f"(one l1_ratio line of the named config per GPU)"}
+
     # ---- end-to-end arm: public API on host (pinned) arrays --------------------------
     if wl.get("device_gen"):
         e2e = None  # 25.6 GB design generated on the device: no host copy to start from
     else:
         e2e = run_e2e(args, torch, wl, shard, barrier, world, dev)
-    finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank)
+    finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank,
+           weak)
 
 
 def run_e2e(args, torch, wl, shard, barrier, world, dev):
@@ -457,7 +499,8 @@ def run_e2e(args, torch, wl, shard, barrier, world, dev):
             "api": "sparselm_b200.model_selection.GridSearchCV.fit (pinned host X, refit included)"}
 
 
-def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank):
+def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank,
+           weak=None):
     if rank != 0:
         return
     X, alphas, F = wl["X"], wl["alphas"], wl["F"]
@@ -509,6 +552,8 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if weak is not None:
+        line["weak_scaling"] = weak
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
     print(json.dumps(line))
@@ -522,6 +567,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling companion run (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":

@@ -40,6 +40,10 @@ typedef struct slm_ctx slm_ctx;
 int slm_version(void);
 int slm_create(int device, slm_ctx** out);
 void slm_destroy(slm_ctx* ctx);
+/* engine switches (the SLM_* environment variables read at slm_create, settable later):
+ * "coop" (cooperative few-column iterations), "small_fused" (fused small-design iterations),
+ * "dense_apply" (solver uses the dense Gram apply), "chunk_w" (columns per support chunk). */
+int slm_set_option(slm_ctx* ctx, const char* name, int value);
 const char* slm_last_error(const slm_ctx* ctx);
 int slm_sm_count(const slm_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
@@ -149,6 +153,8 @@ typedef struct slm_batch {
     /* host outputs */
     int32_t iters_run;     /* outer iterations executed */
     int32_t n_unconverged; /* columns that hit max_iter */
+    int32_t max_group;     /* in: rows of the largest group (gptr_dev given), 0 = unknown; lets the
+                              few-column cooperative iterations size their row ranges */
 } slm_batch;
 
 size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups);

@@ -53,6 +53,7 @@ class SlmBatch(ctypes.Structure):
         ("lipschitz_dev", c_vp),
         ("iters_run", c_i32),
         ("n_unconverged", c_i32),
+        ("max_group", c_i32),
     ]
 
 
@@ -61,6 +62,7 @@ SYMBOLS = {
     "slm_version": (ctypes.c_int, []),
     "slm_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
     "slm_destroy": (None, [c_vp]),
+    "slm_set_option": (ctypes.c_int, [c_vp, ctypes.c_char_p, ctypes.c_int]),
     "slm_last_error": (ctypes.c_char_p, [c_vp]),
     "slm_sm_count": (ctypes.c_int, [c_vp]),
     "slm_launch_count": (c_i64, [c_vp]),

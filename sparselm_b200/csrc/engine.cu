@@ -27,6 +27,7 @@
 #include "solver_kernels.cuh"
 #include "whiten_kernels.cuh"
 #include "cg_kernels.cuh"
+#include "coop_kernels.cuh"
 
 using namespace slm;
 
@@ -58,6 +59,8 @@ struct slm_ctx {
     int n_flags_cap = 0;
     unsigned long long* d_stat = nullptr;  // executed contraction length of the row-sparse applies
     unsigned long long* h_stat = nullptr;
+    unsigned long long* d_ratio = nullptr;  // worst gap / tolerance ratio of a convergence check
+    unsigned long long* h_ratio = nullptr;
     int* h_scount = nullptr;         // pinned copy of the support-list lengths (chunk-width choice)
     double* h_scal = nullptr;        // pinned scalars of the conjugate-gradient loop
     double apply_exec_flops = 0.0;   // flops the row-sparse applies executed (useful, unpadded)
@@ -65,6 +68,8 @@ struct slm_ctx {
     int chunk_w = 32;                // columns per support chunk (SLM_CHUNK_W)
     bool dense_apply = false;        // SLM_DENSE_APPLY=1: solver uses the dense apply (A/B runs)
     bool small_fused = true;         // SLM_SMALL_FUSED=0: never use the fused small-design iterations
+    bool coop = true;                // SLM_COOP=0: never use the cooperative few-column iterations
+    int coop_max_smem = 0;           // opt-in shared memory per block of the device
     int force_sparse_shape = -1;     // SLM_FORCE_SPARSE_SHAPE
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
@@ -769,11 +774,16 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_CHUNK_W")) ctx->chunk_w = std::max(8, atoi(e) / 8 * 8);
     if (const char* e = getenv("SLM_DENSE_APPLY")) ctx->dense_apply = atoi(e) != 0;
     if (const char* e = getenv("SLM_SMALL_FUSED")) ctx->small_fused = atoi(e) != 0;
+    if (const char* e = getenv("SLM_COOP")) ctx->coop = atoi(e) != 0;
+    ctx->coop_max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (!prop.cooperativeLaunch) ctx->coop = false;
     ctx->n_flags_cap = 1 << 20;
     if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
         cudaMalloc(&ctx->d_stat, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_stat, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&ctx->d_ratio, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost(&ctx->h_ratio, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scount, sizeof(int) * kMaxScount) != cudaSuccess ||
         cudaMallocHost(&ctx->h_scal, sizeof(double) * 8) != cudaSuccess ||
         cudaMallocHost(&ctx->h_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess) {
@@ -794,11 +804,29 @@ void slm_destroy(slm_ctx* ctx) {
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->d_stat) cudaFree(ctx->d_stat);
     if (ctx->h_stat) cudaFreeHost(ctx->h_stat);
+    if (ctx->d_ratio) cudaFree(ctx->d_ratio);
+    if (ctx->h_ratio) cudaFreeHost(ctx->h_ratio);
     if (ctx->h_scount) cudaFreeHost(ctx->h_scount);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_counter) cudaFreeHost(ctx->h_counter);
     delete ctx;
+}
+
+int slm_set_option(slm_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return 1;
+    const std::string nm(name);
+    if (nm == "coop")
+        ctx->coop = value != 0;
+    else if (nm == "small_fused")
+        ctx->small_fused = value != 0;
+    else if (nm == "dense_apply")
+        ctx->dense_apply = value != 0;
+    else if (nm == "chunk_w")
+        ctx->chunk_w = std::max(8, value / 8 * 8);
+    else
+        return fail(ctx, 1, "slm_set_option: unknown option " + nm);
+    return 0;
 }
 
 const char* slm_last_error(const slm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -1159,6 +1187,13 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     // (fista_small_kernel, Gram in shared memory); the checks use the regular dense path
     const bool small = ctx->small_fused && p <= kSmallPMax;
     const bool sparse = !ctx->dense_apply && !small;
+    // few columns on a large design: the whole GPU iterates on them inside one cooperative
+    // launch between two convergence checks (coop_kernels.cuh)
+    bool coop = false;
+    CoopArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    int coop_nb = 0;
+    size_t coop_sm = 0;
 
     SolveDev sp;
     memset(&sp, 0, sizeof(sp));
@@ -1197,6 +1232,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.n_iter = bt->n_iter_dev;
     sp.status = bt->status_dev;
     sp.counter = ctx->d_counter;
+    sp.ratio = ctx->d_ratio;
     sp.zflag = sparse ? zflag : nullptr;
     sp.nblk = (int)(ldz / SC);
     sp.tol = bt->tol;
@@ -1218,6 +1254,32 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     bt->iters_run = 0;
     bt->n_unconverged = 0;
     if (Kmax0 == 0) return 0;
+    if (!small && ctx->coop && Ktot <= kCoopMaxProb) {
+        const int nprob = (int)Ktot;
+        const int maxg = bt->gptr_dev ? bt->max_group : 1;  // 0: the caller did not say
+        coop_nb = (int)std::min<int64_t>(ctx->sm_count / nprob, std::max<int64_t>(1, p / 16));
+        coop_sm = coop_smem((int)p);
+        if (maxg > 0 && coop_nb >= 1 && (p + coop_nb - 1) / coop_nb + maxg <= CO_ROWS &&
+            coop_sm <= (size_t)ctx->coop_max_smem) {
+            coop = true;
+            ca.nprob = nprob;
+            ca.seg = coop_seg((int)p);
+            ca.buf[0] = T;
+            ca.buf[1] = T + (size_t)nprob * p;
+            ca.buf[2] = GZ;
+            ca.dpart = part;
+            int q = 0;
+            for (int f = 0; f < F; ++f)
+                for (int k = 0; k < bt->K[f]; ++k, ++q) {
+                    ca.pf[q] = f;
+                    ca.pk[q] = k;
+                }
+            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)coop_sm));
+            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)coop_sm));
+        }
+    }
 
     init_cols_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(theta, tmom, flag, colmap, sp.status, sp.n_iter,
                                                                     bt->skip_dev, (long long)cols, (int)ldz);
@@ -1274,6 +1336,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         wide = (fn == 0.0) || (tw < tn);
     };
     int next_check = 0, interval = check_every;  // small mode: checks get rarer while nothing converges
+    double prev_ratio = 0.0;
+    int prev_check = 0;
     const int p32 = (int)round_up(p, 32);
     const int nsplit = std::max(1, std::min(8, 256 / p32));
     const size_t small_smem = fista_small_smem((int)p, p32, nsplit);
@@ -1285,7 +1349,22 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     }
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
-        const bool check = small ? (it == next_check) : (it % check_every == 0);
+        const bool check = (small || coop) ? (it == next_check) : (it % check_every == 0);
+        if (coop && !check) {
+            // every iteration up to the next check in one cooperative launch: the SMs share the
+            // column(s), one grid barrier per iteration
+            int n_inner = std::min(next_check, (int)bt->max_iter) - it;
+            int parv = par;
+            FamTimer tm(ctx, FAM_PROX, s, 0.0);
+            void* args[] = {(void*)&sp, (void*)&ca, (void*)&parv, (void*)&n_inner};
+            const dim3 cgrid2((unsigned)coop_nb, (unsigned)ca.nprob);
+            CUDA_OK(cudaLaunchCooperativeKernel(grouped ? (const void*)fista_coop_kernel<true>
+                                                        : (const void*)fista_coop_kernel<false>,
+                                                cgrid2, dim3(CO_T), args, coop_sm, s));
+            ctx->launches++;
+            it += n_inner - 1;
+            continue;
+        }
         if (small && !check) {
             // every iteration up to the next check (or max_iter) in one launch
             const int n_inner = std::min(next_check, (int)bt->max_iter) - it;
@@ -1303,7 +1382,11 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         // the supports change fastest in the first iterations (a cold start is all-zero, then
         // every weakly penalised column fills up): re-decide the width there without waiting
         // for the next convergence check
-        const bool probe = can_adapt && !check && (it == 1 || it == 3 || it == 6);
+        if (coop && sparse && it > 0) {  // the cooperative iterations do not maintain the row flags
+            zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
+            LAUNCH_OK("zflags_kernel");
+        }
+        const bool probe = can_adapt && !check && !coop && (it == 1 || it == 3 || it == 6);
         const int cw_now = (wide && !check && !probe) ? cw_wide : cw;
         int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
                                           scount, s, algo)
@@ -1317,6 +1400,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         if (check) {
             CUDA_OK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(int) * SLM_MAX_FOLDS, s));
+            CUDA_OK(cudaMemsetAsync(ctx->d_ratio, 0, sizeof(unsigned long long), s));
             {
                 FamTimer tm(ctx, FAM_GAP, s, 0.0);
                 if (grouped)
@@ -1329,6 +1413,9 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             ctx->launches++;
             CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS,
                                     cudaMemcpyDeviceToHost, s));
+            if (small || coop)
+                CUDA_OK(cudaMemcpyAsync(ctx->h_ratio, ctx->d_ratio, sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToHost, s));
             CUDA_OK(cudaStreamSynchronize(s));
             n_active = 0;
             bool shrink = false;
@@ -1338,9 +1425,22 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
                 if (round_up(n_active_f[f], 8) < round_up(Kcur[f], 8)) shrink = true;
             }
             if (n_active == 0) break;
-            do_compact = shrink && !small;  // idle CTAs of the fused kernel exit at once: no compaction
-            if (small) {  // checks at 0, c, 3c, 7c, ... (c = check_every), at most 2048 apart
-                next_check = it + interval;
+            do_compact = shrink && !small && !coop;  // idle CTAs of the fused kernels cost nothing: no compaction
+            if (small || coop) {
+                // checks at 0, c, 3c, 7c, ... (c = check_every), at most 2048 apart -- sooner when
+                // the worst gap/tolerance ratio of the last two checks says the tolerance is
+                // nearer than that (linear-rate extrapolation + 15 %)
+                int step_to = interval;
+                double ratio;
+                memcpy(&ratio, ctx->h_ratio, sizeof(double));
+                if (prev_ratio > 0.0 && ratio > 1.0 && ratio < prev_ratio && it > prev_check) {
+                    const double rate = log(prev_ratio / ratio) / (double)(it - prev_check);
+                    const double need = 1.15 * log(ratio) / rate + 1.0;
+                    if (need < (double)step_to) step_to = std::max(std::max(2, check_every / 2), (int)ceil(need));
+                }
+                prev_ratio = ratio;
+                prev_check = it;
+                next_check = it + step_to;
                 interval = std::min(interval * 2, 2048);
             }
             if (can_adapt) decide_width();

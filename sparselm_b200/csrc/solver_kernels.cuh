@@ -46,6 +46,9 @@ struct SolveDev {
     double *gap, *primal;
     int *n_iter, *status;
     int* counter;
+    // max over the still-iterating columns of gap / (tol * scale) at a convergence check, as the
+    // bit pattern of a positive double (atomicMax): lets the host pace sparse checks (may be NULL)
+    unsigned long long* ratio;
     // row support of Z per block of SC columns (row-sparse Gram apply): zflag[f][j][cb] != 0
     // iff some active column of column block cb has Z[f][j][k] != 0
     unsigned char* zflag;
@@ -575,6 +578,7 @@ __global__ void gap_final_kernel(const __grid_constant__ SolveDev sp, int it, in
             if (sp.status) sp.status[obase] = finite ? 0 : 2;
         } else {
             atomicAdd(sp.counter + f, 1);
+            if (sp.ratio) atomicMax(sp.ratio, (unsigned long long)__double_as_longlong(gap / (sp.tol * scale)));
         }
     } else {
         const bool undecided = sp.status ? sp.status[obase] == -1 : true;

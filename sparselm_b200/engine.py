@@ -241,6 +241,10 @@ class Engine:
             t = t.to(self.device, non_blocking=True)
         return t.contiguous()
 
+    def set_option(self, name, value):
+        """Engine switch by name ("coop", "small_fused", "dense_apply", "chunk_w")."""
+        self._ck(self.lib.slm_set_option(self.h, name.encode(), int(value)), "slm_set_option")
+
     def launch_count(self):
         return int(self.lib.slm_launch_count(self.h))
 
@@ -687,6 +691,7 @@ class Engine:
         bt.n_folds, bt.n_groups, bt.p, bt.pa, bt.ldz = F, Gn, p, pa, ldz
         bt.G_dev, bt.g_stride = Gs.data_ptr(), pa * pa
         bt.gptr_dev = 0 if gptr_dev is None else gptr_dev.data_ptr()
+        bt.max_group = 0 if g0.gptr is None else int(np.diff(np.asarray(g0.gptr)).max(initial=0))
         lips_dev = lipschitz if isinstance(lipschitz, torch.Tensor) else None
         bt.lipschitz_dev = 0 if lips_dev is None else lips_dev.data_ptr()
         for f in range(F):
