@@ -102,7 +102,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    # SLM_B200_LIB: an alternative build of the same ABI (tuning variants); the default is the in-tree build
+    return os.environ.get("SLM_B200_LIB") or _build.LIB_PATH
 
 
 def load():

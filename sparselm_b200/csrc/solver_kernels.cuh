@@ -20,6 +20,12 @@
 
 namespace slm {
 
+#ifndef SLM_PROX_UR
+#define SLM_PROX_UR 1    // rows of a group in flight together in prox_main_kernel
+#endif
+#ifndef SLM_PROX_MINB
+#define SLM_PROX_MINB 4  // resident blocks per SM prox_main_kernel is compiled for
+#endif
 constexpr int SC = 8;              // grid columns per block
 constexpr int SG = 32;             // group lanes per block
 constexpr int ST = SC * SG;        // threads per block
@@ -119,7 +125,7 @@ __device__ __forceinline__ bool sub_any(unsigned qmask, bool v) {
 // ---- K6a: GB recurrence, gradient step, soft-threshold, group shrink, ridge -----
 // writes T = beta_{k+1} and the per-chunk restart dot  sum (z - b+)(b+ - b)
 template <bool GROUPED>
-__global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ SolveDev sp, int par) {
+__global__ void __launch_bounds__(ST, SLM_PROX_MINB) prox_main_kernel(const __grid_constant__ SolveDev sp, int par) {
     const int f = blockIdx.z, chunk = blockIdx.y;
     const int Kf = sp.K[f];
     const int k0 = blockIdx.x * SC;
@@ -151,25 +157,45 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
     const int rstep = GROUPED ? SUB : 1;
     const unsigned qmask = 0x01010101u << c;
 
+    constexpr int UR = GROUPED ? SLM_PROX_UR : 1;  // rows of a group whose loads are in flight together
     double dot = 0.0;
     for (int i = 0; i < sp.gpt; ++i) {
         const int g = (chunk * sp.gpt + i) * gstep + gsl;
         if (g >= sp.Gn) break;  // uniform over the sub-lanes of a group
         const int ja = sp.gptr ? sp.gptr[g] : g;
         const int jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+        // rows in chunks of UR: all loads of a chunk are issued before its first store (the state
+        // arrays are not restrict-qualified, a store in between would serialise the loads)
         double ss = 0.0;
-        for (int j = ja + sub; j < jb; j += rstep) {
-            const long long e = sbase + (long long)j * ldz;
-            const double gz = sp.GZ[e];
-            const double gb = (gz + theta * sp.GB[e]) * inv1pt;
-            const double v = sp.Z[e] - son * (gz - cvec[j]);
-            const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
-            const double u = softt(v, step * w1);
-            if (active) {
-                sp.GB[e] = gb;
-                sp.T[e] = u;  // stash; scaled below
+        for (int j0 = ja + sub; j0 < jb; j0 += UR * rstep) {
+            double gz[UR], gbo[UR], z[UR], cj[UR], w1[UR];
+#pragma unroll
+            for (int r = 0; r < UR; ++r) {
+                const int j = j0 + r * rstep;
+                if (j < jb) {
+                    const long long e = sbase + (long long)j * ldz;
+                    gz[r] = sp.GZ[e];
+                    gbo[r] = sp.GB[e];
+                    z[r] = sp.Z[e];
+                    cj[r] = cvec[j];
+                    w1[r] = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
+                }
             }
-            ss += u * u;
+#pragma unroll
+            for (int r = 0; r < UR; ++r) {
+                const int j = j0 + r * rstep;
+                if (j < jb) {
+                    const long long e = sbase + (long long)j * ldz;
+                    const double gb = (gz[r] + theta * gbo[r]) * inv1pt;
+                    const double v = z[r] - son * (gz[r] - cj[r]);
+                    const double u = softt(v, step * w1[r]);
+                    if (active) {
+                        sp.GB[e] = gb;
+                        sp.T[e] = u;  // stash; scaled below
+                    }
+                    ss += u * u;
+                }
+            }
         }
         if (GROUPED) ss = sub_sum(qmask, ss);
         const double nrm = sqrt(ss);
@@ -178,11 +204,27 @@ __global__ void __launch_bounds__(ST) prox_main_kernel(const __grid_constant__ S
         double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
         scale = scale / (1.0 + step * d2);
         if (active) {
-            for (int j = ja + sub; j < jb; j += rstep) {
-                const long long e = sbase + (long long)j * ldz;
-                const double bn = scale * sp.T[e];
-                sp.T[e] = bn;
-                dot += (sp.Z[e] - bn) * (bn - sp.B[e]);
+            for (int j0 = ja + sub; j0 < jb; j0 += UR * rstep) {
+                double t[UR], z[UR], bo[UR];
+#pragma unroll
+                for (int r = 0; r < UR; ++r) {
+                    const int j = j0 + r * rstep;
+                    if (j < jb) {
+                        const long long e = sbase + (long long)j * ldz;
+                        t[r] = sp.T[e];
+                        z[r] = sp.Z[e];
+                        bo[r] = sp.B[e];
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < UR; ++r) {
+                    const int j = j0 + r * rstep;
+                    if (j < jb) {
+                        const double bn = scale * t[r];
+                        sp.T[sbase + (long long)j * ldz] = bn;
+                        dot += (z[r] - bn) * (bn - bo[r]);
+                    }
+                }
             }
         }
     }

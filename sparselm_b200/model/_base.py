@@ -302,8 +302,12 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, che
     B_start = None
     if B0 is not None and s0.adaptive is None and not s0.standardize:
         ldz0 = max(8, (max(Ks) + 7) // 8 * 8)
-        B_start = torch.zeros((F, s0.pe, ldz0), dtype=torch.float64, device=engine.device)
-        B_start[0, :, 0] = B0
+        if B0.dim() == 3:  # a start point per (fold, column), solver feature order
+            assert tuple(B0.shape) == (F, s0.pe, ldz0), (tuple(B0.shape), (F, s0.pe, ldz0))
+            B_start = B0
+        else:
+            B_start = torch.zeros((F, s0.pe, ldz0), dtype=torch.float64, device=engine.device)
+            B_start[0, :, 0] = B0
     if max_iter is None:
         # fused small-design iterations cost ~0.3 us each: ill-conditioned small problems (p > n,
         # vanishing penalties) get the iterations plain accelerated proximal gradient needs
