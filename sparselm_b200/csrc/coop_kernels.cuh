@@ -39,8 +39,19 @@ struct CoopArgs {
     double* dpart;   // [2][nprob][NB]
     int nprob;
     int seg;  // per-warp capacity of the support list in shared memory
-    int pf[kCoopMaxProb], pk[kCoopMaxProb];
+    int pf[kCoopMaxProb], pk[kCoopMaxProb];  // grid mode: (fold, column) of every problem
+    const int* plist;                        // cluster mode: device list, fold * 65536 + column
 };
+
+// (fold, column) of the active grid columns, in fold-major order (one block; the host knows
+// their number from the convergence check and sizes the cluster launch with it)
+__global__ void coop_list_kernel(const __grid_constant__ SolveDev sp, int* __restrict__ plist) {
+    if (threadIdx.x != 0) return;
+    int q = 0;
+    for (int f = 0; f < sp.F; ++f)
+        for (int k = 0; k < sp.K[f]; ++k)
+            if (sp.flag[(long long)f * sp.ldz + k] == 0) plist[q++] = f * 65536 + k;
+}
 
 __host__ __device__ inline int coop_seg(int p) { return ((p + 31) / 32 + CO_W - 1) / CO_W * 32; }
 __host__ __device__ inline size_t coop_smem(int p) {
@@ -49,11 +60,15 @@ __host__ __device__ inline size_t coop_smem(int p) {
            sizeof(double) * (CO_W * CO_ROWS + CO_ROWS + 64);
 }
 
-template <bool GROUPED>
+// CLUSTER = false: one cooperative grid, blockIdx.y = problem, gridDim.x CTAs per problem, grid
+// barrier.  CLUSTER = true: one thread-block cluster per problem (any number of problems, each
+// iterating at its own pace), cluster barrier.
+template <bool GROUPED, bool CLUSTER>
 __global__ void __launch_bounds__(CO_T, 1) fista_coop_kernel(const __grid_constant__ SolveDev sp,
                                                               const __grid_constant__ CoopArgs ca, int par,
                                                               int n_inner) {
     cg::grid_group grid = cg::this_grid();
+    cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) unsigned char smraw[];
     const int p = sp.p, seg = ca.seg;
     double* sval = reinterpret_cast<double*>(smraw);              // [CO_W][seg] z of the support rows
@@ -64,8 +79,11 @@ __global__ void __launch_bounds__(CO_T, 1) fista_coop_kernel(const __grid_consta
     __shared__ int scnt[CO_W];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int prob = blockIdx.y, b = blockIdx.x, NB = gridDim.x;
-    const int f = ca.pf[prob], k = ca.pk[prob];
+    const int NB = CLUSTER ? (int)cluster.num_blocks() : (int)gridDim.x;
+    const int b = CLUSTER ? (int)cluster.block_rank() : (int)blockIdx.x;
+    const int prob = CLUSTER ? (int)blockIdx.x / NB : (int)blockIdx.y;
+    const int f = CLUSTER ? ca.plist[prob] >> 16 : ca.pf[prob];
+    const int k = CLUSTER ? (ca.plist[prob] & 0xffff) : ca.pk[prob];
     const long long ldz = sp.ldz;
     const long long colbase = (long long)f * ldz + k;
     const bool active = sp.flag[colbase] == 0;  // a converged / frozen column only keeps the barriers
@@ -238,7 +256,10 @@ __global__ void __launch_bounds__(CO_T, 1) fista_coop_kernel(const __grid_consta
                 ca.dpart[((size_t)(it & 1) * ca.nprob + prob) * NB + b] = ds;
             }
         }
-        grid.sync();
+        if (CLUSTER)
+            cluster.sync();
+        else
+            grid.sync();
         if (active) {
             // ---- restart test and momentum coefficient (every CTA, same fixed order) ---------
             if (warp == 0) {

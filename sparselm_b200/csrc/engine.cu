@@ -69,7 +69,9 @@ struct slm_ctx {
     bool dense_apply = false;        // SLM_DENSE_APPLY=1: solver uses the dense apply (A/B runs)
     bool small_fused = true;         // SLM_SMALL_FUSED=0: never use the fused small-design iterations
     bool coop = true;                // SLM_COOP=0: never use the cooperative few-column iterations
+    bool trace = false;              // SLM_TRACE=1: one stderr line per convergence check
     int coop_max_smem = 0;           // opt-in shared memory per block of the device
+    int max_cluster = 16;            // largest cluster size the cooperative cluster kernel may use
     int force_sparse_shape = -1;     // SLM_FORCE_SPARSE_SHAPE
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
@@ -775,8 +777,19 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_DENSE_APPLY")) ctx->dense_apply = atoi(e) != 0;
     if (const char* e = getenv("SLM_SMALL_FUSED")) ctx->small_fused = atoi(e) != 0;
     if (const char* e = getenv("SLM_COOP")) ctx->coop = atoi(e) != 0;
+    if (const char* e = getenv("SLM_TRACE")) ctx->trace = atoi(e) != 0;
     ctx->coop_max_smem = (int)prop.sharedMemPerBlockOptin;
     if (!prop.cooperativeLaunch) ctx->coop = false;
+    if (const char* e = getenv("SLM_MAX_CLUSTER")) ctx->max_cluster = std::max(1, std::min(16, atoi(e)));
+    if (ctx->max_cluster > 8) {
+        if (cudaFuncSetAttribute(fista_coop_kernel<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(fista_coop_kernel<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) !=
+                cudaSuccess) {
+            cudaGetLastError();
+            ctx->max_cluster = 8;
+        }
+    }
     ctx->n_flags_cap = 1 << 20;
     if (cudaMalloc(&ctx->d_flags, sizeof(int) * (size_t)ctx->n_flags_cap) != cudaSuccess ||
         cudaMalloc(&ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS) != cudaSuccess ||
@@ -1274,10 +1287,37 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
                     ca.pf[q] = f;
                     ca.pk[q] = k;
                 }
-            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)coop_sm));
-            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)coop_sm));
+        }
+    }
+
+    // cluster mode: when few columns are left (or given), one thread-block cluster per column
+    // iterates on it between two checks; columns are independent, so any number of clusters
+    bool clus = false;
+    int clus_cs_min = 0, clus_thr = 0;
+    if (!small && !coop && ctx->coop && p <= 16 * CO_ROWS) {
+        const int maxg = bt->gptr_dev ? bt->max_group : 1;
+        const size_t sm = coop_smem((int)p);
+        if (maxg > 0 && sm <= (size_t)ctx->coop_max_smem) {
+            for (int cs = 1; cs <= ctx->max_cluster; cs *= 2)
+                if ((p + cs - 1) / cs + maxg <= CO_ROWS) {
+                    clus_cs_min = cs;
+                    break;
+                }
+            if (clus_cs_min > 0) {
+                // three rounds of co-resident clusters at most, and the three beta buffers of
+                // every column must fit in the T / GZ scratch arrays
+                clus_thr = (int)std::min<long long>(3LL * (ctx->sm_count / clus_cs_min), (long long)F * ldz / 2);
+                coop_sm = sm;
+                ca.seg = coop_seg((int)p);
+                CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<true, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_sm));
+                CUDA_OK(cudaFuncSetAttribute(fista_coop_kernel<false, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coop_sm));
+            }
         }
     }
 
@@ -1349,7 +1389,44 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     }
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
-        const bool check = (small || coop) ? (it == next_check) : (it % check_every == 0);
+        const bool check = (small || coop || clus) ? (it == next_check) : (it % check_every == 0);
+        if (clus && !check) {
+            int n_inner = std::min(next_check, (int)bt->max_iter) - it;
+            int parv = par;
+            const int nprob = (int)n_active;
+            int cs = clus_cs_min;
+            while (cs * 2 <= ctx->max_cluster && nprob * cs * 2 <= ctx->sm_count) cs *= 2;
+            if (ctx->trace) fprintf(stderr, "[slm] cluster launch it=%d n_inner=%d nprob=%d cs=%d\n", it, n_inner, nprob, cs);
+            coop_list_kernel<<<1, 32, 0, s>>>(sp, src);
+            LAUNCH_OK("coop_list_kernel");
+            ca.nprob = nprob;
+            ca.plist = src;
+            ca.buf[0] = T;
+            ca.buf[1] = T + (size_t)nprob * p;
+            ca.buf[2] = GZ;
+            ca.dpart = part;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)(nprob * cs));
+            cfg.blockDim = dim3(CO_T);
+            cfg.dynamicSmemBytes = coop_sm;
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cs;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            FamTimer tm(ctx, FAM_PROX, s, 0.0);
+            if (grouped)
+                CUDA_OK(cudaLaunchKernelEx(&cfg, fista_coop_kernel<true, true>, sp, ca, parv, n_inner));
+            else
+                CUDA_OK(cudaLaunchKernelEx(&cfg, fista_coop_kernel<false, true>, sp, ca, parv, n_inner));
+            ctx->launches++;
+            it += n_inner - 1;
+            continue;
+        }
         if (coop && !check) {
             // every iteration up to the next check in one cooperative launch: the SMs share the
             // column(s), one grid barrier per iteration
@@ -1358,8 +1435,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);
             void* args[] = {(void*)&sp, (void*)&ca, (void*)&parv, (void*)&n_inner};
             const dim3 cgrid2((unsigned)coop_nb, (unsigned)ca.nprob);
-            CUDA_OK(cudaLaunchCooperativeKernel(grouped ? (const void*)fista_coop_kernel<true>
-                                                        : (const void*)fista_coop_kernel<false>,
+            CUDA_OK(cudaLaunchCooperativeKernel(grouped ? (const void*)fista_coop_kernel<true, false>
+                                                        : (const void*)fista_coop_kernel<false, false>,
                                                 cgrid2, dim3(CO_T), args, coop_sm, s));
             ctx->launches++;
             it += n_inner - 1;
@@ -1382,17 +1459,17 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         // the supports change fastest in the first iterations (a cold start is all-zero, then
         // every weakly penalised column fills up): re-decide the width there without waiting
         // for the next convergence check
-        if (coop && sparse && it > 0) {  // the cooperative iterations do not maintain the row flags
+        if ((coop || clus) && sparse && it > 0) {  // the cooperative iterations do not maintain the row flags
             zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
             LAUNCH_OK("zflags_kernel");
         }
-        const bool probe = can_adapt && !check && !coop && (it == 1 || it == 3 || it == 6);
+        const bool probe = can_adapt && !check && !coop && !clus && (it == 1 || it == 3 || it == 6);
         const int cw_now = (wide && !check && !probe) ? cw_wide : cw;
         int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
                                           scount, s, algo)
                         : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
         if (rc) return rc;
-        if ((check || probe) && can_adapt)
+        if ((check || probe) && (can_adapt || (clus_thr > 0 && sparse && F * ncc <= kMaxScount)))
             CUDA_OK(cudaMemcpyAsync(ctx->h_scount, scount, sizeof(int) * (size_t)F * ncc, cudaMemcpyDeviceToHost, s));
         if (probe) {
             CUDA_OK(cudaStreamSynchronize(s));
@@ -1413,9 +1490,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             ctx->launches++;
             CUDA_OK(cudaMemcpyAsync(ctx->h_counter, ctx->d_counter, sizeof(int) * SLM_MAX_FOLDS,
                                     cudaMemcpyDeviceToHost, s));
-            if (small || coop)
-                CUDA_OK(cudaMemcpyAsync(ctx->h_ratio, ctx->d_ratio, sizeof(unsigned long long),
-                                        cudaMemcpyDeviceToHost, s));
+            CUDA_OK(cudaMemcpyAsync(ctx->h_ratio, ctx->d_ratio, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, s));
             CUDA_OK(cudaStreamSynchronize(s));
             n_active = 0;
             bool shrink = false;
@@ -1424,9 +1500,43 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
                 n_active += n_active_f[f];
                 if (round_up(n_active_f[f], 8) < round_up(Kcur[f], 8)) shrink = true;
             }
+            if (ctx->trace)
+                fprintf(stderr, "[slm] it=%d active=%lld Kmax=%d%s\n", it, n_active, Kmax,
+                        coop ? " coop" : (small ? " small" : (clus ? " cluster" : "")));
             if (n_active == 0) break;
+            if (clus_thr > 0) {
+                // few columns left: one cluster per column pays when the columns are sparse (every
+                // cluster reads its own support rows of the Gram: |S| p 8 bytes per column and
+                // iteration, nothing shared between columns) -- otherwise the GEMM path, which
+                // shares the Gram between the columns of a chunk, stays
+                bool pays = false;
+                if (n_active <= clus_thr && sparse && F * ncc <= kMaxScount) {
+                    double bytes = 0.0, flops = 0.0;
+                    for (int f = 0; f < F; ++f) {
+                        const int Kp = (int)std::min<int64_t>(round_up(n_active_f[f], 8), ldz);
+                        for (int cc = 0; cc * cw < Kp; ++cc) {
+                            const double sc = (double)std::min<long long>(ctx->h_scount[f * ncc + cc], p);
+                            const double ncol = (double)std::min(cw, Kp - cc * cw);
+                            bytes += ncol * (double)p * sc * 8.0;
+                            flops += 2.0 * ncol * (double)p * sc;
+                        }
+                    }
+                    const int conc = std::max(1, std::min(ctx->sm_count / clus_cs_min, 8 * (16 / clus_cs_min)));
+                    const double rounds = (double)((n_active + conc - 1) / conc);
+                    const double t_cl = std::max(rounds * 12e-6, bytes / 3.0e12);
+                    const double t_ge = 90e-6 + flops / 20e12;
+                    pays = t_cl < 0.5 * t_ge;
+                }
+                if (pays && !clus) {
+                    clus = true;
+                    interval = check_every;
+                    prev_ratio = 0.0;
+                } else if (!pays && clus) {
+                    clus = false;  // the supports filled up: back to the shared-Gram GEMM iterations
+                }
+            }
             do_compact = shrink && !small && !coop;  // idle CTAs of the fused kernels cost nothing: no compaction
-            if (small || coop) {
+            if (small || coop || clus) {
                 // checks at 0, c, 3c, 7c, ... (c = check_every), at most 2048 apart -- sooner when
                 // the worst gap/tolerance ratio of the last two checks says the tolerance is
                 // nearer than that (linear-rate extrapolation + 15 %)

@@ -133,3 +133,62 @@ def test_cooperative_multi_column_and_frozen_columns(coop_switch):
     assert np.all(sa == 0) and np.all(sb == 0)
     assert np.abs(ca - cb).max() <= 1e-7 * np.abs(cb).max()
     assert ia[0] < ia[3]  # the strongly penalised column converged (and froze) first
+
+
+# ---- cluster mode: one thread-block cluster per remaining column, switched to mid-solve ----
+@pytest.mark.parametrize("cls", [Lasso, SparseGroupLasso, AdaptiveOverlapGroupLasso, RidgedGroupLasso])
+def test_cluster_mode_grid_search_matches_regular_path(cls, coop_switch):
+    """A small grid (3 folds x 7 alphas) drops under the cluster threshold after the first
+    columns converge; scores, coefficients and iteration counts agree with the regular kernels."""
+    from sparselm_b200.model_selection import GridSearchCV
+
+    eng = coop_switch
+    n, p = 300, 420
+    X, y, groups, rng = _problem(n, p, 30, 21)
+    kw = _kwargs(cls, groups, rng, p)
+    amax = np.abs(X.T @ y).max() / n
+    grid = {"alpha": list(amax * np.logspace(-0.3, -2.2, 7))}
+    res = []
+    for on in (1, 0):
+        eng.set_option("coop", on)
+        l0 = eng.launch_count()
+        gs = GridSearchCV(cls(solver_options={"tol": 1e-11}, **kw), grid, cv=3).fit(X, y)
+        res.append((gs, eng.launch_count() - l0))
+    (a, la), (b, lb) = res
+    assert la < lb  # cluster launches replaced per-iteration launch sets
+    assert a.batched_ and b.batched_
+    np.testing.assert_allclose(a.cv_results_["mean_test_score"], b.cv_results_["mean_test_score"], rtol=1e-8)
+    assert a.best_params_ == b.best_params_
+    assert np.abs(a.best_estimator_.coef_ - b.best_estimator_.coef_).max() <= 1e-7 * np.abs(b.best_estimator_.coef_).max()
+    assert np.all(a.solver_info_["status"] == 0)
+
+
+def test_cluster_mode_from_the_start_with_many_columns(coop_switch):
+    """More than four columns on one Gram, all under the threshold from the first check."""
+    eng = coop_switch
+    n, p = 500, 900
+    X, y, groups, rng = _problem(n, p, 90, 5)
+    amax = np.abs(X.T @ y).max() / n
+    est = SparseGroupLasso(groups=groups)
+    fd = eng.prepare(X, y, None, False, None, col_perm=est._problem_spec(p).col_perm)
+    alphas = amax * np.logspace(-0.2, -2.5, 24)
+    specs = [SparseGroupLasso(groups=groups, alpha=a)._problem_spec(p) for a in alphas]
+    outs = []
+    for on in (1, 0):
+        eng.set_option("coop", on)
+        out = solve_specs(eng, fd, specs, use_full=True, tol=1e-11)
+        outs.append((out["coef"][0].cpu().numpy()[:, :24].copy(), out["status"][0, :24].copy(),
+                     out["gap"][0, :24].copy()))
+    (ca, sa, ga), (cb, sb, gb) = outs
+    assert np.all(sa == 0) and np.all(sb == 0)
+    assert np.abs(ca - cb).max() <= 1e-7 * np.abs(cb).max()
+    # independent certificate from X and y (oracle) for a few columns
+    from sparselm_b200.model._base import _to_original_order
+
+    labels, G = R.group_labels(groups, p)
+    for j in (0, 12, 23):
+        beta = _to_original_order(ca[:, j], specs[j])
+        pen = R.Penalty(labels=labels, w1=np.full(p, 0.5 * alphas[j]), w2=np.full(G, 0.5 * alphas[j]),
+                        delta=np.zeros(G))
+        cert = R.certificate(X, y, beta, pen)
+        assert cert["gap"] <= 1e-9 * max(abs(cert["primal"]), 1e-300), (j, cert)
