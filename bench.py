@@ -270,10 +270,22 @@ def dist_init(n_gpus):
     return rank, world, local
 
 
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm runs on rank 0 alone and is
+    meant to use every host core it may run on (set before the OpenMP runtime of the oracle loads)."""
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(ncpu)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    _all_host_threads()
     wl = workload(args.workload)
     import oracle.reference as R
 
