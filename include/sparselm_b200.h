@@ -74,6 +74,11 @@ int slm_pack_design(slm_ctx* ctx, const double* X_dev, int64_t ldx, const double
  * (_lasso.py:120) being re-canonicalised for every fit.  row_ptr is a HOST array. */
 int slm_gram_blocks(slm_ctx* ctx, const double* Xa_dev, int64_t lda, const int64_t* row_ptr,
                     int n_blocks, double* Gblk_dev, void* stream);
+/* G += Xa[r0:r1]^T Xa[r0:r1] (same kernel, the first writer of every tile adds to what G holds,
+ * upper tiles and their mirror alike): lets the Gram of a host-resident design be accumulated
+ * block of rows by block of rows while the next block is still on the PCIe bus. */
+int slm_gram_block_add(slm_ctx* ctx, const double* Xa_dev, int64_t lda, int64_t r0, int64_t r1,
+                       double* G_dev, void* stream);
 
 /* in place: Gtot = sum_f Gblk[f]; Gblk[f] <- Gtot - Gblk[f]  (training Gram of fold f
  * when the blocks are the CV test folds, model_selection.py:304-323). */

@@ -72,6 +72,7 @@ SYMBOLS = {
     "slm_padded_cols": (c_i64, [c_i64]),
     "slm_pack_design": (ctypes.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "slm_gram_blocks": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.c_int, c_vp, c_vp]),
+    "slm_gram_block_add": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "slm_gram_complement": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int, c_i64, c_vp, c_vp]),
     "slm_tri_size": (c_i64, [c_i64]),
     "slm_tri_pack": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_vp]),

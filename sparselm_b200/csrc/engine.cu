@@ -910,8 +910,23 @@ int slm_pack_design(slm_ctx* ctx, const double* X, int64_t ldx, const double* y,
     return 0;
 }
 
+static int gram_blocks_impl(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* row_ptr, int n_blocks,
+                            double* Gblk, int accumulate, void* stream);
+
 int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* row_ptr, int n_blocks,
                     double* Gblk, void* stream) {
+    return gram_blocks_impl(ctx, Xa, lda, row_ptr, n_blocks, Gblk, 0, stream);
+}
+
+int slm_gram_block_add(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t r0, int64_t r1, double* G,
+                       void* stream) {
+    if (r1 <= r0) return 0;
+    const int64_t ptr[2] = {r0, r1};
+    return gram_blocks_impl(ctx, Xa, lda, ptr, 1, G, 1, stream);
+}
+
+static int gram_blocks_impl(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* row_ptr, int n_blocks,
+                            double* Gblk, int accumulate, void* stream) {
     if (!ctx || !Xa || !row_ptr || !Gblk) return fail(ctx, 1, "slm_gram_blocks: null argument");
     if (lda % 8) return fail(ctx, 1, "slm_gram_blocks: lda must be a multiple of 8");
     cudaStream_t s = (cudaStream_t)stream;
@@ -921,6 +936,7 @@ int slm_gram_blocks(slm_ctx* ctx, const double* Xa, int64_t lda, const int64_t* 
         GemmBatch b;
         memset(&b, 0, sizeof(b));
         b.n_problems = nf;
+        b.accumulate = accumulate;
         double flops = 0.0;
         for (int i = 0; i < nf; ++i) {
             int f = f0 + i;

@@ -73,6 +73,7 @@ struct GemmBatch {
     int rem_unit_begin;
     int* flags;  // one int per tile, zero on entry
     int n_flags;
+    int accumulate;  // != 0: C += A B (the tile's first writer adds to what C holds)
     GemmProblem pr[kMaxGemmProblems];
 };
 
@@ -372,7 +373,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                 if (row < M && col < N) {  // N is even: col+1 < N too
                     double v0 = acc[i][j][0], v1 = acc[i][j][1];
                     double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
-                    if (!first_writer) {
+                    if (!first_writer || batch.accumulate) {
                         const double2 old = __ldcg(dst);
                         v0 += old.x;
                         v1 += old.y;

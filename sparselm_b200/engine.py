@@ -179,6 +179,7 @@ class Engine:
     # 12 block power iterations reach >= 0.93 lambda_max on flat (Marchenko-Pastur) spectra;
     # the margin turns the lower bound into a safe step size (tests/test_gpu_engine.py)
     LIPSCHITZ_ITERS = 12
+    PIPELINE_BLOCK_BYTES = 64 << 20  # rows of a host design travel and enter the Gram in blocks of this size
     LIPSCHITZ_MARGIN = 1.10
 
     def __init__(self, device: int | None = None):
@@ -510,9 +511,13 @@ class Engine:
                  "slm_pack_design")
         part.discard(f)
 
-    def _gram_block_into(self, Xa, lo, hi, out):
-        """out = Xa[lo:hi]^T Xa[lo:hi] (out untouched when the range is empty)."""
+    def _gram_block_into(self, Xa, lo, hi, out, accumulate=False):
+        """out (+)= Xa[lo:hi]^T Xa[lo:hi] (out untouched when the range is empty)."""
         if hi <= lo:
+            return
+        if accumulate:
+            self._ck(self.lib.slm_gram_block_add(self.h, self._ptr(Xa), Xa.shape[1], int(lo), int(hi),
+                                                 ctypes.c_void_p(out.data_ptr()), self.stream), "slm_gram_block_add")
             return
         ptr = np.array([lo, hi], dtype=np.int64)
         self._ck(self.lib.slm_gram_blocks(self.h, self._ptr(Xa), Xa.shape[1],
@@ -595,9 +600,11 @@ class Engine:
         alloc = torch.zeros if shard is not None else torch.empty
         allG = alloc((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=dev)
 
-        # row blocks: the test folds, split further so that a block stays <= 64 MiB
+        # row blocks: the test folds, split further so that a block stays <= PIPELINE_BLOCK_BYTES;
+        # the Gram of a fold (of the whole design for a plain fit) is accumulated block by block,
+        # so only the last block's product is exposed after the last byte has crossed the bus
         blocks = []
-        max_rows = max(1024, (64 << 20) // (8 * p))
+        max_rows = max(1024, self.PIPELINE_BLOCK_BYTES // (8 * p))
         for f in range(F):
             a, b = int(row_ptr[f]), int(row_ptr[f + 1])
             if F > 1 and score_folds is not None and f not in score_folds:
@@ -606,7 +613,7 @@ class Engine:
                     if shard is not None:
                         blocks.append((a, a))  # nothing to build, but the collective still runs
                     continue
-            nb = max(1, -(-(b - a) // max_rows)) if F == 1 else 1
+            nb = max(1, -(-(b - a) // max_rows))
             edges = np.linspace(a, b, nb + 1).astype(np.int64)
             blocks += [(int(edges[i]), int(edges[i + 1])) for i in range(nb) if edges[i + 1] > edges[i] or b == a]
         if not hasattr(self, "_copy_stream"):
@@ -614,6 +621,7 @@ class Engine:
         cur = torch.cuda.current_stream(dev)
         self._copy_stream.wait_stream(cur)
         staged = []
+        started = set()  # Grams that already hold their first block
         for a, b in blocks:
             with torch.cuda.stream(self._copy_stream):
                 blk = Xt[a:b].to(dev, non_blocking=True)
@@ -628,11 +636,13 @@ class Engine:
                                               self._ptr(cp), ctypes.c_void_p(0), b - a, p,
                                               ctypes.c_void_p(Xa.data_ptr() + 8 * a * pa), pa, self.stream),
                      "slm_pack_design")
-            if F > 1:  # one Gram block per test fold, as soon as its rows are packed
-                f = int(np.searchsorted(row_ptr, a, side="right") - 1)
-                self._gram_block_into(Xa, max(a, fold_rows[f][0]), min(b, fold_rows[f][1]), allG[f])
-        if F == 1:  # single fit: one Gram over all (of this rank's) rows once everything is packed
-            self._gram_block_into(Xa, fold_rows[0][0], fold_rows[0][1], allG[0])
+            # the Gram of the block's test fold (F > 1) / of the design (F == 1) takes the block as
+            # soon as its rows are packed
+            f = int(np.searchsorted(row_ptr, a, side="right") - 1) if F > 1 else 0
+            lo, hi = max(a, fold_rows[f][0]), min(b, fold_rows[f][1])
+            if hi > lo:
+                self._gram_block_into(Xa, lo, hi, allG[f], accumulate=f in started)
+                started.add(f)
         if shard is not None:
             self._allreduce_grams(allG[:max(F, 1)] if F > 1 else allG[:1], shard)
         return Xa, allG

@@ -166,8 +166,10 @@ class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
     # ---- sklearn API ---------------------------------------------------------
     def fit(self, X, y, sample_weight=None):
         """Fit the linear model coefficients on the GPU engine."""
+        # finiteness is checked on the device (FoldData.check_finite, raised at the first host sync
+        # of the solve) instead of a host pass over X: 50 ms for the 640 MB of a 20000 x 4000 design
         X, y = validate_data(self, X, y, accept_sparse=False, y_numeric=True, multi_output=False,
-                             dtype=np.float64)
+                             dtype=np.float64, ensure_all_finite=False)
         self._validate_hyperparams(X, y)
         opts = self._engine_options()
         spec = self._problem_spec(X.shape[1])

@@ -34,8 +34,10 @@ class OrdinaryLeastSquares(EngineRegressor):
                            key=("OrdinaryLeastSquares", n_features, bool(self.fit_intercept)))
 
     def fit(self, X, y, sample_weight=None):
+        # finiteness is checked on the device (FoldData.check_finite, raised at the first host sync
+        # of the solve) instead of a host pass over X: 50 ms for the 640 MB of a 20000 x 4000 design
         X, y = validate_data(self, X, y, accept_sparse=False, y_numeric=True, multi_output=False,
-                             dtype=np.float64)
+                             dtype=np.float64, ensure_all_finite=False)
         self._validate_hyperparams(X, y)
         opts = self._engine_options()
         engine = get_engine(opts.pop("device", None))
@@ -47,8 +49,8 @@ class OrdinaryLeastSquares(EngineRegressor):
         p = X.shape[1]
         fd = engine.prepare(X, y, None, self.fit_intercept, sw)
         tol = float(opts.get("tol", 1e-13))
+        fd.check_finite()  # conjugate gradients synchronise at once anyway: validate before them
         X8, iters, rel = engine.gram_cg(fd.G_full, p, tol=tol, max_iter=opts.get("max_iter"))
-        fd.check_finite()
         self.coef_ = X8[:, 0].cpu().numpy()
         if self.fit_intercept:
             self.intercept_ = float(engine.intercepts(fd.G_full, p, X8, 1)[0].item())

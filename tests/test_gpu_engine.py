@@ -54,6 +54,43 @@ def test_gram_build_matches_fp64_reference(engine, n, p, F):
                                        atol=1e-12 * np.abs(tot).max())
 
 
+@pytest.mark.parametrize("F", [1, 3])
+@pytest.mark.parametrize("fit_intercept", [False, True])
+def test_pipelined_host_prepare_accumulates_gram_blocks(engine, F, fit_intercept):
+    """A host-resident design travels in row blocks; every block enters its Gram as soon as it is
+    packed (slm_gram_block_add): same Grams as numpy, exactly symmetric."""
+    rng = _rng(17 + F)
+    n, p = 5000, 70
+    X = rng.standard_normal((n, p)) + 0.3
+    y = rng.standard_normal(n)
+    folds = None if F == 1 else [np.arange(f * n // F, (f + 1) * n // F) for f in range(F)]
+    old = engine.PIPELINE_BLOCK_BYTES
+    engine.PIPELINE_BLOCK_BYTES = 1 << 16  # floor of 1024 rows per block: five blocks
+    try:
+        fd = engine.prepare(X, y, folds, fit_intercept, None)
+    finally:
+        engine.PIPELINE_BLOCK_BYTES = old
+    fd.check_finite()
+
+    def gram(rows):
+        Xr, yr = X[rows], y[rows]
+        if fit_intercept:
+            Xr, yr = Xr - Xr.mean(0), yr - yr.mean()
+        return Xr.T @ Xr, Xr.T @ yr
+
+    G, c = gram(np.arange(n))
+    got = fd.G_full.cpu().numpy()
+    np.testing.assert_allclose(got[:p, :p], G, rtol=1e-12, atol=1e-11 * np.abs(G).max())
+    np.testing.assert_allclose(got[p, :p], c, rtol=1e-12, atol=1e-11 * np.abs(G).max())
+    assert np.array_equal(got, got.T)
+    for f in range(F if F > 1 else 0):
+        Gf, cf = gram(np.setdiff1d(np.arange(n), folds[f]))
+        gf = fd.G_train[f].cpu().numpy()
+        np.testing.assert_allclose(gf[:p, :p], Gf, rtol=1e-12, atol=1e-11 * np.abs(Gf).max())
+        np.testing.assert_allclose(gf[p, :p], cf, rtol=1e-12, atol=1e-11 * np.abs(Gf).max())
+        assert np.array_equal(gf, gf.T)
+
+
 def test_pack_with_permutations(engine):
     rng = _rng(5)
     n, p = 50, 13

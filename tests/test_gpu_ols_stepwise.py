@@ -79,6 +79,24 @@ def test_ols_matches_lstsq(n, p):
         assert reg.score(X, y) > 0.99
 
 
+@pytest.mark.parametrize("bad", [np.nan, np.inf])
+def test_non_finite_input_raises_value_error(bad):
+    # the finiteness check of a plain fit runs on the device (no host pass over X)
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(50, 6))
+    y = rng.normal(size=50)
+    Xb = X.copy()
+    Xb[17, 3] = bad
+    yb = y.copy()
+    yb[5] = bad
+    for est in (OrdinaryLeastSquares(), Lasso(alpha=0.1), OrdinaryLeastSquares(fit_intercept=True)):
+        with pytest.raises(ValueError, match="NaN|infinity"):
+            est.fit(Xb, y)
+        with pytest.raises(ValueError, match="NaN|infinity"):
+            est.fit(X, yb)
+        est.fit(X, y)  # the engine is usable afterwards
+
+
 def test_ols_equals_vanishing_lasso():
     rng = np.random.default_rng(5)
     X = rng.normal(size=(200, 15))
