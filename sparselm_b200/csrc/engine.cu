@@ -1394,6 +1394,9 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     int next_check = 0, interval = check_every;  // small mode: checks get rarer while nothing converges
     double prev_ratio = 0.0;
     int prev_check = 0;
+    int next_regular = 0;  // next check of the per-iteration kernels: every check_every iterations, twice
+                           // as often once an eighth of the columns is left (the tail iterates at the
+                           // latency floor of the launch set, a check costs about one iteration)
     const int p32 = (int)round_up(p, 32);
     const int nsplit = std::max(1, std::min(8, 256 / p32));
     const size_t small_smem = fista_small_smem((int)p, p32, nsplit);
@@ -1405,7 +1408,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     }
     for (it = 0; it < bt->max_iter; ++it) {
         const int par = it & 1;
-        const bool check = (small || coop || clus) ? (it == next_check) : (it % check_every == 0);
+        const bool check = (small || coop || clus) ? (it == next_check) : (it == next_regular);
         if (clus && !check) {
             int n_inner = std::min(next_check, (int)bt->max_iter) - it;
             int parv = par;
@@ -1516,6 +1519,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
                 n_active += n_active_f[f];
                 if (round_up(n_active_f[f], 8) < round_up(Kcur[f], 8)) shrink = true;
             }
+            next_regular = it + ((n_active * 8 <= Ktot && Ktot >= 16) ? std::max(2, check_every / 2) : check_every);
             if (ctx->trace)
                 fprintf(stderr, "[slm] it=%d active=%lld Kmax=%d%s\n", it, n_active, Kmax,
                         coop ? " coop" : (small ? " small" : (clus ? " cluster" : "")));

@@ -227,3 +227,53 @@ def test_miqp_names_exist_and_fail_loudly():
     for cls in (L1L0, L2L0, BestSubsetSelection, RegularizedL0, RidgedBestSubsetSelection):
         with pytest.raises(NotImplementedError):
             cls().fit(np.eye(3), np.ones(3))
+
+
+# ---- host logic added with the widening rows (no GPU needed) ------------------------------
+def test_device_metrics_forms():
+    from sparselm_b200.model_selection import _device_metrics
+
+    assert _device_metrics(None) == "r2"
+    assert _device_metrics("neg_mean_absolute_error") == "neg_mean_absolute_error"
+    assert _device_metrics("explained_variance") is None
+    assert _device_metrics(["r2", "neg_mean_squared_error"]) == {"r2": "r2",
+                                                                 "neg_mean_squared_error": "neg_mean_squared_error"}
+    assert _device_metrics(("r2", "r2")) is None  # duplicate names: sklearn's own error path
+    assert _device_metrics({"a": "r2", "b": "neg_root_mean_squared_error"}) == {
+        "a": "r2", "b": "neg_root_mean_squared_error"}
+    assert _device_metrics({"a": "r2", "b": "max_error"}) is None
+    assert _device_metrics(lambda est, X, y: 0.0) is None
+    assert _device_metrics([]) is None
+
+
+def test_metric_formulas_match_sklearn():
+    from sklearn.metrics import mean_absolute_error, mean_squared_error, r2_score
+
+    from sparselm_b200.model_selection import _metric
+
+    rng = np.random.default_rng(0)
+    y, yp = rng.normal(size=40), rng.normal(size=40)
+    sse, sae, sst = ((y - yp) ** 2).sum(), np.abs(y - yp).sum(), ((y - y.mean()) ** 2).sum()
+    assert _metric("r2", sse, sae, 40, sst) == pytest.approx(r2_score(y, yp))
+    assert _metric("neg_mean_squared_error", sse, sae, 40, sst) == pytest.approx(-mean_squared_error(y, yp))
+    assert _metric("neg_root_mean_squared_error", sse, sae, 40, sst) == pytest.approx(-np.sqrt(mean_squared_error(y, yp)))
+    assert _metric("neg_mean_absolute_error", sse, sae, 40, sst) == pytest.approx(-mean_absolute_error(y, yp))
+    # constant target: sklearn's force_finite convention
+    assert _metric("r2", np.array([0.0, 1.0]), None, 5, 0.0).tolist() == [1.0, 0.0]
+
+
+def test_warm_start_views_are_lazy_and_first_fold_wins():
+    import torch
+
+    from sparselm_b200.model_selection import _WarmStarts
+
+    B = torch.arange(2 * 3 * 8, dtype=torch.float64).reshape(2, 3, 8)  # [F, p, ldz]
+    w = _WarmStarts()
+    idxs = np.array([5, 2, 9])  # batch columns -> candidate indices
+    w.add(B, idxs, [np.array([0, 2]), np.array([1, 2])])  # fold 0 solved 5 and 9, fold 1 solved 2 and 9
+    assert torch.equal(w.get(5), B[0, :, 0])
+    assert torch.equal(w.get(9), B[0, :, 1])  # the first fold that solved it
+    assert torch.equal(w[2], B[1, :, 0])
+    assert w.get(7) is None
+    with pytest.raises(KeyError):
+        w[7]
