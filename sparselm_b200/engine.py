@@ -820,10 +820,13 @@ class Engine:
         dnorm.copy_(torch.from_numpy(dn))
 
     # ---- standardize=True: per-group whitening -------------------------------------
-    def whiten(self, G, p, gptr, n_obs, shift=None, ridge=None):
+    def whiten(self, G, p, gptr, n_obs, shift=None, ridge=None, gscale=None):
         """Whitened copies of the Grams G [F, pa, pa] for the group structure gptr:
         Gw_f = W_f^T G_f W_f (+ n_f ridge_g W_g^T W_g on the diagonal blocks), W_f =
-        blockdiag(R_g^{-1}), R_g^T R_g = G_f[g, g] (+ shift_g I).  Returns (Gw, ctx) where ctx
+        blockdiag(R_g^{-1}), R_g^T R_g = gscale_f G_f[g, g] (+ shift_g I).  gscale_f (default 1) is
+        rows / sum(sample_weight) of Gram f: the reference forms its standardized norms on rows
+        scaled by weights *normalised to sum to the number of rows* (_base.py:214), the engine's
+        Gram carries the raw weights.  Returns (Gw, ctx) where ctx
         carries the device-resident factors for `unwhiten`.  Raises ValueError if some
         group's columns are linearly dependent on the rows of a Gram (its block is not
         positive definite): ||X_g b_g|| is then only a semi-norm."""
@@ -846,10 +849,15 @@ class Engine:
         tmp = torch.empty((pa, pa), dtype=torch.float64, device=self.device)
         Gw = torch.empty_like(Gs)
         for f in range(F):
+            kf = 1.0 if gscale is None else float(gscale[f])
+            # R^T R = k G_gg + s I = k (G_gg + (s/k) I): factor the bracket, then W = R^{-1} = W' / sqrt(k)
+            sh = shift_dev if (shift_dev is None or kf == 1.0) else shift_dev / kf
             self._ck(self.lib.slm_group_whiten_factors(self.h, self._ptr(Gs[f]), pa, p, self._ptr(gptr_dev),
-                                                       self._ptr(wptr_dev), Gn, self._ptr(shift_dev), self._ptr(W[f]),
+                                                       self._ptr(wptr_dev), Gn, self._ptr(sh), self._ptr(W[f]),
                                                        self._ptr(scratch), self._ptr(info), self.stream),
                      "slm_group_whiten_factors")
+            if kf != 1.0:
+                W[f].mul_(1.0 / np.sqrt(kf))
             self._ck(self.lib.slm_gram_whiten(self.h, self._ptr(Gs[f]), pa, p, self._ptr(gptr_dev),
                                               self._ptr(wptr_dev), Gn, self._ptr(W[f]), self._ptr(ridge_dev),
                                               float(n_obs[f]), self._ptr(tmp), self._ptr(Gw[f]), self.stream),

@@ -294,7 +294,12 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, che
         # (:776-789): solve in the whitened variables gamma_g = R_g b_g, ridge folded into the Gram
         gptr = np.arange(s0.pe + 1) if s0.gptr is None else s0.gptr
         dl = s0.std_delta
-        Gs, wctx = engine.whiten(Gs, s0.pe, gptr, n_obs, shift=None if dl is None else np.sqrt(dl), ridge=dl)
+        gscale = None
+        if fd.extra.get("weighted"):  # weights normalised to sum to the row count (_base.py:214)
+            rows = np.array([float(fd.n) if k == "full" else float(fd.n_train[k]) for k in keys])
+            gscale = rows / n_obs
+        Gs, wctx = engine.whiten(Gs, s0.pe, gptr, n_obs, shift=None if dl is None else np.sqrt(dl), ridge=dl,
+                                 gscale=gscale)
     # step sizes stay on the device: nothing before the solver's first convergence check
     # synchronises the host, so packing, Gram build and power iterations are enqueued back to back
     if Gs is not G:

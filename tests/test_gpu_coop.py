@@ -192,3 +192,27 @@ def test_cluster_mode_from_the_start_with_many_columns(coop_switch):
                         delta=np.zeros(G))
         cert = R.certificate(X, y, beta, pen)
         assert cert["gap"] <= 1e-9 * max(abs(cert["primal"]), 1e-300), (j, cert)
+
+
+@pytest.mark.parametrize("cls", [GroupLasso, AdaptiveRidgedGroupLasso])
+def test_cooperative_fit_standardized_and_weighted(cls, coop_switch):
+    """standardize=True (whitened Gram) and sample weights go through the same cooperative kernel."""
+    eng = coop_switch
+    n, p = 400, 288
+    X, y, _, rng = _problem(n, p, 24, 13, True)
+    groups = np.repeat(np.arange(24), 12)
+    sw = 2.0 + rng.random(n)  # mean far from 1: the standardized norms see weights normalised to sum n
+    kw = {"groups": groups, "standardize": True}
+    if "Ridged" in cls.__name__:
+        kw["delta"] = (0.4,)
+    fits = []
+    for on in (1, 0):
+        eng.set_option("coop", on)
+        fits.append(cls(alpha=0.05, fit_intercept=True, solver_options={"tol": 1e-12}, **kw).fit(X, y, sample_weight=sw))
+    a, b = fits
+    assert a.solver_info_["status"] == 0
+    assert np.abs(a.coef_ - b.coef_).max() <= 1e-7 * np.abs(b.coef_).max()
+    assert abs(a.intercept_ - b.intercept_) <= 1e-8 * max(1.0, abs(b.intercept_))
+    b_ref, i_ref = R.fit(cls.__name__, X, y, alpha=0.05, fit_intercept=True, sample_weight=sw, **kw)
+    assert np.abs(a.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+    assert abs(a.intercept_ - i_ref) <= 1e-6 * max(1.0, abs(i_ref))

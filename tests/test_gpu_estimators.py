@@ -153,6 +153,40 @@ def test_standardized_estimator_matches_oracle(cls, fit_intercept):
         assert est.n_iter_ == det["n_iter"]
 
 
+@pytest.mark.parametrize("cls", [GroupLasso, RidgedGroupLasso, AdaptiveGroupLasso])
+def test_standardized_estimator_with_sample_weight_matches_oracle(cls):
+    """The reference normalises the weights to sum to the row count before it scales the rows
+    (_base.py:214), and its standardized group norms are formed on those rows: the penalty sees
+    sum(sw) / n, the data term does not."""
+    rng = np.random.default_rng(31)
+    n, p = 90, 24
+    X = rng.standard_normal((n, p)) + 0.4
+    y = X[:, :4] @ [1.5, -1.0, 0.8, 0.5] + 0.2 * rng.standard_normal(n) + 1.0
+    groups = np.repeat(np.arange(6), 4)
+    sw = 3.0 * (0.5 + rng.random(n))
+    extra = {"delta": (0.5,)} if "Ridged" in cls.__name__ else {}
+    for fi in (False, True):
+        est = cls(groups=groups, alpha=0.05, standardize=True, fit_intercept=fi, solver_options={"tol": 1e-12},
+                  **extra).fit(X, y, sample_weight=sw)
+        b_ref, i_ref = R.fit(cls.__name__, X, y, alpha=0.05, groups=groups, standardize=True, fit_intercept=fi,
+                             sample_weight=sw, **extra)
+        assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+        assert abs(est.intercept_ - i_ref) <= 1e-6 * max(1.0, abs(i_ref))
+    # and through a batched, weighted CV search (every training fold has its own scale)
+    alphas = [0.02, 0.1, 0.4]
+    gs = GridSearchCV(cls(groups=groups, standardize=True, fit_intercept=True, solver_options={"tol": 1e-12}, **extra),
+                      {"alpha": alphas}, cv=3).fit(X, y, sample_weight=sw)
+    assert gs.batched_
+    from sklearn.model_selection import KFold
+
+    for f, (tr, te) in enumerate(KFold(3).split(X)):
+        for i, a in enumerate(alphas):
+            b, ic = R.fit(cls.__name__, X[tr], y[tr], alpha=a, groups=groups, standardize=True, fit_intercept=True,
+                          sample_weight=sw[tr], **extra)
+            rmse = np.sqrt(np.mean((y[te] - X[te] @ b - ic) ** 2))
+            assert gs.cv_results_[f"split{f}_test_score"][i] == pytest.approx(-rmse, rel=1e-7)
+
+
 def test_standardized_grid_search_matches_per_fit_oracle():
     """Every training fold has its own whitening (X_g^T X_g of the training rows)."""
     rng = np.random.default_rng(44)
