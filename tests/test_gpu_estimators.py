@@ -510,3 +510,26 @@ def test_readme_example_adaptive_lasso_grid():
     npt.assert_allclose(mean, ref.mean(1), rtol=0, atol=2e-6)
     ties = np.flatnonzero(ref.mean(1) >= ref.mean(1).max() - 1e-6)
     assert gs.best_index_ in ties
+
+
+# ---- third-party conic solutions (tests/golden/make_golden_nlp.py) --------------------------------
+def _nlp_cases():
+    from test_oracle import NLP
+
+    return NLP["cases"]
+
+
+@pytest.mark.parametrize("case", _nlp_cases(), ids=lambda c: f"{c['name']}-s{c['seed']}-{c['alpha']:.3g}")
+def test_estimators_match_third_party_conic_solution(case):
+    """Engine estimators against scipy's SLSQP / trust-region Newton solves of the cone program the
+    reference would hand to cvxpy: north_star tolerances (coefficients 1e-6 * ||b||_inf, support above 1e-6)."""
+    import sparselm_b200.model as M
+    from test_oracle import nlp_case_kwargs
+
+    X, y, kw = nlp_case_kwargs(case)
+    est = getattr(M, case["name"])(alpha=case["alpha"], fit_intercept=False, **kw).fit(X, y)
+    assert est.solver_info_["status"] == 0
+    ref = np.array(case["coef"])
+    assert est.intercept_ == 0.0
+    assert np.abs(est.coef_ - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(np.abs(est.coef_) > 1e-6, np.abs(ref) > 1e-6)
