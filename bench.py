@@ -120,8 +120,22 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.samples, self.stop_flag = None, [], False
 
     def start(self):
+        # NVML polled every ~10 ms from a thread (a timed region of five 33 ms steps sees ~15 samples; the solver
+        # loop runs inside ctypes calls, which release the GIL); nvidia-smi -lms 100 when NVML is not importable
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -131,11 +145,34 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop_flag:
+            try:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                break
+            time.sleep(0.01)
+
+    def _stop_nvml(self):
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        sm = [a for a, _, _ in self.samples]
+        reasons = sorted(nm for nm, b in bits.items() if any(r & b for _, _, r in self.samples))
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(m for _, m, _ in self.samples)) if sm else None,
+                "samples": len(sm), "source": "nvml", "reasons": reasons}
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
