@@ -9,6 +9,8 @@ is no CPU fallback: constructing an Engine without a CUDA device raises.
 from __future__ import annotations
 
 import ctypes
+import os
+import sys
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -649,8 +651,12 @@ class Engine:
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,
-              check_every=10):
+              check_every=10, newton=False):
         """Solve grids[f] (a PenaltyGrid) on Gram G[f] for every f, as one batch.
+
+        newton: pure group penalties only (no l1 term) -- columns that have not converged after a
+        first stretch of iterations get a lock-step Newton phase on their active groups
+        (sparselm_b200/newton.py) between further stretches; off by default.
 
         Returns dict with B (torch [F,p,ldz]), and numpy [F][K_f] arrays gap, primal,
         n_iter, status, n_pass.
@@ -718,12 +724,19 @@ class Engine:
         bt.n_iter_dev, bt.status_dev = n_iter.data_ptr(), status.data_ptr()
 
         ad = g0.adaptive
+        nctx = None
+        if newton and (W2 is not None or (ad is not None and ad.get("a2") is not None)):
+            no_l1 = not np.any(np.concatenate([np.asarray(g.lam1, dtype=float).ravel() for g in grids]) != 0.0)
+            if no_l1 and (ad is None or ad.get("a1") is None) and g0.gptr is not None:
+                gid = torch.from_numpy(np.repeat(np.arange(Gn), np.diff(np.asarray(g0.gptr))).astype(np.int64)).to(dev)
+                nctx = dict(Gs=Gs, B=B, gid=gid, n_obs=[float(v) for v in n_obs], Ks=Ks, status=status, n_iter=n_iter,
+                            primal=primal, get_W2=lambda: W2, D2=D2, p=p, ldz=ldz, F=F, tol=tol, floor_rel=floor_rel,
+                            stats={"phases": 0, "factorizations": 0, "newton_columns": 0})
         n_pass = np.ones((F, ldz), dtype=np.int64)
         total_iters = 0
         if ad is None:
             bt.W1_dev, bt.skip_dev = 0, 0
-            self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
-            total_iters = bt.iters_run
+            total_iters = self._run_batch(bt, nctx)
         else:
             max_pass = int(ad["max_iter"])
             use_w1 = ad.get("a1") is not None
@@ -753,8 +766,7 @@ class Engine:
             for ps in range(max_pass):
                 bt.W1_dev = 0 if W1 is None else W1.data_ptr()
                 bt.skip_dev = skip.data_ptr()
-                self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
-                total_iters += bt.iters_run
+                total_iters += self._run_batch(bt, nctx, base_skip=skip)
                 n_pass[~conv] = ps + 1
                 if use_w1 and W1 is None:  # previous l1 weights were lam1 (broadcast)
                     W1 = lam1[:, None, :].expand(F, p, ldz).contiguous()
@@ -782,9 +794,78 @@ class Engine:
             "n_iter": rh[16 * ncol: 20 * ncol].view(np.int32).reshape(F, ldz),
             "status": rh[20 * ncol:].view(np.int32).reshape(F, ldz),
             "n_pass": n_pass, "iters_run": int(total_iters), "n_unconverged": int(bt.n_unconverged),
-            "W1": W1, "W2": W2,
+            "W1": W1, "W2": W2, "newton": None if nctx is None else nctx["stats"],
         }
         return res
+
+    def _run_batch(self, bt, nctx, base_skip=None):
+        """One slm_solve_batch call -- or, with a Newton context, stretches of iterations with a
+        lock-step Newton phase (newton.newton_phase) on the still unconverged columns in between.
+        Converged columns are frozen through skip_dev; iteration counts are accumulated over the
+        stretches.  Convergence is only ever decided by the engine's own certificate."""
+        if nctx is None:
+            self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
+            return bt.iters_run
+        from .newton import newton_phase
+
+        torch = self.torch
+        F, ldz, p, Ks = nctx["F"], nctx["ldz"], nctx["p"], nctx["Ks"]
+        B, Gs, status, n_iter = nctx["B"], nctx["Gs"], nctx["status"], nctx["n_iter"]
+        budget, first, later, max_phases = int(bt.max_iter), 500, 200, 12
+        skip_ph = torch.zeros((F, ldz), dtype=torch.int32, device=self.device)
+        if base_skip is not None:
+            skip_ph.copy_(base_skip)
+        for f in range(F):
+            skip_ph[f, Ks[f]:] = 1
+        base = skip_ph.cpu().numpy() != 0
+        frozen = base.copy()
+        acc = np.zeros((F, ldz), dtype=np.int64)
+        orig_skip = bt.skip_dev
+        bt.skip_dev = skip_ph.data_ptr()
+        total = 0
+        try:
+            for ph in range(max_phases):
+                last = ph == max_phases - 1
+                bt.max_iter = max(1, budget - total) if last else max(1, min(first if ph == 0 else later, budget - total))
+                self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
+                total += bt.iters_run
+                st = status.cpu().numpy()
+                acc[~frozen] += n_iter.cpu().numpy()[~frozen]
+                slow = ~frozen & (st == 1)
+                if not slow.any() or total >= budget or last:
+                    break
+                frozen |= ~slow
+                skip_ph.copy_(torch.from_numpy(frozen.astype(np.int32)))
+                fi, ki = np.nonzero(slow)
+                W2, D2 = nctx["get_W2"](), nctx["D2"]
+                prim = nctx["primal"].cpu().numpy()
+                floor = max(nctx["floor_rel"], 4e-15 / nctx["tol"])
+                yty = Gs[:, p, p].cpu().numpy()
+                scale = np.array([max(abs(prim[f, k]), floor * yty[f] / (2.0 * nctx["n_obs"][f])) for f, k in zip(fi, ki)])
+                # chunks of columns: four [k, p, p] FP64 temporaries at most ~16 GB
+                chunk = max(1, int(16e9 // (32.0 * p * p)))
+                for c0 in range(0, len(fi), chunk):
+                    fc = torch.from_numpy(fi[c0:c0 + chunk].astype(np.int64)).to(self.device)
+                    kc = torch.from_numpy(ki[c0:c0 + chunk].astype(np.int64)).to(self.device)
+                    X = B[fc, :, kc]
+                    w2 = W2[fc, :, kc]
+                    d2 = None if D2 is None else D2[fc, :, kc]
+                    nn = torch.tensor([nctx["n_obs"][f] for f in fi[c0:c0 + chunk]], dtype=torch.float64, device=self.device)
+                    sc = torch.from_numpy(scale[c0:c0 + chunk]).to(self.device)
+                    Xn, info = newton_phase(Gs, fc, nn, X, w2, d2, nctx["gid"], sc, nctx["tol"])
+                    B[fc, :, kc] = Xn
+                    nctx["stats"]["factorizations"] += int(info["factorizations"])
+                nctx["stats"]["phases"] += 1
+                nctx["stats"]["newton_columns"] += len(fi)
+        finally:
+            bt.skip_dev = orig_skip
+            bt.max_iter = budget
+        if os.environ.get("SLM_TRACE"):
+            print(f"[slm newton] iterations {total} stats {nctx['stats']} unconverged {int(bt.n_unconverged)}", file=sys.stderr)
+        keep = n_iter.cpu().numpy()
+        keep[~base] = np.minimum(acc[~base], np.iinfo(np.int32).max)
+        n_iter.copy_(torch.from_numpy(keep.astype(np.int32)))
+        return total
 
     def _host_update(self, ad, grids, B, W1, W2, dnorm, a1, a2, gptr_dev, gw, p, ldz, Ks):
         """User-supplied update_function (arbitrary Python, _adaptive_lasso.py:116-118,

@@ -160,7 +160,7 @@ class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
         opts = dict(self.solver_options) if self.solver_options is not None else {}
         if not isinstance(opts, dict):
             raise TypeError("solver_options must be a dictionary")
-        known = {"tol", "max_iter", "check_every", "floor_rel", "device"}
+        known = {"tol", "max_iter", "check_every", "floor_rel", "device", "newton"}
         return {k: v for k, v in opts.items() if k in known}
 
     # ---- sklearn API ---------------------------------------------------------
@@ -258,7 +258,7 @@ SMALL_P = 160  # designs up to this many (expanded) features iterate inside one 
 
 
 def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, check_every=10,
-                floor_rel=1e-14, B0=None):
+                floor_rel=1e-14, B0=None, newton=False):
     """Solve problems (equal structure keys) on every training Gram of `fd` (or on its
     full Gram when use_full) as one engine batch.  `specs` is either one list (the same
     K problems on every fold) or a list of per-fold lists (sharded grids).
@@ -320,7 +320,7 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, che
         # vanishing penalties) get the iterations plain accelerated proximal gradient needs
         max_iter = 1000000 if s0.pe <= SMALL_P else 20000
     res = engine.solve(Gs, s0.pe, n_obs, L, grids, B0=B_start, tol=tol, max_iter=max_iter,
-                       check_every=check_every, floor_rel=floor_rel)
+                       check_every=check_every, floor_rel=floor_rel, newton=newton)
     fd.check_finite()  # the solve synchronised: the deferred input validation is free here
     B = res["B"]
     ldz = res["ldz"]

@@ -1,0 +1,140 @@
+"""Second-order phase for slow columns of a batched solve: lock-step Newton on the active manifold.
+
+Why ("known weak spot"): accelerated proximal-gradient iterations need
+~sqrt(condition number) iterations.  A group-penalised problem whose penalty is nearly flat on its
+support (the adaptive passes weight an active group by alpha^2/||b_g||, reference
+_adaptive_lasso.py:364-374) on a Gram with exactly flat directions (the duplicated columns of the
+overlap expansion, _lasso.py:440-461) reaches condition numbers of 1e6 and more: the active groups
+settle after a few hundred iterations and 10^4 more crawl along the flat directions.  On the
+settled support the objective
+
+    phi(b) = 1/(2n) b' G b - c' b / n + sum_g w_g ||b_g|| + 1/2 sum_g d_g ||b_g||^2,   b_g = 0 off the support,
+
+is smooth (||b_g|| > 0 on every active group), so a damped Newton iteration finishes in a handful of
+factorisations.  The conic interior-point solvers behind the reference's cvxpy call
+(_base.py:512-519) are second-order methods too.
+
+What this module does: host-side orchestration on device tensors, all slow columns in lock step
+(one batched Hessian build, one batched Cholesky, one vectorised line search per Newton step).
+The dense factorisation is a plain library call (``torch.linalg.cholesky_ex`` = cuSOLVER potrf);
+everything is written with torch operations so the same code runs on CPU tensors in
+``tests/test_newton.py``.  It never decides convergence: the points go back into the engine's
+batch and the engine's own duality-gap certificate (exact ``G b``, all groups,
+``gap_final_kernel``) judges them.  A step on a wrong support only costs time: every accepted step
+decreases phi (Armijo test on the *difference* of objective values, formed without cancellation).
+
+Scope: pure group penalties (no l1 term) with optional ridge: GroupLasso, OverlapGroupLasso,
+RidgedGroupLasso and their adaptive variants (also in whitened variables, standardize=True).
+Off by default; ``solver_options={"newton": True}`` turns it on (engine.Engine.solve).
+"""
+
+from __future__ import annotations
+
+import torch
+
+__all__ = ["newton_phase"]
+
+
+def _gsum(v, gid, n_groups):
+    """Per-column group sums: v [K, p] -> [K, n_groups]."""
+    out = torch.zeros((v.shape[0], n_groups), dtype=v.dtype, device=v.device)
+    out.index_add_(1, gid, v)
+    return out
+
+
+def newton_phase(Gs, fold, n_obs, X, w2, d2, gid, scale, tol, max_steps=12, chol_batched=True):
+    """Lock-step damped Newton iteration for K columns.
+
+    Gs [F, pa, pa] Grams (rows/cols < p: X'X, row p: X'y), fold [K] int64 (Gram of every column),
+    n_obs [K] rows of the data term, X [K, p] start points (solver feature order), w2 [K, Gn] group
+    weights, d2 [K, Gn] ridge weights or None, gid [p] int64 group of every feature, scale [K] =
+    max(|P|, floor) of the engine's relative test, tol its tolerance: a column is finished once the
+    Newton decrement says phi - phi* <= 1e-3 * tol * scale after a full step.
+
+    Returns (X_new [K, p], info) with info = dict(steps [K], factorizations int, finished [K] bool).
+    """
+    K, p = X.shape
+    Gn = w2.shape[1]
+    dt, dev = X.dtype, X.device
+    X = X.clone()
+    same = (gid[:, None] == gid[None, :]).to(dt)                      # [p, p] shared by all columns
+    steps = torch.zeros(K, dtype=torch.int64, device=dev)
+    finished = torch.zeros(K, dtype=torch.bool, device=dev)
+    live = torch.arange(K, device=dev)                                # columns still iterating
+    target = 1e-3 * tol * scale
+    n_fact = 0
+    small_t = torch.zeros(K, dtype=torch.int64, device=dev)
+    for _ in range(max_steps):
+        if live.numel() == 0:
+            break
+        x = X.index_select(0, live)                                   # [k, p]
+        k = x.shape[0]
+        n = n_obs.index_select(0, live)[:, None]
+        w = w2.index_select(0, live)
+        d = torch.zeros_like(w) if d2 is None else d2.index_select(0, live)
+        f = fold.index_select(0, live)
+        nrm_g = torch.sqrt(_gsum(x * x, gid, Gn))                     # [k, Gn]
+        act_g = nrm_g > 0
+        act = act_g.index_select(1, gid)                              # [k, p]
+        actf = act.to(dt)
+        safe = torch.where(act_g, nrm_g, torch.ones_like(nrm_g))
+        nrm = safe.index_select(1, gid)
+        u = x / nrm * actf
+        wp = w.index_select(1, gid) * actf
+        dp = d.index_select(1, gid) * actf
+        kk = wp / nrm
+        GA = Gs.index_select(0, f)[:, :p, :p] / n[:, :, None]         # [k, p, p]
+        cA = Gs[f, p, :p] / n
+        Gx = torch.bmm(GA, x[:, :, None])[:, :, 0]
+        gs = (Gx - cA) * actf                                         # gradient of the quadratic part
+        grad = gs + wp * u + dp * x
+        H = GA * actf[:, :, None] * actf[:, None, :]
+        H -= same[None] * (kk * u)[:, :, None] * u[:, None, :]
+        H.diagonal(dim1=1, dim2=2).add_(kk + dp + (1.0 - actf))       # identity on the inactive coordinates
+        if chol_batched:
+            L, err = torch.linalg.cholesky_ex(H)
+        else:
+            L = torch.empty_like(H)
+            err = torch.zeros(k, dtype=torch.int32, device=dev)
+            for i in range(k):
+                L[i], err[i] = torch.linalg.cholesky_ex(H[i])
+        n_fact += k
+        del H
+        ok = err == 0
+        dlt = -torch.cholesky_solve(grad[:, :, None], torch.where(ok[:, None, None], L, torch.eye(p, dtype=dt, device=dev)[None]))[:, :, 0]
+        dlt = dlt * actf
+        del L
+        gd = (grad * dlt).sum(1)                                      # = -decrement^2
+        dec = -gd
+        Gd = torch.bmm(GA, dlt[:, :, None])[:, :, 0]
+        del GA
+        q1, q2 = (gs * dlt).sum(1), (dlt * Gd).sum(1)
+        xd, dd = x * dlt, dlt * dlt
+        r1, r2 = (dp * xd).sum(1), (dp * dd).sum(1)
+        g1, g2 = _gsum(xd, gid, Gn), _gsum(dd, gid, Gn)
+        t = torch.ones(k, dtype=dt, device=dev)
+        accepted = torch.zeros(k, dtype=torch.bool, device=dev)
+        usable = ok & (dec > 0)
+        for _ls in range(24):                                         # Armijo backtracking, per column
+            dsq = 2.0 * t[:, None] * g1 + (t * t)[:, None] * g2       # ||x_g + t d_g||^2 - ||x_g||^2
+            new_nrm = torch.sqrt(torch.clamp(nrm_g * nrm_g + dsq, min=0.0))
+            dpen = (w * dsq / (new_nrm + safe)).sum(1)
+            dphi = t * q1 + 0.5 * t * t * q2 + t * r1 + 0.5 * t * t * r2 + dpen
+            good = usable & ~accepted & (dphi <= 1e-4 * t * gd)
+            accepted |= good
+            t = torch.where(accepted | ~usable, t, 0.5 * t)
+            if bool((accepted | ~usable).all()):
+                break
+        t = torch.where(accepted, t, torch.zeros_like(t))
+        x_new = x + t[:, None] * dlt
+        X.index_copy_(0, live, x_new)
+        steps.index_add_(0, live, accepted.to(torch.int64))
+        full = accepted & (t == 1.0)
+        fin = full & (0.5 * dec <= target.index_select(0, live))
+        st = small_t.index_select(0, live)
+        st = torch.where(accepted & (t < 1e-4), st + 1, torch.zeros_like(st))
+        small_t.index_copy_(0, live, st)
+        finished.index_copy_(0, live, fin)
+        keep = accepted & ~fin & (st < 2)                             # not accepted / crawling: back to the engine
+        live = live[keep]
+    return X, {"steps": steps, "factorizations": n_fact, "finished": finished}
