@@ -89,7 +89,7 @@ def workload(name):
         extra = rng.random(p) < 0.3
         group_list = [[int(base[j])] + ([int((base[j] + 1 + rng.integers(G - 1)) % G)] if extra[j] else [])
                       for j in range(p)]
-        est = AdaptiveOverlapGroupLasso(group_list=group_list, solver_options={"tol": TOL, "max_iter": 50000})
+        est = AdaptiveOverlapGroupLasso(group_list=group_list, solver_options={**opts, "max_iter": 50000})
         desc = "AdaptiveOverlapGroupLasso, 30% overlap, 3 reweight passes, 20 alphas x 5 folds, n=5000 p=1500 (configs[3])"
         oracle = dict(name="AdaptiveOverlapGroupLasso", group_list=group_list)
     elif name == "c5":

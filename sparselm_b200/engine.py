@@ -651,12 +651,15 @@ class Engine:
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,
-              check_every=10, newton=False):
+              check_every=10, newton=None):
         """Solve grids[f] (a PenaltyGrid) on Gram G[f] for every f, as one batch.
 
         newton: pure group penalties only (no l1 term) -- columns that have not converged after a
-        first stretch of iterations get a lock-step Newton phase on their active groups
-        (sparselm_b200/newton.py) between further stretches; off by default.
+        first stretch of 500 iterations get a lock-step Newton phase on their active groups
+        (sparselm_b200/newton.py) between further stretches.  None (default) = on for
+        160 < p <= 2048: below, the fused small-design kernel iterates at ~0.3 us per iteration;
+        above, one p x p factorisation per column and step costs more than the iterations it saves
+        unless the problem is known to be ill-conditioned (then pass True).
 
         Returns dict with B (torch [F,p,ldz]), and numpy [F][K_f] arrays gap, primal,
         n_iter, status, n_pass.
@@ -725,6 +728,8 @@ class Engine:
 
         ad = g0.adaptive
         nctx = None
+        if newton is None:
+            newton = 160 < p <= 2048
         if newton and (W2 is not None or (ad is not None and ad.get("a2") is not None)):
             no_l1 = not np.any(np.concatenate([np.asarray(g.lam1, dtype=float).ravel() for g in grids]) != 0.0)
             if no_l1 and (ad is None or ad.get("a1") is None) and g0.gptr is not None:

@@ -258,7 +258,7 @@ SMALL_P = 160  # designs up to this many (expanded) features iterate inside one 
 
 
 def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, check_every=10,
-                floor_rel=1e-14, B0=None, newton=False):
+                floor_rel=1e-14, B0=None, newton=None):
     """Solve problems (equal structure keys) on every training Gram of `fd` (or on its
     full Gram when use_full) as one engine batch.  `specs` is either one list (the same
     K problems on every fold) or a list of per-fold lists (sharded grids).

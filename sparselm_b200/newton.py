@@ -25,7 +25,10 @@ decreases phi (Armijo test on the *difference* of objective values, formed witho
 
 Scope: pure group penalties (no l1 term) with optional ridge: GroupLasso, OverlapGroupLasso,
 RidgedGroupLasso and their adaptive variants (also in whitened variables, standardize=True).
-Off by default; ``solver_options={"newton": True}`` turns it on (engine.Engine.solve).
+On by default for 160 < p <= 2048 (engine.Engine.solve); ``solver_options={"newton": True / False}``
+forces it.  Measured on C4 (AdaptiveOverlapGroupLasso, 20 alphas x 5 folds x 3 passes, p_ext = 1961): 2.1 s per
+search against 12.4 s, 2100 iterations against 129 350, no column left on max_iter (6 before), scores
+equal to 3e-8 relative; 1109 factorisations per search, batched cuSOLVER potrf 0.39 ms each at n = 1961.
 """
 
 from __future__ import annotations
