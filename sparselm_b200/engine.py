@@ -825,12 +825,14 @@ class Engine:
         base = skip_ph.cpu().numpy() != 0
         frozen = base.copy()
         acc = np.zeros((F, ldz), dtype=np.int64)
+        fails = np.zeros((F, ldz), dtype=np.int64)  # Newton phases a column went through without finishing
         orig_skip = bt.skip_dev
         bt.skip_dev = skip_ph.data_ptr()
         total = 0
         try:
+            last = False
             for ph in range(max_phases):
-                last = ph == max_phases - 1
+                last = last or ph == max_phases - 1
                 bt.max_iter = max(1, budget - total) if last else max(1, min(first if ph == 0 else later, budget - total))
                 self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
                 total += bt.iters_run
@@ -841,7 +843,12 @@ class Engine:
                     break
                 frozen |= ~slow
                 skip_ph.copy_(torch.from_numpy(frozen.astype(np.int32)))
-                fi, ki = np.nonzero(slow)
+                # a column that three Newton phases did not finish stays with the iterations (bounded extra cost
+                # on problems the phase does not help); with no candidate left the next stretch runs to max_iter
+                fi, ki = np.nonzero(slow & (fails < 3))
+                if len(fi) == 0:
+                    last = True
+                    continue
                 W2, D2 = nctx["get_W2"](), nctx["D2"]
                 prim = nctx["primal"].cpu().numpy()
                 floor = max(nctx["floor_rel"], 4e-15 / nctx["tol"])
@@ -859,6 +866,8 @@ class Engine:
                     sc = torch.from_numpy(scale[c0:c0 + chunk]).to(self.device)
                     Xn, info = newton_phase(Gs, fc, nn, X, w2, d2, nctx["gid"], sc, nctx["tol"])
                     B[fc, :, kc] = Xn
+                    nf = ~info["finished"].cpu().numpy()
+                    fails[fi[c0:c0 + chunk][nf], ki[c0:c0 + chunk][nf]] += 1
                     nctx["stats"]["factorizations"] += int(info["factorizations"])
                 nctx["stats"]["phases"] += 1
                 nctx["stats"]["newton_columns"] += len(fi)
