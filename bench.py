@@ -600,6 +600,12 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
                 "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
                 "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
                 "traffic": traffic, "gram_build_tflops": build_tf, "step_ms_by_kernel_family": step_ms}
+    nw = res.get("newton") or {}
+    if nw.get("factorizations"):  # second-order phase of the last timed step (library Cholesky, sparselm_b200/newton.py)
+        roof["newton_phase"] = {"ms_per_step": float(nw["ms"]), "factorizations_per_step": int(nw["factorizations"]),
+                                "phases_per_step": int(nw["phases"]),
+                                "note": "lock-step Newton steps on the active groups of the slow columns: batched cuSOLVER "
+                                        "potrf through torch.linalg, not one of this repo's kernels and not in gpu_launches"}
     line = {
         "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",

@@ -736,7 +736,7 @@ class Engine:
                 gid = torch.from_numpy(np.repeat(np.arange(Gn), np.diff(np.asarray(g0.gptr))).astype(np.int64)).to(dev)
                 nctx = dict(Gs=Gs, B=B, gid=gid, n_obs=[float(v) for v in n_obs], Ks=Ks, status=status, n_iter=n_iter,
                             primal=primal, get_W2=lambda: W2, D2=D2, p=p, ldz=ldz, F=F, tol=tol, floor_rel=floor_rel,
-                            stats={"phases": 0, "factorizations": 0, "newton_columns": 0})
+                            stats={"phases": 0, "factorizations": 0, "newton_columns": 0, "ms": 0.0})
         n_pass = np.ones((F, ldz), dtype=np.int64)
         total_iters = 0
         if ad is None:
@@ -856,6 +856,8 @@ class Engine:
                 scale = np.array([max(abs(prim[f, k]), floor * yty[f] / (2.0 * nctx["n_obs"][f])) for f, k in zip(fi, ki)])
                 # chunks of columns: four [k, p, p] FP64 temporaries at most ~16 GB
                 chunk = max(1, int(16e9 // (32.0 * p * p)))
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
                 for c0 in range(0, len(fi), chunk):
                     fc = torch.from_numpy(fi[c0:c0 + chunk].astype(np.int64)).to(self.device)
                     kc = torch.from_numpy(ki[c0:c0 + chunk].astype(np.int64)).to(self.device)
@@ -869,6 +871,9 @@ class Engine:
                     nf = ~info["finished"].cpu().numpy()
                     fails[fi[c0:c0 + chunk][nf], ki[c0:c0 + chunk][nf]] += 1
                     nctx["stats"]["factorizations"] += int(info["factorizations"])
+                ev1.record()
+                ev1.synchronize()
+                nctx["stats"]["ms"] += ev0.elapsed_time(ev1)
                 nctx["stats"]["phases"] += 1
                 nctx["stats"]["newton_columns"] += len(fi)
         finally:

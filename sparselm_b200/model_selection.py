@@ -190,6 +190,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     sst_test = np.array([float(((yv[t] - yv[t].mean()) ** 2).sum()) if need_r2 else 0.0 for t in test_folds])
     tot_sum, tot_sq = float(yv.sum()), float((yv * yv).sum())
     n_unconverged = 0
+    newton_stats = {}
     iters_run = 0
 
     fds = {} if fds is None else dict(fds)  # may arrive pre-populated (prepare started early)
@@ -260,6 +261,8 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         score_time[idxs] = (t2 - t1) / (K * n_splits)
         n_unconverged += int(out["n_unconverged"])
         iters_run += int(out["iters_run"])
+        for k, v in (out.get("newton") or {}).items():  # second-order phase of this rank's batches (engine._run_batch)
+            newton_stats[k] = newton_stats.get(k, 0) + v
     if shard is not None and shard.world > 1:
         # the only data-path exchange of the sharded grid: one sum of the zero-padded tables
         tabs = [np.nan_to_num(test_tabs[m], nan=0.0) for m in metrics]
@@ -284,7 +287,7 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     if train_scores is not None:
         train_scores = train_tabs if multi else train_tabs["score"]
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
-                info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm)
+                info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm, newton=newton_stats)
 
 
 class GridSearchCV(_SkGridSearchCV):
