@@ -182,3 +182,35 @@ def test_oracle_matches_third_party_conic_solution(case):
         obj = (np.sum((y - X @ b) ** 2) / (2 * n) + l1r * case["alpha"] * np.abs(b).sum()
                + (1 - l1r) * case["alpha"] * (gw * nr).sum() + 0.5 * (dl * nr * nr).sum())
         assert abs(obj - case["objective"]) <= 1e-8 * abs(case["objective"])
+
+
+def nlp_pre_case(case):
+    """(X, y, sample_weight or None, constructor kwargs) of a "cases_preprocess" record."""
+    pb = NLP["problems"][case["problem"]]
+    X, y = np.array(pb["X"]), np.array(pb["y"])
+    sw = np.array(pb["sample_weight"]) if case["use_sample_weight"] else None
+    kw = dict(groups=np.array(pb["groups"]), alpha=case["alpha"], fit_intercept=case["fit_intercept"],
+              standardize=case["standardize"])
+    if "l1_ratio" in case:
+        kw["l1_ratio"] = case["l1_ratio"]
+    if "delta" in case:
+        kw["delta"] = tuple(case["delta"])
+    return X, y, sw, kw
+
+
+def _pre_id(c):
+    return (f"{c['name']}-{c['problem']}-{c['alpha']:.3g}-fi{int(c['fit_intercept'])}"
+            f"-sw{int(c['use_sample_weight'])}-std{int(c['standardize'])}")
+
+
+@pytest.mark.parametrize("case", NLP["cases_preprocess"], ids=_pre_id)
+def test_oracle_preprocessing_and_standardize_match_third_party(case):
+    """Intercepts, sample weights (rescaled to sum n, rows scaled by sqrt(sw), _base.py:207-227) and the
+    standardized group norms ||X_g b_g|| / ||sqrtm(X_g'X_g + sqrt(delta_g) I) b_g|| (_lasso.py:249-252, :776-789):
+    the generator restates them independently and solves with scipy's SLSQP / trust-exact."""
+    X, y, sw, kw = nlp_pre_case(case)
+    b, icpt = R.fit(case["name"], X, y, sample_weight=sw, **kw)
+    ref = np.array(case["coef"])
+    assert np.abs(b - ref).max() <= 1e-6 * np.abs(ref).max()
+    assert np.array_equal(np.abs(b) > 1e-6, np.abs(ref) > 1e-6)
+    assert abs(icpt - case["intercept"]) <= 1e-6 * max(1.0, abs(case["intercept"]))
