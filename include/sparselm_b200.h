@@ -42,12 +42,16 @@ int slm_create(int device, slm_ctx** out);
 void slm_destroy(slm_ctx* ctx);
 /* engine switches (the SLM_* environment variables read at slm_create, settable later):
  * "coop" (cooperative few-column iterations), "small_fused" (fused small-design iterations),
- * "dense_apply" (solver uses the dense Gram apply), "chunk_w" (columns per support chunk). */
+ * "dense_apply" (solver uses the dense Gram apply), "chunk_w" (columns per support chunk),
+ * "tma" (bit mask of the kernel families fed by TMA + mbarrier instead of cp.async: 1 Gram build,
+ * 2 dense Gram apply, 4 row-sparse Gram apply; default 7). */
 int slm_set_option(slm_ctx* ctx, const char* name, int value);
 const char* slm_last_error(const slm_ctx* ctx);
 int slm_sm_count(const slm_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t slm_launch_count(const slm_ctx* ctx);
+/* how many of those were TMA-fed GEMM launches (gemm_f64_tma_kernel) */
+int64_t slm_tma_launch_count(const slm_ctx* ctx);
 /* average device time in ms of the `which` kernel family since the last reset,
  * measured with CUDA events on the launching stream when timing is enabled.
  * which: 0 = gram build, 1 = gram apply (solver), 2 = prox, 3 = gap, 4 = score,
@@ -95,6 +99,14 @@ int slm_tri_pack(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa
                  double* buf_dev, void* stream);
 int slm_tri_unpack(slm_ctx* ctx, const double* buf_dev, int64_t pa, int n_grams, double* G_dev,
                    int64_t g_stride, void* stream);
+
+/* Diagnostic of the TMA path (gemm_f64_tma.cuh): loads the [16 rows][16 doubles] box at (row0, col0) of
+ * the row-major device matrix A_dev[rows][ld] with a tiled tensor map and the four rows r[0..3] at col0
+ * with a tile::gather4 map (both 128-byte swizzled) and writes the raw shared-memory images to
+ * out_dev[320] (256 + 64 doubles).  tests/test_gpu_tma.py checks them against the layout the
+ * consumers assume (chunk XOR (row & 7), zero fill outside the matrix). */
+int slm_tma_probe(slm_ctx* ctx, const double* A_dev, int64_t rows, int64_t ld, int32_t col0, int32_t row0,
+                  const int32_t* r4_host, double* out_dev, void* stream);
 
 /* in-place centering of one augmented Gram using its ones row/column
  * (fit_intercept=True, _base.py:216-222): G <- G - s s^T / n on the [0,p] block. */

@@ -66,6 +66,7 @@ SYMBOLS = {
     "slm_last_error": (ctypes.c_char_p, [c_vp]),
     "slm_sm_count": (ctypes.c_int, [c_vp]),
     "slm_launch_count": (c_i64, [c_vp]),
+    "slm_tma_launch_count": (c_i64, [c_vp]),
     "slm_timing_enable": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "slm_timing_read": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_dbl), ctypes.POINTER(c_i64), ctypes.POINTER(c_dbl)]),
     "slm_timing_reset": (ctypes.c_int, [c_vp]),
@@ -77,6 +78,7 @@ SYMBOLS = {
     "slm_tri_size": (c_i64, [c_i64]),
     "slm_tri_pack": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_vp]),
     "slm_tri_unpack": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp]),
+    "slm_tma_probe": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, ctypes.POINTER(c_i32), c_vp, c_vp]),
     "slm_gram_center": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "slm_gram_gather": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
     "slm_lipschitz_workspace": (c_sz, [c_i64, ctypes.c_int]),

@@ -24,6 +24,7 @@
 
 #include "../../include/sparselm_b200.h"
 #include "gemm_f64.cuh"
+#include "gemm_f64_tma.cuh"
 #include "solver_kernels.cuh"
 #include "whiten_kernels.cuh"
 #include "cg_kernels.cuh"
@@ -51,6 +52,7 @@ struct slm_ctx {
     int sm_count = 148;
     std::string err;
     int64_t launches = 0;
+    int64_t tma_launches = 0;
     bool timing = false;
     Family fam[FAM_COUNT];
     int* d_counter = nullptr;
@@ -75,6 +77,10 @@ struct slm_ctx {
     int force_sparse_shape = -1;     // SLM_FORCE_SPARSE_SHAPE
     int force_apply_shape = -1;  // tuning/testing hook (SLM_FORCE_APPLY_SHAPE)
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
+    // TMA-fed GEMM kernels (gemm_f64_tma.cuh): bit 0 Gram build, bit 1 dense apply, bit 2 row-sparse
+    // apply (SLM_TMA / slm_set_option "tma"); encode = cuTensorMapEncodeTiled resolved at run time
+    int tma_mask = 7;
+    void* encode = nullptr;
 };
 
 static int fail(slm_ctx* ctx, int code, const std::string& msg) {
@@ -211,6 +217,74 @@ static cudaError_t launch_gemm_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+
+// ---- TMA-fed variants ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D map over a row-major [rows][ld] FP64 matrix, boxes of [box_rows][16 doubles], 128-byte swizzle,
+// out-of-bounds elements read as zero
+static bool make_map(slm_ctx* ctx, CUtensorMap* map, const double* base, long long rows, long long ld, int box_rows) {
+    if (!ctx->encode || !base || rows <= 0 || ld <= 0 || (ld & 1) || ((uintptr_t)base & 15)) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxCols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = ((EncodeTiledFn)ctx->encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// can this batch run on the TMA kernels?  Fills prow0 / qrow0 / qcol0 of every problem.
+static bool tma_prepare(slm_ctx* ctx, GemmBatch& b, int family_bit) {
+    if (!(ctx->tma_mask & family_bit) || !ctx->encode || !b.baseP || !b.baseQ) return false;
+    for (int i = 0; i < b.n_problems; ++i) {
+        GemmProblem& pr = b.pr[i];
+        if (pr.ldp != b.pr[0].ldp || pr.ldq != b.pr[0].ldq) return false;
+        const long long dp = pr.P - b.baseP, dq = pr.Q - b.baseQ;
+        if (dp < 0 || dq < 0 || dp % pr.ldp != 0) return false;
+        pr.prow0 = (int)(dp / pr.ldp);
+        pr.qrow0 = (int)(dq / pr.ldq);
+        pr.qcol0 = (int)(dq % pr.ldq);
+        if ((long long)pr.prow0 + pr.Kd > (1LL << 30) || (long long)pr.qrow0 + pr.Kd > (1LL << 30)) return false;
+    }
+    return true;
+}
+
+template <int WM, int WN, int MI, int NI, bool SYM, int MINB, bool KSP, int BK, int STAGES>
+static cudaError_t launch_gemm_tma_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
+    using Cfg = TmaCfg<WM, WN, MI, NI, BK, STAGES>;
+    auto kern = gemm_f64_tma_kernel<WM, WN, MI, NI, BK, STAGES, SYM, MINB, KSP>;
+    static int occupancy = 0;
+    if (occupancy == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::SMEM);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        occupancy = std::min(occ, MINB);
+    }
+    fill_units(b, Cfg::BM, Cfg::BN, SYM, ctx->sm_count * occupancy, BK);
+    if (b.total_units <= 0) return cudaSuccess;
+    if (b.n_flags > ctx->n_flags_cap) return cudaErrorInvalidValue;
+    b.flags = ctx->d_flags;
+    CUtensorMap mp, mq;
+    const int box_rows = KSP ? 1 : BK;
+    if (!make_map(ctx, &mp, b.baseP, b.rowsP, b.pr[0].ldp, box_rows) ||
+        !make_map(ctx, &mq, b.baseQ, b.rowsQ, b.pr[0].ldq, box_rows))
+        return cudaErrorInvalidValue;
+    int grid = b.full_waves > 0 ? ctx->sm_count * occupancy : (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
+    if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
+    cudaError_t e = cudaMemsetAsync(b.flags, 0, sizeof(int) * (size_t)b.n_flags, s);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b, mp, mq);
+    ctx->tma_launches++;
+    return cudaGetLastError();
+}
+
 // K-major (apply) menu.  X(id, WM, WN, MI, NI, MINB, eff): tile = (WM*MI*8) x (WN*NI*8);
 // eff = measured fraction of the per-SM DMMA peak of that warp layout (profiles/).
 #define SLM_APPLY_SHAPES(X)        \
@@ -240,6 +314,14 @@ static const Shape kApplyShapes[] = {
 constexpr int kNumApplyShapes = sizeof(kApplyShapes) / sizeof(Shape);
 
 static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
+    if (tma_prepare(ctx, b, 2)) {
+        switch (id) {
+#define X(id_, wm, wn, mi, ni, minb, eff) \
+    case id_: return launch_gemm_tma_t<wm, wn, mi, ni, false, minb, false, kBK, kStages>(ctx, b, s);
+            SLM_APPLY_SHAPES(X)
+#undef X
+        }
+    }
     switch (id) {
 #define X(id_, wm, wn, mi, ni, minb, eff) \
     case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb>(ctx, b, s);
@@ -272,6 +354,14 @@ static const Shape kSparseShapes[] = {
 };
 constexpr int kNumSparseShapes = sizeof(kSparseShapes) / sizeof(Shape);
 static cudaError_t launch_sparse_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
+    if (id < 12 && tma_prepare(ctx, b, 4)) {
+        switch (id) {
+#define X(id_, wm, wn, mi, ni, minb, eff) \
+    case id_: return launch_gemm_tma_t<wm, wn, mi, ni, false, minb, true, kBK, (minb >= 3 ? 3 : kStages)>(ctx, b, s);
+            SLM_SPARSE_SHAPES(X)
+#undef X
+        }
+    }
     switch (id) {
 #define X(id_, wm, wn, mi, ni, minb, eff) \
     case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb, true, kBK, (minb >= 3 ? 3 : kStages)>(ctx, b, s);
@@ -300,6 +390,10 @@ static cudaError_t launch_score_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
 // a 32-deep k-slab (half as many CTA-wide barriers per flop) with 3 stages beats 16-deep x 4
 // stages by 9 % (11.25 vs 12.26 ms); more warps or other warp tiles change little.
 static cudaError_t launch_syrk_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
+    if (id <= 1 && tma_prepare(ctx, b, 1)) {
+        if (id == 0) return launch_gemm_tma_t<2, 4, 8, 4, true, 1, false, 32, 3>(ctx, b, s);
+        return launch_gemm_tma_t<4, 4, 4, 4, true, 1, false, 32, 3>(ctx, b, s);
+    }
     switch (id) {
         case 0: return launch_gemm_t<2, 4, 8, 4, false, true, 1, false, 32, 3>(ctx, b, s);
         case 1: return launch_gemm_t<4, 4, 4, 4, false, true, 1, false, 32, 3>(ctx, b, s);
@@ -346,6 +440,12 @@ static int apply_batched(slm_ctx* ctx, const double* G, int64_t g_stride, int64_
         ProblemDims pd[kMaxGemmProblems];
         double flops = 0.0;
         b.n_problems = nf;
+        if (g_stride % pa == 0) {  // the Grams are row blocks of one [rows][pa] matrix: TMA-addressable
+            b.baseP = G;
+            b.rowsP = (int64_t)(F - 1) * (g_stride / pa) + pa;
+            b.baseQ = Z;
+            b.rowsQ = (int64_t)F * p;
+        }
         for (int i = 0; i < nf; ++i) {
             int f = f0 + i;
             GemmProblem& pr = b.pr[i];
@@ -389,6 +489,12 @@ static int apply_rowsparse(slm_ctx* ctx, const SolveDev& sp, const int32_t* K, c
     auto flush = [&]() -> int {
         if (np == 0) return 0;
         b.n_problems = np;
+        if (sp.g_stride % sp.pa == 0) {
+            b.baseP = sp.G;
+            b.rowsP = (int64_t)(F - 1) * (sp.g_stride / sp.pa) + sp.pa;
+            b.baseQ = Z;
+            b.rowsQ = (int64_t)F * p;
+        }
         int sid = pick_shape(kSparseShapes, kNumSparseShapes, pd, np, ctx->sm_count);
         if (ctx->force_sparse_shape >= 0 && ctx->force_sparse_shape < 14) sid = ctx->force_sparse_shape;
         FamTimer tm(ctx, FAM_APPLY, s, first ? std::max(algo_flops, 0.0) : 0.0);
@@ -778,6 +884,16 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_SMALL_FUSED")) ctx->small_fused = atoi(e) != 0;
     if (const char* e = getenv("SLM_COOP")) ctx->coop = atoi(e) != 0;
     if (const char* e = getenv("SLM_TRACE")) ctx->trace = atoi(e) != 0;
+    if (const char* e = getenv("SLM_TMA")) ctx->tma_mask = atoi(e);
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            ctx->encode = fn;
+        else
+            cudaGetLastError();
+    }
     ctx->coop_max_smem = (int)prop.sharedMemPerBlockOptin;
     if (!prop.cooperativeLaunch) ctx->coop = false;
     if (const char* e = getenv("SLM_MAX_CLUSTER")) ctx->max_cluster = std::max(1, std::min(16, atoi(e)));
@@ -837,6 +953,8 @@ int slm_set_option(slm_ctx* ctx, const char* name, int value) {
         ctx->dense_apply = value != 0;
     else if (nm == "chunk_w")
         ctx->chunk_w = std::max(8, value / 8 * 8);
+    else if (nm == "tma")
+        ctx->tma_mask = value;
     else
         return fail(ctx, 1, "slm_set_option: unknown option " + nm);
     return 0;
@@ -845,6 +963,7 @@ int slm_set_option(slm_ctx* ctx, const char* name, int value) {
 const char* slm_last_error(const slm_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int slm_sm_count(const slm_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 int64_t slm_launch_count(const slm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t slm_tma_launch_count(const slm_ctx* ctx) { return ctx ? ctx->tma_launches : 0; }
 
 int slm_timing_enable(slm_ctx* ctx, int on) {
     if (!ctx) return 1;
@@ -937,6 +1056,8 @@ static int gram_blocks_impl(slm_ctx* ctx, const double* Xa, int64_t lda, const i
         memset(&b, 0, sizeof(b));
         b.n_problems = nf;
         b.accumulate = accumulate;
+        b.baseP = b.baseQ = Xa;
+        b.rowsP = b.rowsQ = row_ptr[n_blocks];
         double flops = 0.0;
         for (int i = 0; i < nf; ++i) {
             int f = f0 + i;
@@ -986,6 +1107,19 @@ int slm_tri_unpack(slm_ctx* ctx, const double* buf, int64_t pa, int n_grams, dou
     dim3 grid((unsigned)((pa + 255) / 256), (unsigned)pa, (unsigned)n_grams);
     tri_unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(buf, slm_tri_size(pa), pa, G, g_stride);
     LAUNCH_OK("tri_unpack_kernel");
+    return 0;
+}
+
+int slm_tma_probe(slm_ctx* ctx, const double* A, int64_t rows, int64_t ld, int32_t col0, int32_t row0,
+                  const int32_t* r4, double* out, void* stream) {
+    if (!ctx || !A || !r4 || !out) return fail(ctx, 1, "slm_tma_probe: null argument");
+    if (!ctx->encode) return fail(ctx, 8, "slm_tma_probe: cuTensorMapEncodeTiled is not available");
+    CUtensorMap mt, mg;
+    if (!make_map(ctx, &mt, A, rows, ld, 16) || !make_map(ctx, &mg, A, rows, ld, 1))
+        return fail(ctx, 8, "slm_tma_probe: tensor map encoding failed");
+    tma_probe_kernel<<<1, 128, 8192, (cudaStream_t)stream>>>(mt, mg, col0, row0, make_int4(r4[0], r4[1], r4[2], r4[3]),
+                                                           out);
+    LAUNCH_OK("tma_probe_kernel");
     return 0;
 }
 

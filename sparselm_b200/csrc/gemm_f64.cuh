@@ -58,6 +58,9 @@ struct GemmProblem {
     int unit_begin;  // first linear work unit (tile * kt + slab) of this problem
     int flag_begin;  // first per-tile flag of this problem
     int tile_begin;  // first global tile index of this problem
+    // TMA kernels (gemm_f64_tma.cuh): the operands are addressed through tensor maps over the whole
+    // matrices baseP / baseQ of the batch; a problem starts at these rows / this column of them
+    int prow0, qrow0, qcol0;
 };
 
 struct GemmBatch {
@@ -74,6 +77,10 @@ struct GemmBatch {
     int* flags;  // one int per tile, zero on entry
     int n_flags;
     int accumulate;  // != 0: C += A B (the tile's first writer adds to what C holds)
+    // TMA kernels: base matrices of the P / Q operands of every problem and their row counts
+    // (NULL: the batch can only run on the cp.async kernel)
+    const double *baseP, *baseQ;
+    long long rowsP, rowsQ;
     GemmProblem pr[kMaxGemmProblems];
 };
 

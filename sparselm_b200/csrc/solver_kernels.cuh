@@ -624,10 +624,10 @@ __global__ void gap_final_kernel(const __grid_constant__ SolveDev sp, int it, in
         }
     } else {
         const bool undecided = sp.status ? sp.status[obase] == -1 : true;
-        if (undecided) {  // not flagged inside the loop: judge the final point
-            if (sp.n_iter) sp.n_iter[obase] = it;
-            if (sp.status) sp.status[obase] = !finite ? 2 : (conv ? 0 : 1);
-        }
+        if (undecided && sp.n_iter) sp.n_iter[obase] = it;  // not flagged inside the loop
+        // the exact certificate has the last word: a column the loop flagged from the momentum
+        // recurrence of G*B (which can drift) is downgraded when the exact product disagrees
+        if (sp.status && (undecided || !conv || !finite)) sp.status[obase] = !finite ? 2 : (conv ? 0 : 1);
         if (!conv) atomicAdd(sp.counter + f, 1);
     }
 }

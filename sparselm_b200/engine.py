@@ -245,11 +245,24 @@ class Engine:
         return t.contiguous()
 
     def set_option(self, name, value):
-        """Engine switch by name ("coop", "small_fused", "dense_apply", "chunk_w")."""
+        """Engine switch by name ("coop", "small_fused", "dense_apply", "chunk_w", "tma")."""
         self._ck(self.lib.slm_set_option(self.h, name.encode(), int(value)), "slm_set_option")
 
     def launch_count(self):
         return int(self.lib.slm_launch_count(self.h))
+
+    def tma_launch_count(self):
+        """TMA-fed GEMM launches (gemm_f64_tma_kernel) among them."""
+        return int(self.lib.slm_tma_launch_count(self.h))
+
+    def tma_probe(self, A, col0, row0, rows4):
+        """Raw shared-memory images of one tiled box load and one 4-row gather (diagnostic)."""
+        torch = self.torch
+        out = torch.empty(320, dtype=torch.float64, device=self.device)
+        r4 = (ctypes.c_int32 * 4)(*[int(r) for r in rows4])
+        self._ck(self.lib.slm_tma_probe(self.h, self._ptr(A), A.shape[0], A.shape[1], int(col0), int(row0), r4,
+                                        self._ptr(out), self.stream), "slm_tma_probe")
+        return out
 
     def timing_enable(self, on=True):
         self.lib.slm_timing_enable(self.h, 1 if on else 0)
@@ -453,11 +466,13 @@ class Engine:
         # rows of every test fold whose Gram block this rank builds (all of them unless sharded)
         fold_rows = shard.fold_row_ranges(row_ptr) if sharded else \
             [(int(row_ptr[f]), int(row_ptr[f + 1])) for f in range(F)]
+        partial = False  # did the prepare routine leave rows of unscored folds unpacked?
         if on_host and row_perm is None and n >= 4096:
-            Xa, allG = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows, shard if sharded else None,
-                                               score_folds if sharded else None)
+            Xa, allG, partial = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows,
+                                                        shard if sharded else None, score_folds if sharded else None)
         elif sharded:
-            Xa, allG = self._prepare_sharded(X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard, score_folds)
+            Xa, allG, partial = self._prepare_sharded(X, y, sw, col_perm, row_perm, row_ptr, fold_rows, shard,
+                                                      score_folds)
         else:
             Xa = self.pack(X, y, sw, col_perm, row_perm)
             allG = self.gram_blocks(Xa, row_ptr, extra=1 if F > 1 else 0)
@@ -484,7 +499,7 @@ class Engine:
             self.gram_center(G_full, p)
             if F > 1:
                 self.gram_center(G_train, p)
-        if sharded and score_folds is not None and row_perm is None and F > 1 and (not on_host or n >= 4096):
+        if partial:
             # rows of the other folds reached the device only as far as the Gram build needed
             extra["partial_folds"] = {f for f in range(F) if f not in score_folds}
             extra["pack_args"] = (sw, col_perm)
@@ -533,7 +548,8 @@ class Engine:
         in `score_folds` (None = everything)."""
         torch = self.torch
         F = len(row_ptr) - 1
-        if score_folds is None or row_perm is not None or F == 1:
+        partial = not (score_folds is None or row_perm is not None or F == 1)
+        if not partial:
             Xa = self.pack(X, y, sw, col_perm, row_perm)
         else:
             Xd = self.to_device(X, torch.float64)
@@ -550,7 +566,7 @@ class Engine:
         for f, (lo, hi) in enumerate(fold_rows):
             self._gram_block_into(Xa, lo, hi, allG[f])
         self._allreduce_grams(allG[:F], shard)
-        return Xa, allG
+        return Xa, allG, partial
 
     def _allreduce_grams(self, G, shard):
         """Sum the partial Gram blocks G [F, pa, pa] over the ranks: upper triangles packed into
@@ -647,7 +663,7 @@ class Engine:
                 started.add(f)
         if shard is not None:
             self._allreduce_grams(allG[:max(F, 1)] if F > 1 else allG[:1], shard)
-        return Xa, allG
+        return Xa, allG, bool(F > 1 and score_folds is not None)
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,

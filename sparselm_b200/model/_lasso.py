@@ -80,8 +80,8 @@ class GroupLasso(Lasso):
     def _n_groups(self, n_features):
         if self.groups is None:
             return n_features
-        cache = self.__dict__.get("_group_cache")
-        if cache is not None and cache[0] is self.groups:
+        cache = self._cached_groups(n_features)
+        if cache is not None:
             return cache[4]
         return len(np.unique(self.groups))
 
@@ -110,22 +110,33 @@ class GroupLasso(Lasso):
             )
         return bool(self.standardize)
 
-    def _group_spec(self, n_features):
-        """(col_perm, gptr, gw) for the current groups (memoised on the identity of the
-        `groups` object: a grid search re-describes the same structure per candidate)."""
+    def _cached_groups(self, n_features):
+        """The memoised group structure if it still describes `self.groups`: same object AND same
+        content (a list or array mutated in place between fits must not reuse the old structure)."""
         cache = self.__dict__.get("_group_cache")
         if cache is None or cache[0] is not self.groups or cache[1] != n_features:
+            return None
+        if self.groups is not None and hash(np.asarray(self.groups).tobytes()) != cache[6]:
+            return None
+        return cache
+
+    def _group_spec(self, n_features):
+        """(col_perm, gptr, gw) for the current groups (memoised on the identity + a content
+        fingerprint of `groups`: a grid search re-describes the same structure per candidate)."""
+        cache = self._cached_groups(n_features)
+        if cache is None:
             groups = np.arange(n_features) if self.groups is None else np.asarray(self.groups)
             col_perm, gptr, n_groups = group_structure(groups, n_features)
-            cache = (self.groups, n_features, col_perm, gptr, n_groups, _arr_key(self.groups))
+            fp = None if self.groups is None else hash(np.asarray(self.groups).tobytes())
+            cache = (self.groups, n_features, col_perm, gptr, n_groups, _arr_key(self.groups), fp)
             self.__dict__["_group_cache"] = cache
-        _, _, col_perm, gptr, n_groups, _ = cache
+        _, _, col_perm, gptr, n_groups, _, _ = cache
         gw = np.ones(n_groups) if self.group_weights is None else np.asarray(self.group_weights, dtype=float)
         return col_perm, gptr, gw
 
     def _structure_key(self, name, n_features):
-        cache = self.__dict__.get("_group_cache")
-        gkey = cache[5] if (cache is not None and cache[0] is self.groups) else _arr_key(self.groups)
+        cache = self._cached_groups(n_features)
+        gkey = cache[5] if cache is not None else _arr_key(self.groups)
         return (name, n_features, bool(self.fit_intercept), bool(self.standardize), gkey,
                 _arr_key(self.group_weights))
 

@@ -147,8 +147,12 @@ def prepare_folds(engine, X, yv, test_folds, est, spec, cache=None, cache_key=No
     work (H2D copies, packing, Gram build): the caller can keep working on the host."""
     ck = None
     if cache is not None and cache_key is not None:
-        ck = (cache_key, _fold_key(est, spec), tuple(len(t) for t in test_folds),
-              tuple(int(t[0]) for t in test_folds))
+        # keyed on the full content of the split: a shuffling splitter draws a new partition per
+        # line, and two partitions can agree in fold sizes and first indices
+        import hashlib
+
+        fold_hash = hashlib.sha1(np.concatenate([np.asarray(t, dtype=np.int64) for t in test_folds]).tobytes()).hexdigest()
+        ck = (cache_key, _fold_key(est, spec), tuple(len(t) for t in test_folds), fold_hash)
         if ck in cache:
             return cache[ck]
     fd = engine.prepare(X, yv, test_folds, est.fit_intercept, sample_weight, col_perm=spec.col_perm, shard=shard,
@@ -555,6 +559,12 @@ class LineSearchCV(BaseSearchCV):
         history = []
         fd_cache = {}  # device-resident design shared by every line (same X, y, folds)
         best = None
+        if isinstance(self.estimator, EngineRegressor) and y is not None and not hasattr(X, "columns"):
+            # one float64 conversion for all lines: the FoldData cache recognises the design by identity
+            try:
+                X, y = check_X_y(X, y, dtype=np.float64, y_numeric=True, ensure_min_samples=2, ensure_all_finite=False)
+            except Exception:
+                pass  # the first GridSearchCV raises the proper error
         for i in range(n_iter):
             pid = i % n_params
             last = [values[0] for _, values in grid] if best is None else [best[name] for name, _ in grid]

@@ -492,6 +492,90 @@ def test_line_search_alpha_l1_ratio():
     npt.assert_allclose(ls.predict(X), X @ ls.best_estimator_.coef_ + ls.best_estimator_.intercept_)
 
 
+def _oracle_line_search(name, X, y, grid, methods, n_iter, cv, fixed_kw):
+    """The reference's LineSearchCV.fit (model_selection.py:656-695) as an explicit loop: every
+    (candidate, fold) cell is one per-fit oracle solve scored with neg RMSE; selection by the first
+    rank-1 candidate (max_score) or the one-standard-error rule (:190-223)."""
+    from sklearn.model_selection import KFold
+
+    from sparselm_b200.model_selection import _select_best_index_onestd
+
+    folds = list(KFold(cv).split(X))
+    best, lines = None, []
+    for i in range(n_iter):
+        pid = i % len(grid)
+        last = [vals[0] for _, vals in grid] if best is None else [best[nm] for nm, _ in grid]
+        cands = [{nm: (v if j == pid else last[j]) for j, (nm, _) in enumerate(grid)} for v in grid[pid][1]]
+        scores = np.zeros((len(cands), cv))
+        for ci, c in enumerate(cands):
+            for f, (tr, te) in enumerate(folds):
+                b, icpt = R.fit(name, X[tr], y[tr], **c, **fixed_kw)
+                scores[ci, f] = -np.sqrt(np.mean((y[te] - X[te] @ b - icpt) ** 2))
+        mean, std = scores.mean(1), scores.std(1)
+        if methods[pid] == "max_score":
+            bi = int(np.argmax(mean))
+        else:
+            from scipy.stats import rankdata
+
+            res = {"rank_test_score": rankdata(-mean, method="min"), "mean_test_score": mean, "std_test_score": std,
+                   "params": cands}
+            for nm, _ in grid:
+                res[f"param_{nm}"] = [c[nm] for c in cands]
+            bi = int(_select_best_index_onestd(True, "score", res))
+        best = dict(cands[bi])
+        lines.append(dict(cands=cands, mean=mean, std=std, best=best))
+    return lines
+
+
+@pytest.mark.parametrize("methods", [None, ["one_std_score", "max_score"]])
+def test_line_search_matches_explicit_oracle_loop(methods):
+    """LineSearchCV against an independently computed search: every line's mean / std test scores,
+    every line's best_params_, and the final refit, vs a loop of per-fit oracle solves that follows
+    the reference's LineSearchCV.fit step by step."""
+    rng = np.random.default_rng(21)
+    n, p = 120, 24
+    X = rng.standard_normal((n, p))
+    y = X[:, :3] @ [2.0, -1.5, 1.0] + X[:, 8:10] @ [0.8, -0.6] + 0.6 * rng.standard_normal(n)
+    groups = np.repeat(np.arange(6), 4)
+    grid = [("alpha", list(np.logspace(-2.3, -0.3, 6))), ("l1_ratio", [0.1, 0.5, 0.9])]
+    est = SparseGroupLasso(groups=groups, fit_intercept=True, solver_options={"tol": 1e-12})
+    ls = LineSearchCV(est, grid, cv=3, n_iter=4, opt_selection_method=methods).fit(X, y)
+    ref = _oracle_line_search("SparseGroupLasso", X, y, grid, methods or ["max_score"] * 2, 4, 3,
+                              dict(groups=groups, fit_intercept=True))
+    assert len(ls.history_) == 4
+    for gs, line in zip(ls.history_, ref):
+        assert gs.batched_
+        assert [dict(c) for c in gs.cv_results_["params"]] == line["cands"]
+        npt.assert_allclose(gs.cv_results_["mean_test_score"], line["mean"], rtol=1e-8, atol=1e-10)
+        npt.assert_allclose(gs.cv_results_["std_test_score"], line["std"], rtol=1e-6, atol=1e-9)
+        assert gs.best_params_ == line["best"]
+    assert ls.best_params_ == ref[-1]["best"]
+    b, icpt = R.fit("SparseGroupLasso", X, y, groups=groups, fit_intercept=True, **ref[-1]["best"])
+    assert np.abs(ls.best_estimator_.coef_ - b).max() <= 1e-6 * np.abs(b).max()
+    assert abs(ls.best_estimator_.intercept_ - icpt) <= 1e-6 * max(1.0, abs(icpt))
+
+
+def test_line_search_resplits_with_a_shuffling_splitter():
+    """A shuffling splitter without a fixed seed draws a new partition per line: the device-resident
+    fold cache must not serve the Grams of an earlier partition (it is keyed on the split's content)."""
+    from sklearn.model_selection import KFold
+
+    rng = np.random.default_rng(22)
+    X = rng.standard_normal((80, 10))
+    y = X[:, 0] - 0.5 * X[:, 1] + 0.3 * rng.standard_normal(80)
+    cv = KFold(2, shuffle=True, random_state=np.random.RandomState(3))  # a new shuffle on every split() call
+    grid = [("alpha", [0.01, 0.1, 0.3])]
+    ls = LineSearchCV(Lasso(solver_options={"tol": 1e-12}), grid, cv=cv, n_iter=3).fit(X, y)
+    cv2 = KFold(2, shuffle=True, random_state=np.random.RandomState(3))
+    for gs in ls.history_:
+        folds = list(cv2.split(X))
+        for ci, a in enumerate(grid[0][1]):
+            for f, (tr, te) in enumerate(folds):
+                b, _ = R.fit("Lasso", X[tr], y[tr], alpha=a)
+                ref = -np.sqrt(np.mean((y[te] - X[te] @ b) ** 2))
+                assert gs.cv_results_[f"split{f}_test_score"][ci] == pytest.approx(ref, rel=1e-8)
+
+
 def test_readme_example_adaptive_lasso_grid():
     """BASELINE config 1: README example; best_params_ compared tie-tolerantly."""
     from sklearn.model_selection import GridSearchCV as SkGS
