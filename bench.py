@@ -13,9 +13,16 @@ One "step" = one full cross-validated grid search of the workload (every
               timed region, refit on the full data included
 * roofline  : the dominant kernel (FP64 DMMA Gram apply) against the FP64 tensor peak, which
               MEASURED_PEAKS.json does not hold: it is measured here with cuBLAS DGEMM 8192^3
-* cpu_baseline / --impl reference : the CPU oracle (oracle/, block coordinate descent in C with
-              OpenMP over independent fits) on a bounded sample of the same workload.  The
-              reference's own cvxpy path cannot run in this image (cvxpy is not installed).
+* cpu_baseline / --impl reference : the CPU oracle (oracle/) on the host cores.  Two arms: "gram_path"
+              = what a careful CPU implementation of the same search does (per-fold Grams built once with
+              BLAS, block coordinate descent in Gram form, every alpha warm-started from the previous
+              one, OpenMP over fold x path-segment tasks) on the WHOLE workload -- this is the value of
+              `--impl reference`; and "per_fit" = one independent residual-form solve per (alpha, fold)
+              cell, one cell per thread, the structural analogue of the reference's joblib fan-out of
+              cvxpy solves, on a bounded sample.  The reference's own cvxpy path cannot run in this
+              image (cvxpy is not installed); both arms are far faster than it would be.
+* tall      : (default workload only) the tall-design config C5 (n=400k, p=8k, X row-sharded, Gram
+              all-reduce) as a companion object, 3 steps; `--workload c5` gives it a full line.
 """
 
 from __future__ import annotations
@@ -69,8 +76,10 @@ def workload(name):
         n, p, K, F = 10000, 2000, 100, 5
         X, y = make_data(n, p)
         est = Lasso(solver_options=opts)
-        desc = "Lasso, 100 alphas x 5 folds, n=10000 p=2000 (BASELINE configs[1], one line of LineSearchCV)"
+        desc = ("Lasso LineSearchCV, 100 alphas x 5 folds, n=10000 p=2000 (BASELINE configs[1]): n_iter = 2 lines of "
+                "the alpha grid + a refit per line")
         oracle = dict(name="Lasso")
+        lines = 2
     elif name == "c1":
         from sklearn.datasets import make_regression
 
@@ -108,7 +117,8 @@ def workload(name):
         raise SystemExit(f"unknown workload {name}")
     alpha_max = np.abs(X.T @ y).max() / n
     alphas = alpha_max * np.logspace(0, -3, K)
-    return dict(X=X, y=y, est=est, alphas=alphas, F=F, desc=desc, name=name, oracle=oracle)
+    return dict(X=X, y=y, est=est, alphas=alphas, F=F, desc=desc, name=name, oracle=oracle,
+                lines=lines if name == "c2" else 1)
 
 
 # --------------------------------------------------------------------------- #
@@ -273,6 +283,65 @@ def cpu_run(sp):
     return K / dt, dt, infos
 
 
+def cpu_gram_path_problem(wl):
+    """Inputs of the Gram-form path arm: features in group order, fold edges, penalty tables."""
+    import oracle.reference as R
+
+    if wl.get("device_gen") or wl["oracle"]["name"] not in ("Lasso", "SparseGroupLasso"):
+        return None
+    X, y, o, F = wl["X"], wl["y"], wl["oracle"], wl["F"]
+    n, p = X.shape
+    if o["name"] == "Lasso":
+        labels, G, l1r = np.arange(p), p, 1.0
+    else:
+        labels, G = R.group_labels(o["groups"], p)
+        l1r = o["l1_ratio"]
+    order = np.argsort(labels, kind="stable")
+    gptr = np.concatenate([[0], np.cumsum(np.bincount(labels, minlength=G))]).astype(np.int64)
+    return dict(Xo=np.ascontiguousarray(X[:, order]), y=y, F=F, n=n, p=p, G=G, gptr=gptr, l1r=l1r,
+                alphas=np.asarray(wl["alphas"], dtype=float), edges=np.linspace(0, n, F + 1).astype(int))
+
+
+def cpu_gram_path_run(gp, threads):
+    """One whole CV search on the host: fold Grams (BLAS), then fold x path-segment tasks of
+    warm-started Gram-form BCD (slmo_gram_path_many).  Returns (fits/s, seconds, infos)."""
+    import ctypes
+
+    import oracle.reference as R
+
+    lib = R._load()
+    F, n, p, G, alphas, edges = gp["F"], gp["n"], gp["p"], gp["G"], gp["alphas"], gp["edges"]
+    t0 = time.perf_counter()
+    blocks = []
+    for f in range(F):
+        Xf, yf = gp["Xo"][edges[f]:edges[f + 1]], gp["y"][edges[f]:edges[f + 1]]
+        blocks.append((Xf.T @ Xf, Xf.T @ yf, float(yf @ yf)))
+    Gtot, ctot, ytot = sum(b[0] for b in blocks), sum(b[1] for b in blocks), sum(b[2] for b in blocks)
+    Gs = [Gtot - b[0] for b in blocks]
+    cs = [ctot - b[1] for b in blocks]
+    K = len(alphas)
+    nseg = max(1, min(K // 8, -(-threads // F)))  # enough tasks for every thread, paths of >= 8 alphas
+    segs = np.linspace(0, K, nseg + 1).astype(int)
+    tasks = [(f, segs[i], segs[i + 1]) for i in range(nseg) for f in range(F)]
+    T = len(tasks)
+    koff = np.concatenate([[0], np.cumsum([b - a for _, a, b in tasks])]).astype(np.int64)
+    Kt = int(koff[-1])
+    w1, w2, dl = np.zeros((Kt, p)), np.zeros((Kt, G)), np.zeros((Kt, G))
+    for t, (f, a, b) in enumerate(tasks):
+        w1[koff[t]:koff[t + 1]] = (gp["l1r"] * alphas[a:b])[:, None]
+        w2[koff[t]:koff[t + 1]] = ((1 - gp["l1r"]) * alphas[a:b])[:, None]
+    dp = ctypes.POINTER(ctypes.c_double)
+    Gp = (dp * T)(*[R._dp(Gs[f]) for f, _, _ in tasks])
+    cp = (dp * T)(*[R._dp(cs[f]) for f, _, _ in tasks])
+    yty = np.array([ytot - blocks[f][2] for f, _, _ in tasks])
+    ns = np.array([float(n - (edges[f + 1] - edges[f])) for f, _, _ in tasks])
+    betas, infos = np.zeros((Kt, p)), np.zeros((Kt, 4))
+    lib.slmo_gram_path_many(T, p, Gp, cp, R._dp(yty), R._dp(ns), G, R._ip(gp["gptr"]), R._ip(koff), R._dp(w1),
+                            R._dp(w2), R._dp(dl), TOL, 1e-14, 100000, 2, R._dp(betas), R._dp(infos))
+    dt = time.perf_counter() - t0
+    return Kt / dt, dt, infos
+
+
 def cpu_baseline(wl, n_fits=None):
     import oracle.reference as R
 
@@ -284,10 +353,20 @@ def cpu_baseline(wl, n_fits=None):
         return {"value": None, "unit": "fits/s", "cores": threads, "kind": "port",
                 "sample": "not timed for this workload"}
     v, dt, infos = cpu_run(sp)
-    return {"value": v, "unit": "fits/s", "cores": threads, "kind": "port",
-            "sample": f"{len(sp['alphas'])} of the {len(wl['alphas'])} alphas on training fold 0 "
-                      f"(n={sp['n']}, p={sp['p']}), oracle BCD to gap {TOL:g}, {dt:.1f} s, "
-                      f"mean sweeps {infos[:, 0].mean():.0f}; cvxpy not installed: reference path not timed"}
+    per_fit = {"value": v, "unit": "fits/s", "cores": threads,
+               "sample": f"{len(sp['alphas'])} of the {len(wl['alphas'])} alphas on training fold 0 "
+                         f"(n={sp['n']}, p={sp['p']}), one independent residual-form BCD solve per thread to gap "
+                         f"{TOL:g}, {dt:.1f} s, mean sweeps {infos[:, 0].mean():.0f}"}
+    gp = cpu_gram_path_problem(wl)
+    if gp is None:
+        return {**per_fit, "kind": "port", "sample": per_fit["sample"] + "; cvxpy not installed: reference path not timed"}
+    v2, dt2, infos2 = cpu_gram_path_run(gp, threads)
+    return {"value": v2, "unit": "fits/s", "cores": threads, "kind": "port",
+            "sample": f"the whole workload ({len(infos2)} fits): per-fold Grams by BLAS + Gram-form BCD along "
+                      f"warm-started alpha paths (OpenMP over fold x segment tasks) to gap {TOL:g}, {dt2:.1f} s, "
+                      f"mean sweeps {infos2[:, 0].mean():.1f}, {int((infos2[:, 3] == 1).sum())} unconverged; "
+                      f"cvxpy not installed: reference path not timed",
+            "per_fit": per_fit}
 
 
 # --------------------------------------------------------------------------- #
@@ -328,20 +407,26 @@ def run_reference(args):
 
     R.build()
     threads = R.num_threads()
-    sp = cpu_sample_problem(wl, max(4, min(threads, 16)))
-    if sp is None:
+    gp = cpu_gram_path_problem(wl)
+    sp = None if gp is not None else cpu_sample_problem(wl, max(4, min(threads, 16)))
+    if gp is None and sp is None:
         print(json.dumps({"impl": "reference", "unavailable": "CPU oracle arm not wired for this workload"}))
         return
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, _ = cpu_run(sp)
+        v, dt, _ = cpu_gram_path_run(gp, threads) if gp is not None else cpu_run(sp)
         if i >= args.warmup:
             vals.append((v, dt))
     value = float(np.mean([v for v, _ in vals]))
     ms = float(np.mean([dt for _, dt in vals])) * 1e3
-    sample = (f"{len(sp['alphas'])} of {len(wl['alphas'])} alphas x 1 of {wl['F']} folds per step, oracle BCD "
-              f"(C, OpenMP over fits) to gap {TOL:g}; cvxpy is not installed so the reference's own solve "
-              f"cannot be timed")
+    if gp is not None:
+        sample = (f"the whole workload per step ({len(wl['alphas'])} alphas x {wl['F']} folds): per-fold Grams by BLAS + "
+                  f"Gram-form block coordinate descent along warm-started alpha paths (C, OpenMP over fold x segment "
+                  f"tasks) to gap {TOL:g}; cvxpy is not installed so the reference's own solve cannot be timed")
+    else:
+        sample = (f"{len(sp['alphas'])} of {len(wl['alphas'])} alphas x 1 of {wl['F']} folds per step, oracle BCD "
+                  f"(C, OpenMP over fits) to gap {TOL:g}; cvxpy is not installed so the reference's own solve "
+                  f"cannot be timed")
     line = {
         "impl": "reference", "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -387,7 +472,8 @@ def run_engine(args):
         wl = device_data(wl, torch, dev)
     X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
     n, p = X.shape
-    n_fits = len(alphas) * F
+    lines = int(wl.get("lines", 1))  # line searches per step (LineSearchCV: the Grams are built once)
+    n_fits = len(alphas) * F * lines
     shard = None
     if world > 1:
         from sparselm_b200.parallel import GridShard
@@ -411,10 +497,14 @@ def run_engine(args):
         ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
     opts = est._engine_options()
 
-    def step_device():
-        return batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error",
-                          shard=shard) if shard is not None else \
-            batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error")
+    def step_device(sh=shard):
+        if lines == 1:
+            return batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error", shard=sh)
+        cache = {}  # what LineSearchCV keeps between its lines: the device-resident design and Grams
+        for _ in range(lines):
+            out = batched_cv(engine, Xd, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error", shard=sh,
+                             cache=cache, cache_key="bench")
+        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -464,13 +554,101 @@ def run_engine(args):
     if world > 1 and args.workload == "c3" and not args.no_weak:
         weak = run_weak(args, torch, engine, Xd, y, folds, work, alphas, F, p, opts, shard, barrier, world, dev)
 
+    # ---- sharded search against the un-sharded one (outside every timed region) ----------------
+    parity = None
+    if world > 1:
+        try:
+            if rank == 0:
+                single = step_device(None)
+                a, b = np.asarray(res["test_scores"]), np.asarray(single["test_scores"])
+                parity = {"sharded_vs_single_rel_err": float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))),
+                          "what": "max relative difference of the (alpha, fold) test-score table between the sharded "
+                                  f"search on {world} GPUs and the same search on rank 0 alone"}
+        except Exception as exc:  # noqa: BLE001
+            parity = {"sharded_vs_single_rel_err": None, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        barrier()
+
+    # ---- tall-design companion (BASELINE configs[4]) ---------------------------------------------
+    tall = None
+    if args.workload == "c3" and not args.no_tall:
+        tall = run_tall(args, torch, engine, shard, barrier, world, rank, dev, peak)
+
     # ---- end-to-end arm: public API on host (pinned) arrays --------------------------
     if wl.get("device_gen"):
         e2e = None  # 25.6 GB design generated on the device: no host copy to start from
     else:
         e2e = run_e2e(args, torch, wl, shard, barrier, world, dev)
     finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank,
-           weak)
+           weak, parity, tall)
+
+
+def run_tall(args, torch, engine, shard, barrier, world, rank, dev, peak):
+    """C5 next to the headline: RidgedGroupLasso, n=400000, p=8000, 100 alphas x 5 folds, rows of the
+    Gram build sharded over the ranks (one all-reduce), 3 timed steps.  A failure here must not cost
+    the headline line: it is reported inside the object instead."""
+    import gc
+    from types import SimpleNamespace
+
+    from sklearn.base import clone
+    from sklearn.model_selection import KFold
+
+    from sparselm_b200.model_selection import batched_cv
+
+    try:
+        wl = device_data(workload("c5"), torch, dev)
+        X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
+        n, p = X.shape
+        work = clone(est)
+        ests, specs = [], []
+        for a in alphas:
+            work.set_params(alpha=a)
+            specs.append(work._problem_spec(p))
+            ests.append(SimpleNamespace(fit_intercept=bool(work.fit_intercept)))
+        opts = est._engine_options()
+        folds = [te for _, te in KFold(F).split(np.empty((n, 1)))]
+
+        def step():
+            return batched_cv(engine, X, y, folds, ests, specs, dict(opts), "neg_root_mean_squared_error", shard=shard)
+
+        for _ in range(3):
+            res = step()
+        barrier()
+        engine.timing_enable(True)
+        engine.timing_reset()
+        ts = []
+        for _ in range(3):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = step()
+            e1.record()
+            barrier()
+            ts.append(e0.elapsed_time(e1))
+        tim = engine.timing_read()
+        engine.timing_enable(False)
+        ms = float(np.mean(ts))
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gb = tim["gram_build"]
+        build_tf = gb["flops"] / (gb["ms"] * 1e-3) / 1e12 if gb["ms"] > 0 else None
+        out = {"workload": wl["desc"], "value": len(alphas) * F / (ms / 1e3), "unit": "fits/s", "ms_per_step": ms,
+               "steps": 3, "warmup": 3, "n_gpus": world, "unconverged": int(res["n_unconverged"]),
+               "iterations_per_step": int(res["iters_run"]),
+               "roofline": {"bound": "tensor", "kernel": "gemm_f64_tma_kernel<SYM> (this rank's share of the Gram build, "
+                                                         "FP64 DMMA, SYRK flop count)",
+                            "achieved": build_tf, "peak": peak, "unit": "TFLOP/s",
+                            "frac": build_tf / peak if build_tf else None,
+                            "step_ms_by_kernel_family": {k: v["ms"] / 3 for k, v in tim.items()}}}
+        del X, wl, res
+        gc.collect()
+        torch.cuda.empty_cache()
+        return out
+    except Exception as exc:  # noqa: BLE001
+        return {"value": None, "unit": "fits/s", "error": f"{type(exc).__name__}: {exc}"[:300]}
 
 
 def run_weak(args, torch, engine, Xd, y, folds, work, alphas, F, p, opts, shard, barrier, world, dev):
@@ -523,17 +701,21 @@ def run_weak(args, torch, engine, Xd, y, folds, work, alphas, F, p, opts, shard,
 def run_e2e(args, torch, wl, shard, barrier, world, dev):
     from sklearn.base import clone
 
-    from sparselm_b200.model_selection import GridSearchCV
+    from sparselm_b200.model_selection import GridSearchCV, LineSearchCV
 
     X, y, est, alphas, F = wl["X"], wl["y"], wl["est"], wl["alphas"], wl["F"]
     n, p = X.shape
-    n_fits = len(alphas) * F
+    lines = int(wl.get("lines", 1))
+    n_fits = len(alphas) * F * lines
     Xp = torch.from_numpy(X).pin_memory()
     Xh = Xp.numpy()
     grid = {"alpha": list(alphas)}
 
     def step_e2e():
-        gs = GridSearchCV(clone(est), grid, cv=F)
+        if lines > 1:  # BASELINE configs[1]: LineSearchCV, n_iter = 2 * n_params lines, a refit per line
+            gs = LineSearchCV(clone(est), [("alpha", list(alphas))], cv=F)
+        else:
+            gs = GridSearchCV(clone(est), grid, cv=F)
         if shard is not None:
             gs._shard = shard
         gs.fit(Xh, y)
@@ -556,19 +738,21 @@ def run_e2e(args, torch, wl, shard, barrier, world, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     h2d = X.nbytes + y.nbytes
-    d2h = 8 * (n_fits * 2 + n_fits + p + 1)  # residual sums, per-fit info, refit coefficients
+    d2h = 8 * (n_fits * 2 + n_fits + lines * (p + 1))  # residual sums, per-fit info, refit coefficients
+    api = "LineSearchCV.fit (2 lines, pinned host X uploaded once, a refit per line)" if lines > 1 else \
+        "GridSearchCV.fit (pinned host X, refit included)"
     return {"value": n_fits / (e2e_ms / 1e3), "unit": "fits/s", "ms_per_step": e2e_ms,
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "api": "sparselm_b200.model_selection.GridSearchCV.fit (pinned host X, refit included)"}
+            "api": "sparselm_b200.model_selection." + api}
 
 
 def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, launches, clocks, peak, world, rank,
-           weak=None):
+           weak=None, parity=None, tall=None):
     if rank != 0:
         return
     X, alphas, F = wl["X"], wl["alphas"], wl["F"]
     n, p = X.shape
-    n_fits = len(alphas) * F
+    n_fits = len(alphas) * F * int(wl.get("lines", 1))
     xbytes = n * p * 8
     ap = tim["gram_apply"]
     apply_ms = ap["ms"] / max(ap["launches"], 1)
@@ -577,10 +761,13 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     # dense-equivalent figure 2 p^2 K_active is reported next to it
     achieved = exec_flops / (ap["ms"] * 1e-3) / 1e12 if ap["ms"] > 0 else None
     dense_equiv = ap["flops"] / (ap["ms"] * 1e-3) / 1e12 if ap["ms"] > 0 else None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("gram_apply_dram_bytes_per_launch")
+    # DRAM bytes per launch of the dominant kernel from an ncu --set full capture of THIS workload on one GPU
+    # (profiles/): a constant of that capture, so it is only quoted for the configuration it was taken on
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if world == 1 and os.path.exists(tpath):
+        ent = json.load(open(tpath)).get(args.workload, {})
+        traffic, traffic_src = ent.get("gram_apply_dram_bytes_per_launch"), ent.get("source")
     step_ms = {k: v["ms"] / args.steps for k, v in tim.items()}
     info = res["info"]
     gb = tim["gram_build"]
@@ -588,18 +775,19 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
     if gb["ms"] > ap["ms"]:
         # tall designs: the dominant kernel is the Gram build (SYRK count n pa (pa+1))
-        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel<SYM> (Gram build, FP64 DMMA, SYRK flop count)",
+        roof = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel<SYM> (Gram build, TMA-fed FP64 DMMA, SYRK flop count)",
                 "achieved": build_tf, "peak": peak, "unit": "TFLOP/s", "frac": build_tf / peak if build_tf else None,
                 "peak_source": src, "avg_launch_ms": gb["ms"] / max(gb["launches"], 1),
                 "launches_per_step": gb["launches"] / args.steps, "traffic": None,
                 "gram_apply_tflops": achieved, "step_ms_by_kernel_family": step_ms}
     else:
-        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (row-sparse Gram apply, FP64 DMMA)",
+        roof = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (row-sparse Gram apply, TMA gather4-fed FP64 DMMA)",
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                 "peak_source": src, "dense_equivalent_tflops": dense_equiv,
                 "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
                 "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
-                "traffic": traffic, "gram_build_tflops": build_tf, "step_ms_by_kernel_family": step_ms}
+                "traffic": traffic, "traffic_source": traffic_src, "gram_build_tflops": build_tf,
+                "step_ms_by_kernel_family": step_ms}
     nw = res.get("newton") or {}
     if nw.get("factorizations"):  # second-order phase of the last timed step (library Cholesky, sparselm_b200/newton.py)
         roof["newton_phase"] = {"ms_per_step": float(nw["ms"]), "factorizations_per_step": int(nw["factorizations"]),
@@ -623,6 +811,11 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     }
     if weak is not None:
         line["weak_scaling"] = weak
+    if parity is not None:
+        line["sharded_parity"] = parity
+    if tall is not None:
+        line["tall"] = tall
+    line["tma_launches"] = int(engine.tma_launch_count())
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(wl)
     print(json.dumps(line))
@@ -637,6 +830,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling companion run (N > 1)")
+    ap.add_argument("--no-tall", action="store_true", help="skip the tall-design (C5) companion object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":

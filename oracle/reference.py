@@ -88,6 +88,16 @@ def _load():
             ctypes.c_int64, ip, dp, dp, dp, ctypes.c_double, ctypes.c_double,
             ctypes.c_int64, ctypes.c_int64, dp, dp,
         ]
+        lib.slmo_gram_path.restype = ctypes.c_int
+        lib.slmo_gram_path.argtypes = [
+            ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ip, ctypes.c_int64,
+            dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int64, dp, dp, dp,
+        ]
+        lib.slmo_gram_path_many.restype = ctypes.c_int
+        lib.slmo_gram_path_many.argtypes = [
+            ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(dp), ctypes.POINTER(dp), dp, dp, ctypes.c_int64, ip, ip,
+            dp, dp, dp, ctypes.c_double, ctypes.c_double, ctypes.c_int64, ctypes.c_int64, dp, dp,
+        ]
         lib.slmo_num_threads.restype = ctypes.c_int
         _lib = lib
     return _lib
@@ -432,6 +442,32 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
     if return_details:
         return beta, intercept, details
     return beta, intercept
+
+
+def gram_path(G, c, yty, n, pen_list, labels, tol=1e-13, max_sweeps=200000, check_every=5, floor_rel_y=1e-16):
+    """Gram-form BCD along a path (slmo_gram_path): G = X^T X [p, p], c = X^T y, yty, n of one
+    training set; pen_list = Penalty objects sharing `labels` (solved in order, each warm-started
+    from the previous solution).  Returns (betas [K, p], infos [K, 4])."""
+    lib = _load()
+    p = len(c)
+    n_groups = pen_list[0].n_groups
+    order = np.argsort(labels, kind="stable")
+    counts = np.bincount(labels, minlength=n_groups)
+    gptr = np.zeros(n_groups + 1, dtype=np.int64)
+    np.cumsum(counts, out=gptr[1:])
+    Gp = np.ascontiguousarray(G[np.ix_(order, order)], dtype=np.float64)
+    cp = np.ascontiguousarray(c[order], dtype=np.float64)
+    K = len(pen_list)
+    w1 = np.ascontiguousarray(np.stack([pn.w1[order] for pn in pen_list]))
+    w2 = np.ascontiguousarray(np.stack([pn.w2 for pn in pen_list]))
+    dl = np.ascontiguousarray(np.stack([pn.delta for pn in pen_list]))
+    betas = np.zeros((K, p))
+    infos = np.zeros((K, 4))
+    lib.slmo_gram_path(p, _dp(Gp), _dp(cp), float(yty), float(n), n_groups, _ip(gptr), K, _dp(w1), _dp(w2), _dp(dl),
+                       tol, floor_rel_y, max_sweeps, check_every, None, _dp(betas), _dp(infos))
+    out = np.empty_like(betas)
+    out[:, order] = betas
+    return out, infos
 
 
 def num_threads():

@@ -288,6 +288,186 @@ int slmo_bcd_many(i64 K, const i64 *n, i64 p, const double *const *Xs,
     return bad;
 }
 
+
+/* ---- second CPU baseline: Gram-form block coordinate descent along a warm-started path --------
+ * What a careful CPU implementation of the same search would do (the strongest CPU arm bench.py
+ * reports; still test/bench infrastructure): the training Gram G = X^T X, c = X^T y and y^T y are
+ * built once per fold (BLAS, in the caller) and every alpha of a descending path starts from the
+ * solution of the previous one.  A block update costs O(p |g|) through q = G beta instead of
+ * O(n |g|) through the residual.  Same objective, same duality-gap certificate (evaluated from the
+ * Gram quantities), same stopping rule as slmo_bcd.
+ * G: p x p row-major (symmetric); w1 [K][p], w2 [K][G], delta [K][G]; betas [K][p] out;
+ * infos [K][4] = sweeps, primal, gap, status.  beta0 (may be NULL): start of the first problem. */
+static void gram_certificate(i64 p, const double *c, double yty, double n, i64 G, const i64 *gptr,
+                             const double *w1, const double *w2, const double *delta,
+                             const double *beta, const double *q, double *gbuf, double *out) {
+    double cb = 0.0, bq = 0.0, pen = 0.0, ridge = 0.0, omega = 0.0;
+    for (i64 gi = 0; gi < G; ++gi) {
+        i64 a = gptr[gi], b = gptr[gi + 1];
+        double nb = 0.0;
+        for (i64 j = a; j < b; ++j) {
+            gbuf[j] = (c[j] - q[j]) / n - delta[gi] * beta[j];
+            cb += c[j] * beta[j];
+            bq += beta[j] * q[j];
+            pen += w1[j] * fabs(beta[j]);
+            nb += beta[j] * beta[j];
+        }
+        pen += w2[gi] * sqrt(nb);
+        ridge += delta[gi] * nb;
+        double nu = group_dual_norm(gbuf + a, w1 + a, b - a, w2[gi]);
+        if (nu > omega) omega = nu;
+    }
+    double rr_aug = yty - 2.0 * cb + bq + n * ridge;
+    double yr = yty - cb;
+    double primal = rr_aug / (2.0 * n) + pen;
+    double s = (omega > 1.0) ? 1.0 / omega : 1.0;
+    if (!(omega < INFINITY)) s = 0.0;
+    double dual = (2.0 * s * yr - s * s * rr_aug) / (2.0 * n);
+    out[0] = primal; out[1] = dual; out[2] = primal - dual; out[3] = omega;
+}
+
+int slmo_gram_path(i64 p, const double *Gm, const double *c, double yty, double n, i64 G,
+                   const i64 *gptr, i64 K, const double *w1, const double *w2, const double *delta,
+                   double tol, double floor_rel_y, i64 max_sweeps, i64 check_every,
+                   const double *beta0, double *betas, double *infos) {
+    double *beta = (double *)calloc((size_t)p, sizeof(double));
+    double *q = (double *)calloc((size_t)p, sizeof(double));
+    double *gbuf = (double *)malloc(sizeof(double) * (size_t)p);
+    double *L = (double *)malloc(sizeof(double) * (size_t)G);
+    i64 smax = 1;
+    for (i64 gi = 0; gi < G; ++gi)
+        if (gptr[gi + 1] - gptr[gi] > smax) smax = gptr[gi + 1] - gptr[gi];
+    double *vnew = (double *)malloc(sizeof(double) * (size_t)smax);
+    double *pv = (double *)malloc(sizeof(double) * (size_t)smax);
+    double *dl = (double *)malloc(sizeof(double) * (size_t)smax);
+    if (beta0) {
+        memcpy(beta, beta0, sizeof(double) * (size_t)p);
+        for (i64 j = 0; j < p; ++j)
+            if (beta[j] != 0.0) {
+                const double *gj = Gm + j * p;
+                for (i64 i = 0; i < p; ++i) q[i] += gj[i] * beta[j];
+            }
+    }
+    /* block curvature lambda_max(G_gg)/n by power iteration on the diagonal block */
+    for (i64 gi = 0; gi < G; ++gi) {
+        i64 a = gptr[gi], s = gptr[gi + 1] - a;
+        if (s == 1) { L[gi] = Gm[a * p + a] / n; continue; }
+        for (i64 k = 0; k < s; ++k) pv[k] = 1.0 / sqrt((double)s) * (1.0 + 0.01 * (double)k);
+        double lam = 0.0;
+        for (int it = 0; it < 60; ++it) {
+            double nrm = 0.0;
+            for (i64 k = 0; k < s; ++k) {
+                double d = 0.0;
+                const double *row = Gm + (a + k) * p + a;
+                for (i64 m = 0; m < s; ++m) d += row[m] * pv[m];
+                vnew[k] = d;
+                nrm += d * d;
+            }
+            nrm = sqrt(nrm);
+            if (nrm == 0.0) { lam = 0.0; break; }
+            lam = nrm;
+            for (i64 k = 0; k < s; ++k) pv[k] = vnew[k] / nrm;
+        }
+        L[gi] = 1.02 * lam / n;
+    }
+    const double floor_abs = floor_rel_y * yty / (2.0 * n);
+    int bad = 0;
+    for (i64 k = 0; k < K; ++k) {
+        const double *w1k = w1 + k * p, *w2k = w2 + k * G, *dk = delta + k * G;
+        double cert[4] = {0, 0, 0, 0};
+        int status = 1;
+        i64 sweep;
+        for (sweep = 1; sweep <= max_sweeps; ++sweep) {
+            double max_change = 0.0, max_beta = 0.0;
+            for (i64 gi = 0; gi < G; ++gi) {
+                i64 a = gptr[gi], s = gptr[gi + 1] - a;
+                double Lg = L[gi];
+                if (Lg <= 0.0) continue;
+                for (int bt = 0; bt < 60; ++bt) {
+                    double un = 0.0;
+                    for (i64 m = 0; m < s; ++m) {
+                        double grad = (q[a + m] - c[a + m]) / n;
+                        double u = soft(beta[a + m] - grad / Lg, w1k[a + m] / Lg);
+                        vnew[m] = u;
+                        un += u * u;
+                    }
+                    un = sqrt(un);
+                    double shrink = 0.0;
+                    if (un > 0.0) {
+                        double t = 1.0 - (w2k[gi] / Lg) / un;
+                        shrink = (t > 0.0 ? t : 0.0) / (1.0 + dk[gi] / Lg);
+                    }
+                    double dn = 0.0;
+                    for (i64 m = 0; m < s; ++m) {
+                        vnew[m] *= shrink;
+                        dl[m] = vnew[m] - beta[a + m];
+                        dn += dl[m] * dl[m];
+                    }
+                    if (dn == 0.0) break;
+                    if (s > 1) { /* majoriser check on the diagonal block */
+                        double quad = 0.0;
+                        for (i64 m = 0; m < s; ++m) {
+                            const double *row = Gm + (a + m) * p + a;
+                            double d = 0.0;
+                            for (i64 t2 = 0; t2 < s; ++t2) d += row[t2] * dl[t2];
+                            quad += dl[m] * d;
+                        }
+                        if (quad / n > Lg * dn * (1.0 + 1e-12)) {
+                            Lg *= 1.5;
+                            L[gi] = Lg;
+                            continue;
+                        }
+                    }
+                    if (dn > max_change) max_change = dn;
+                    for (i64 m = 0; m < s; ++m) {
+                        if (dl[m] != 0.0) {
+                            const double *gj = Gm + (a + m) * p;
+                            const double d = dl[m];
+                            for (i64 i = 0; i < p; ++i) q[i] += gj[i] * d;
+                        }
+                        beta[a + m] = vnew[m];
+                    }
+                    break;
+                }
+            }
+            for (i64 j = 0; j < p; ++j)
+                if (fabs(beta[j]) > max_beta) max_beta = fabs(beta[j]);
+            int stationary = sqrt(max_change) <= 4e-16 * max_beta;
+            if (stationary || sweep % check_every == 0 || sweep == max_sweeps) {
+                gram_certificate(p, c, yty, n, G, gptr, w1k, w2k, dk, beta, q, gbuf, cert);
+                double scale = fabs(cert[0]) > floor_abs ? fabs(cert[0]) : floor_abs;
+                if (cert[2] <= tol * scale) { status = 0; break; }
+                if (stationary) { status = 2; break; }
+            }
+        }
+        if (sweep > max_sweeps) sweep = max_sweeps;
+        memcpy(betas + k * p, beta, sizeof(double) * (size_t)p);
+        infos[k * 4 + 0] = (double)sweep; infos[k * 4 + 1] = cert[0];
+        infos[k * 4 + 2] = cert[2]; infos[k * 4 + 3] = (double)status;
+        if (status == 1) ++bad;
+    }
+    free(beta); free(q); free(gbuf); free(L); free(vnew); free(pv); free(dl);
+    return bad;
+}
+
+/* T independent path segments (fold x alpha range), one OpenMP thread each: segment t works on
+ * Gram Gs[t] / cs[t] / yty[t] / ns[t] and the problems koff[t] .. koff[t+1]-1 of the flat
+ * w1 / w2 / delta / betas / infos arrays (cold start at the head of every segment). */
+int slmo_gram_path_many(i64 T, i64 p, const double *const *Gs, const double *const *cs, const double *yty,
+                        const double *ns, i64 G, const i64 *gptr, const i64 *koff, const double *w1,
+                        const double *w2, const double *delta, double tol, double floor_rel_y,
+                        i64 max_sweeps, i64 check_every, double *betas, double *infos) {
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
+    for (i64 t = 0; t < T; ++t) {
+        const i64 k0 = koff[t], K = koff[t + 1] - koff[t];
+        bad += slmo_gram_path(p, Gs[t], cs[t], yty[t], ns[t], G, gptr, K, w1 + k0 * p, w2 + k0 * G,
+                              delta + k0 * G, tol, floor_rel_y, max_sweeps, check_every, NULL,
+                              betas + k0 * p, infos + k0 * 4);
+    }
+    return bad;
+}
+
 int slmo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -79,7 +79,7 @@ struct slm_ctx {
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
     // TMA-fed GEMM kernels (gemm_f64_tma.cuh): bit 0 Gram build, bit 1 dense apply, bit 2 row-sparse
     // apply (SLM_TMA / slm_set_option "tma"); encode = cuTensorMapEncodeTiled resolved at run time
-    int tma_mask = 7;
+    int tma_mask = 7 + 8;  // + bit 3: wide bands for the gather kernels, bit 4: for the tiled kernels
     void* encode = nullptr;
 };
 
@@ -225,14 +225,16 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D map over a row-major [rows][ld] FP64 matrix, boxes of [box_rows][16 doubles], 128-byte swizzle,
 // out-of-bounds elements read as zero
-static bool make_map(slm_ctx* ctx, CUtensorMap* map, const double* base, long long rows, long long ld, int box_rows) {
+static bool make_map(slm_ctx* ctx, CUtensorMap* map, const double* base, long long rows, long long ld, int box_rows,
+                     int box_cols = kTmaBoxCols, bool swizzle = true) {
     if (!ctx->encode || !base || rows <= 0 || ld <= 0 || (ld & 1) || ((uintptr_t)base & 15)) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     const cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(double)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxCols, (cuuint32_t)box_rows};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = ((EncodeTiledFn)ctx->encode)(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                              swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -253,10 +255,10 @@ static bool tma_prepare(slm_ctx* ctx, GemmBatch& b, int family_bit) {
     return true;
 }
 
-template <int WM, int WN, int MI, int NI, bool SYM, int MINB, bool KSP, int BK, int STAGES>
-static cudaError_t launch_gemm_tma_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
-    using Cfg = TmaCfg<WM, WN, MI, NI, BK, STAGES>;
-    auto kern = gemm_f64_tma_kernel<WM, WN, MI, NI, BK, STAGES, SYM, MINB, KSP>;
+template <int WM, int WN, int MI, int NI, bool SYM, int MINB, bool KSP, int BK, int STAGES, bool WIDE>
+static cudaError_t launch_gemm_tma_w(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
+    using Cfg = TmaCfg<WM, WN, MI, NI, BK, STAGES, WIDE>;
+    auto kern = gemm_f64_tma_kernel<WM, WN, MI, NI, BK, STAGES, SYM, MINB, KSP, WIDE>;
     static int occupancy = 0;
     if (occupancy == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
@@ -273,8 +275,8 @@ static cudaError_t launch_gemm_tma_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s)
     b.flags = ctx->d_flags;
     CUtensorMap mp, mq;
     const int box_rows = KSP ? 1 : BK;
-    if (!make_map(ctx, &mp, b.baseP, b.rowsP, b.pr[0].ldp, box_rows) ||
-        !make_map(ctx, &mq, b.baseQ, b.rowsQ, b.pr[0].ldq, box_rows))
+    if (!make_map(ctx, &mp, b.baseP, b.rowsP, b.pr[0].ldp, box_rows, Cfg::A_COLS, !WIDE) ||
+        !make_map(ctx, &mq, b.baseQ, b.rowsQ, b.pr[0].ldq, box_rows, Cfg::B_COLS, !WIDE))
         return cudaErrorInvalidValue;
     int grid = b.full_waves > 0 ? ctx->sm_count * occupancy : (b.total_units + b.units_per_cta - 1) / b.units_per_cta;
     if (KSP) grid = (int)std::min<long long>((long long)ctx->sm_count * occupancy, b.total_units);
@@ -283,6 +285,14 @@ static cudaError_t launch_gemm_tma_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s)
     kern<<<grid, Cfg::NT, Cfg::SMEM, s>>>(b, mp, mq);
     ctx->tma_launches++;
     return cudaGetLastError();
+}
+
+// layout choice (tma_mask bit 3 = wide bands for the gather kernels, bit 4 = wide bands for the tiled ones)
+template <int WM, int WN, int MI, int NI, bool SYM, int MINB, bool KSP, int BK, int STAGES>
+static cudaError_t launch_gemm_tma_t(slm_ctx* ctx, GemmBatch& b, cudaStream_t s) {
+    const bool wide = (ctx->tma_mask & (KSP ? 8 : 16)) != 0;
+    if (wide) return launch_gemm_tma_w<WM, WN, MI, NI, SYM, MINB, KSP, BK, STAGES, true>(ctx, b, s);
+    return launch_gemm_tma_w<WM, WN, MI, NI, SYM, MINB, KSP, BK, STAGES, false>(ctx, b, s);
 }
 
 // K-major (apply) menu.  X(id, WM, WN, MI, NI, MINB, eff): tile = (WM*MI*8) x (WN*NI*8);
@@ -334,19 +344,25 @@ static cudaError_t launch_apply_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaSt
 // narrow tiles run 3 CTAs (24 warps) per SM with a 3-stage pipeline: measured 6.6 % faster than
 // 2 CTAs x 4 stages on the mid-solve scenario of tools/apply_probe.py (more warps hide the
 // gather latency; 80 registers, no spills)
+// eff: measured with the TMA wide-band kernels (tools/gemm_probe.py, profiles/r02c_gemm_probe.txt).  A tile
+// re-reads its 128-column band of the support rows of G whatever its width: below ~40 columns the tile time
+// is set by that L2 -> shared-memory traffic, not by the DMMA pipe, so the efficiency of narrow tiles
+// falls in proportion to their width (a 16-column tile costs what a 32-column tile costs).
 #define SLM_SPARSE_SHAPES(X)      \
-    X(0, 8, 1, 2, 1, 3, 0.55)     \
-    X(1, 8, 1, 2, 2, 3, 0.70)     \
-    X(2, 8, 1, 2, 3, 3, 0.78)     \
-    X(3, 8, 1, 2, 4, 3, 0.84)     \
-    X(4, 8, 1, 2, 5, 3, 0.80)     \
-    X(5, 8, 1, 2, 6, 3, 0.79)     \
-    X(6, 8, 1, 2, 7, 2, 0.765)    \
+    X(0, 8, 1, 2, 1, 3, 0.18)     \
+    X(1, 8, 1, 2, 2, 3, 0.36)     \
+    X(2, 8, 1, 2, 3, 3, 0.54)     \
+    X(3, 8, 1, 2, 4, 3, 0.72)     \
+    X(4, 8, 1, 2, 5, 3, 0.76)     \
+    X(5, 8, 1, 2, 6, 3, 0.78)     \
+    X(6, 8, 1, 2, 7, 2, 0.78)     \
     X(7, 4, 2, 4, 4, 2, 0.78)     \
-    X(8, 16, 1, 1, 9, 1, 0.775)   \
-    X(9, 16, 1, 1, 11, 1, 0.775)  \
-    X(10, 16, 1, 1, 13, 1, 0.776) \
-    X(11, 2, 4, 8, 4, 1, 0.76)
+    X(8, 16, 1, 1, 9, 1, 0.82)    \
+    X(9, 16, 1, 1, 11, 1, 0.86)   \
+    X(10, 16, 1, 1, 13, 1, 0.90)  \
+    X(11, 2, 4, 8, 4, 1, 0.76)    \
+    X(12, 8, 1, 2, 13, 1, 0.88)   \
+    X(13, 8, 1, 2, 8, 2, 0.78)
 static const Shape kSparseShapes[] = {
 #define X(id, wm, wn, mi, ni, minb, eff) {wm * mi * 8, wn * ni * 8, minb, eff},
     SLM_SPARSE_SHAPES(X)
@@ -354,7 +370,9 @@ static const Shape kSparseShapes[] = {
 };
 constexpr int kNumSparseShapes = sizeof(kSparseShapes) / sizeof(Shape);
 static cudaError_t launch_sparse_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaStream_t s) {
-    if (id < 12 && tma_prepare(ctx, b, 4)) {
+    // tiles of <= 16 columns run a few microseconds per launch: the cp.async kernel starts faster there
+    // (no barrier ring / register re-allocation / descriptor fetch), measured in tools/gemm_probe.py
+    if (kSparseShapes[id].bn > 16 && tma_prepare(ctx, b, 4)) {
         switch (id) {
 #define X(id_, wm, wn, mi, ni, minb, eff) \
     case id_: return launch_gemm_tma_t<wm, wn, mi, ni, false, minb, true, kBK, (minb >= 3 ? 3 : kStages)>(ctx, b, s);
@@ -367,9 +385,6 @@ static cudaError_t launch_sparse_shape(slm_ctx* ctx, int id, GemmBatch& b, cudaS
     case id_: return launch_gemm_t<wm, wn, mi, ni, false, false, minb, true, kBK, (minb >= 3 ? 3 : kStages)>(ctx, b, s);
         SLM_SPARSE_SHAPES(X)
 #undef X
-        // experimental 128x32 variants (SLM_FORCE_SPARSE_SHAPE only)
-        case 12: return launch_gemm_t<8, 1, 2, 4, false, false, 2, true>(ctx, b, s);
-        case 13: return launch_gemm_t<8, 1, 2, 4, false, false, 4, true, 16, 2>(ctx, b, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -955,6 +970,12 @@ int slm_set_option(slm_ctx* ctx, const char* name, int value) {
         ctx->chunk_w = std::max(8, value / 8 * 8);
     else if (nm == "tma")
         ctx->tma_mask = value;
+    else if (nm == "force_apply_shape")
+        ctx->force_apply_shape = value;
+    else if (nm == "force_sparse_shape")
+        ctx->force_sparse_shape = value;
+    else if (nm == "force_syrk_shape")
+        ctx->force_syrk_shape = value;
     else
         return fail(ctx, 1, "slm_set_option: unknown option " + nm);
     return 0;

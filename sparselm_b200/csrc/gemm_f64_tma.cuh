@@ -23,6 +23,14 @@
 // (row & 7) in {0,2,4,6} or {1,3,5,7}: the XOR then maps the two chunks a half-warp touches per
 // row to four disjoint chunk pairs -- 16 distinct 8-byte banks, conflict-free without padding.
 //
+// WIDE layout (template flag): one TMA operation moves a tile row band of BM+4 (BN+4) doubles
+// WITHOUT swizzle -- rows of (BM+4)*8 bytes, a pitch that is 32 (or 96) mod 128 bytes, so the four k rows of
+// a fragment fall on four different 32-byte bank groups (the same padded layout as the cp.async kernel,
+// written by the TMA unit).  A k-slab then takes 2 operations (tiled) or 2 per four gathered rows instead
+// of one per 128-byte box: the row-sparse apply at 32-column tiles issued 40 gather operations of 512 bytes
+// per slab and ran at the TMA unit's operation rate (about one per 46 cycles per SM = 3.1 TB/s), not at the
+// DMMA rate.
+//
 // Tails.  Rows of the last k-slab beyond the contraction length are not masked by the copy
 // (dense: they are the next rows of the matrix or zero-filled out-of-bounds rows; gather: the
 // list is padded with its last index): the consumers zero both fragments of those rows.  Columns
@@ -80,7 +88,7 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
 }
 constexpr int kTmaBoxCols = 16;  // doubles per box row = 128 bytes (the swizzle span)
 
-template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES>
+template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool WIDE>
 struct TmaCfg {
     static constexpr int BM = WARPS_M * MI * 8;
     static constexpr int BN = WARPS_N * NI * 8;
@@ -90,25 +98,31 @@ struct TmaCfg {
     // cost the same registers.  Only the first warp of the group issues copies.
     static constexpr int NT = (NCW + 4) * 32;
     static_assert(NCW % 4 == 0, "consumer warps come in groups of four (setmaxnreg)");
+    // swizzled layout: boxes of [BK][16 doubles]
     static constexpr int ABOX = BM / kTmaBoxCols;
     static constexpr int BBOX = (BN + kTmaBoxCols - 1) / kTmaBoxCols;
     static constexpr int BOXB = BK * 128;                // bytes per box
-    static constexpr int A_BYTES = ABOX * BOXB;
-    static constexpr int STAGE_BYTES = (ABOX + BBOX) * BOXB;
+    // wide layout: one band of BM+4 / BN+4 doubles per row
+    static constexpr int A_COLS = WIDE ? BM + 4 : kTmaBoxCols;  // box width of the P map (doubles)
+    static constexpr int B_COLS = WIDE ? BN + 4 : kTmaBoxCols;
+    static constexpr int A_PITCH = (BM + 4) * 8, B_PITCH = (BN + 4) * 8;  // bytes (WIDE)
+    static constexpr int A_BYTES = WIDE ? BK * A_PITCH : ABOX * BOXB;
+    static constexpr int STAGE_BYTES = WIDE ? BK * (A_PITCH + B_PITCH) : (ABOX + BBOX) * BOXB;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2 * STAGES * 8 + 64;
     static_assert(BM % kTmaBoxCols == 0, "the M tile must be whole boxes");
     static_assert(BK % 8 == 0, "slabs are groups of 8 rows (swizzle period)");
+    static_assert(A_BYTES % 128 == 0 && STAGE_BYTES % 128 == 0, "TMA destinations are 128-byte aligned");
 };
 
 // A operand K-major only (Gram build, Gram apply).  SYM / KSPARSE as in gemm_f64_kernel.
 // mapP / mapQ: 2-D tensor maps over the whole operand matrices (P: [rows][ldp], Q: [rows][ldq]),
 // box [BK][16] for the tiled mode, [1][16] for the gather mode.  A problem addresses its rows
 // through prow0 / qrow0 and its Q columns through qcol0.
-template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool SYM, int MINB, bool KSPARSE>
+template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool SYM, int MINB, bool KSPARSE, bool WIDE>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ GemmBatch batch, const __grid_constant__ CUtensorMap mapP,
                         const __grid_constant__ CUtensorMap mapQ) {
-    using Cfg = TmaCfg<WARPS_M, WARPS_N, MI, NI, BK, STAGES>;
+    using Cfg = TmaCfg<WARPS_M, WARPS_N, MI, NI, BK, STAGES, WIDE>;
     constexpr int BM = Cfg::BM, BN = Cfg::BN, NCW = Cfg::NCW;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t tiles0 = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 1024-byte aligned: swizzle atoms
@@ -238,7 +252,11 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
                 if (lane == 0) mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES);
                 __syncwarp();
                 const int k0 = kt * BK;
-                if (!KSPARSE) {
+                if (!KSPARSE && WIDE) {
+                    // one operation per operand: the whole [BK][BM+4] / [BK][BN+4] band of the slab
+                    if (lane == 0) tma_load_2d(sA, &mapP, m0, prow0 + k0, fb);
+                    if (lane == 1) tma_load_2d(sB, &mapQ, n0, qrow0 + k0, fb);
+                } else if (!KSPARSE) {
                     // one box per lane round: boxes 0..ABOX-1 of A, then BBOX boxes of B
                     for (int b = lane; b < Cfg::ABOX + Cfg::BBOX; b += 32) {
                         if (b < Cfg::ABOX)
@@ -257,6 +275,24 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
                         myidx = kk >= 0 ? __ldg(kidx + kk) : 0;
                     }
                     constexpr int QUADS = BK / 4;
+                    if (WIDE) {
+                        // lane 2q gathers rows 4q..4q+3 of the A band, lane 2q+1 those of the B band
+                        const int oq = min(lane >> 1, QUADS - 1);
+                        const int r0 = __shfl_sync(0xffffffffu, myidx, 4 * oq + 0);
+                        const int r1 = __shfl_sync(0xffffffffu, myidx, 4 * oq + 1);
+                        const int r2 = __shfl_sync(0xffffffffu, myidx, 4 * oq + 2);
+                        const int r3 = __shfl_sync(0xffffffffu, myidx, 4 * oq + 3);
+                        if (lane < 2 * QUADS) {
+                            if ((lane & 1) == 0)
+                                tma_gather4(sA + (uint32_t)oq * 4u * Cfg::A_PITCH, &mapP, m0, prow0 + r0, prow0 + r1,
+                                            prow0 + r2, prow0 + r3, fb);
+                            else
+                                tma_gather4(sB + (uint32_t)oq * 4u * Cfg::B_PITCH, &mapQ, n0, qrow0 + r0, qrow0 + r1,
+                                            qrow0 + r2, qrow0 + r3, fb);
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     constexpr int OPS = QUADS * (Cfg::ABOX + Cfg::BBOX);
 #pragma unroll 1
                     for (int o0 = 0; o0 < OPS; o0 += 32) {
@@ -338,7 +374,46 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             const uint8_t* sbase = tiles_ptr + (size_t)stage * Cfg::STAGE_BYTES;
             const int kd_rem = sg.Kd - kt * BK;  // valid rows of this slab (>= BK: all)
             mbar_wait(full_bar(stage), phase);
-            if (kd_rem >= BK) {
+            if (WIDE) {
+                // padded-pitch layout: element (k, x) of a band at k * PITCH + 8 x, natural k order
+                const double* As = reinterpret_cast<const double*>(sbase);
+                const double* Bs = reinterpret_cast<const double*>(sbase + Cfg::A_BYTES);
+                constexpr int A_LD = BM + 4, B_LD = BN + 4;
+                if (kd_rem >= BK) {
+#pragma unroll
+                    for (int s = 0; s < BK / 4; ++s) {
+                        double a[MI], b[NI];
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) a[i] = As[(s * 4 + lk) * A_LD + (wm * MI + i) * 8 + lx];
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) b[j] = Bs[(s * 4 + lk) * B_LD + (wn * NI + j) * 8 + lx];
+#pragma unroll
+                        for (int i = 0; i < MI; ++i)
+#pragma unroll
+                            for (int j = 0; j < NI; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int s = 0; s < BK / 4; ++s) {
+                        const bool ok = s * 4 + lk < kd_rem;
+                        double a[MI], b[NI];
+#pragma unroll
+                        for (int i = 0; i < MI; ++i) {
+                            const double v = As[(s * 4 + lk) * A_LD + (wm * MI + i) * 8 + lx];
+                            a[i] = ok ? v : 0.0;
+                        }
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) {
+                            const double v = Bs[(s * 4 + lk) * B_LD + (wn * NI + j) * 8 + lx];
+                            b[j] = ok ? v : 0.0;
+                        }
+#pragma unroll
+                        for (int i = 0; i < MI; ++i)
+#pragma unroll
+                            for (int j = 0; j < NI; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                }
+            } else if (kd_rem >= BK) {
 #pragma unroll
                 for (int s = 0; s < BK / 4; ++s) {
                     const uint8_t* so = sbase + (s >> 1) * 1024 + (s & 1) * 128;

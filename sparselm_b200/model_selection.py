@@ -574,6 +574,8 @@ class LineSearchCV(BaseSearchCV):
                               verbose=self.verbose, pre_dispatch=self.pre_dispatch, error_score=self.error_score,
                               return_train_score=self.return_train_score)
             gs._fd_cache = fd_cache
+            if getattr(self, "_shard", None) is not None:
+                gs._shard = self._shard
             if groups is not None:
                 fit_params = dict(fit_params, groups=groups)
             gs.fit(X, y, **fit_params)

@@ -40,8 +40,12 @@ def test_tma_box_and_gather4_layout(engine, col0, row0, rows4):
     np.testing.assert_array_equal(out[256:].reshape(4, 16), _expected_image(Ah, col0, list(rows4)))
 
 
+LAYOUTS = [7, 31]  # 128-byte swizzled boxes / wide padded-pitch bands (bits 3, 4 of the "tma" option)
+
+
+@pytest.mark.parametrize("mask", LAYOUTS)
 @pytest.mark.parametrize("n,p,F", [(37, 5, 1), (300, 81, 3), (1000, 250, 5), (513, 130, 4), (2050, 300, 2)])
-def test_tma_gram_build(tma_switch, n, p, F):
+def test_tma_gram_build(tma_switch, n, p, F, mask):
     import torch
 
     eng = tma_switch
@@ -52,7 +56,7 @@ def test_tma_gram_build(tma_switch, n, p, F):
     eng.set_option("tma", 0)
     G0 = eng.gram_blocks(Xa, row_ptr)
     c0 = eng.tma_launch_count()
-    eng.set_option("tma", 7)
+    eng.set_option("tma", mask)
     G1 = eng.gram_blocks(Xa, row_ptr)
     assert eng.tma_launch_count() > c0, "the TMA kernel did not run"
     Xh = Xa.cpu().numpy()
@@ -68,11 +72,13 @@ def test_tma_gram_build(tma_switch, n, p, F):
     assert (Gacc - 2 * G1[0]).abs().max().item() <= 1e-12 * G1[0].abs().max().item()
 
 
+@pytest.mark.parametrize("mask", LAYOUTS)
 @pytest.mark.parametrize("p,Ks", [(80, [1]), (80, [10, 7]), (515, [100, 100, 100]), (1030, [33]), (300, [64, 0, 9])])
-def test_tma_dense_apply(tma_switch, p, Ks):
+def test_tma_dense_apply(tma_switch, p, Ks, mask):
     import torch
 
     eng = tma_switch
+    eng.set_option("tma", mask)
     F = len(Ks)
     pa = eng.padded_cols(p)
     g = torch.Generator(device="cpu").manual_seed(p)
@@ -92,10 +98,12 @@ def test_tma_dense_apply(tma_switch, p, Ks):
 
 @pytest.mark.parametrize("p,Ks,chunk_w,density", [(515, [100, 64], 32, 0.3), (300, [40], 8, 0.05), (1030, [33, 33, 8], 16, 0.6),
                                                   (200, [24], 32, 0.0), (257, [16, 72], 32, 1.0)])
-def test_tma_rowsparse_apply(tma_switch, p, Ks, chunk_w, density):
+@pytest.mark.parametrize("mask", LAYOUTS)
+def test_tma_rowsparse_apply(tma_switch, p, Ks, chunk_w, density, mask):
     import torch
 
     eng = tma_switch
+    eng.set_option("tma", mask)
     F = len(Ks)
     pa = eng.padded_cols(p)
     g = torch.Generator(device="cpu").manual_seed(p + 1)
@@ -107,7 +115,8 @@ def test_tma_rowsparse_apply(tma_switch, p, Ks, chunk_w, density):
     Z = (Z * keep).to(eng.device)
     c0 = eng.tma_launch_count()
     GZ = eng.gram_apply_rowsparse(G, p, Ks, Z, chunk_w=chunk_w)
-    assert eng.tma_launch_count() > c0
+    if chunk_w > 16 and max(Ks) > 16:  # tiles of <= 16 columns stay on the cp.async kernel (faster start)
+        assert eng.tma_launch_count() > c0
     eng.set_option("tma", 0)
     GZ0 = eng.gram_apply_rowsparse(G, p, Ks, Z, chunk_w=chunk_w)
     for f in range(F):
@@ -115,6 +124,28 @@ def test_tma_rowsparse_apply(tma_switch, p, Ks, chunk_w, density):
         tol = 1e-12 * max(ref.abs().max().item(), 1e-300)
         assert (GZ[f, :, :Ks[f]] - ref).abs().max().item() <= tol
         assert (GZ[f, :, :Ks[f]] - GZ0[f, :, :Ks[f]]).abs().max().item() <= tol
+
+
+def test_solver_on_tma_kernels_agrees_with_cp_async_kernels(tma_switch):
+    """A whole CV search (dense cold-start phase, row-sparse middle, tail) with the TMA-fed kernels
+    against the same search on the cp.async kernels."""
+    from sparselm_b200.model import Lasso
+    from sparselm_b200.model_selection import GridSearchCV
+
+    rng = np.random.default_rng(12)
+    n, p = 600, 400
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) + rng.standard_normal(n)     # dense truth: dense iterates
+    alphas = np.abs(X.T @ y).max() / n * np.logspace(-2.0, -4.0, 40)
+    eng = tma_switch
+    out = []
+    for mask in (15, 0):
+        eng.set_option("tma", mask)
+        gs = GridSearchCV(Lasso(solver_options={"tol": 1e-11}), {"alpha": list(alphas)}, cv=3).fit(X, y)
+        assert gs.batched_ and (gs.solver_info_["status"] == 0).all()
+        out.append((gs.cv_results_["mean_test_score"].copy(), gs.best_estimator_.coef_.copy()))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-8)
+    assert np.abs(out[0][1] - out[1][1]).max() <= 1e-7 * np.abs(out[1][1]).max()
 
 
 def test_tma_results_are_reproducible(tma_switch):
