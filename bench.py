@@ -789,11 +789,14 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
                 "traffic": traffic, "traffic_source": traffic_src, "gram_build_tflops": build_tf,
                 "step_ms_by_kernel_family": step_ms}
     nw = res.get("newton") or {}
-    if nw.get("factorizations"):  # second-order phase of the last timed step (library Cholesky, sparselm_b200/newton.py)
+    if nw.get("factorizations"):  # second-order phase of the last timed step (csrc/newton_kernels.cuh)
+        torch_model = os.environ.get("SLM_NEWTON_TORCH", "0") == "1"
         roof["newton_phase"] = {"ms_per_step": float(nw["ms"]), "factorizations_per_step": int(nw["factorizations"]),
                                 "phases_per_step": int(nw["phases"]),
-                                "note": "lock-step Newton steps on the active groups of the slow columns: batched cuSOLVER "
-                                        "potrf through torch.linalg, not one of this repo's kernels and not in gpu_launches"}
+                                "note": ("SLM_NEWTON_TORCH=1: the torch / cuSOLVER model of the phase (A/B run)" if torch_model else
+                                         "lock-step Newton steps on the active groups of the slow columns, this repo's kernels: "
+                                         "Hessian assembly from the Gram, batched blocked Cholesky with tensor-core trailing "
+                                         "updates, blocked triangular solves, device-side line search (slm_newton_step)")}
     line = {
         "metric": "cv_grid_fits_per_sec", "value": value, "unit": "fits/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",

@@ -100,6 +100,29 @@ int slm_tri_pack(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa
 int slm_tri_unpack(slm_ctx* ctx, const double* buf_dev, int64_t pa, int n_grams, double* G_dev,
                    int64_t g_stride, void* stream);
 
+/* slm_tri_complement: the reduced packed buffer buf_dev[n_blocks][slm_tri_size(pa)] -> the n_blocks
+ * training Grams (sum of the other blocks) followed by the total in G_dev[n_blocks + 1][pa][pa] (full
+ * symmetric matrices): slm_tri_unpack + slm_gram_complement in one pass.
+ *
+ * Collectives of the sharded search on the CALLER's NCCL communicator (an ncclComm_t passed as void*; the
+ * reference side gets it from its process group, e.g. torch.distributed's ProcessGroupNCCL._comm_ptr()).
+ * The library does not link NCCL: it uses the NCCL already loaded in the process, so communicator and
+ * entry points match.  All are enqueued on `stream`; NCCL's usual rule applies (every rank issues the same
+ * collectives in the same order).
+ *   slm_gram_allreduce: this rank's partial fold blocks G_dev[n_blocks][pa][pa] -> training Grams + total
+ *       of all ranks in G_dev[n_blocks + 1][pa][pa] (pack upper triangles, ONE ncclAllReduce, unpack +
+ *       complement); buf_dev holds n_blocks * slm_tri_size(pa) doubles; nccl_comm NULL = single rank.
+ *   slm_allreduce_sum: in-place sum of count doubles (the zero-padded CV score / info tables).
+ *   slm_gather_results: ncclAllGather of count_per_rank doubles per rank (coefficients + intercepts of the
+ *       columns a rank solved) so that every rank can score its rows of every test fold. */
+int slm_tri_complement(slm_ctx* ctx, const double* buf_dev, int64_t pa, int n_blocks, double* G_dev,
+                       int64_t g_stride, void* stream);
+int slm_gram_allreduce(slm_ctx* ctx, void* nccl_comm, double* G_dev, int64_t g_stride, int64_t pa,
+                       int n_blocks, double* buf_dev, void* stream);
+int slm_allreduce_sum(slm_ctx* ctx, void* nccl_comm, double* buf_dev, int64_t count, void* stream);
+int slm_gather_results(slm_ctx* ctx, void* nccl_comm, const double* send_dev, double* recv_dev,
+                       int64_t count_per_rank, void* stream);
+
 /* Diagnostic of the TMA path (gemm_f64_tma.cuh): loads the [16 rows][16 doubles] box at (row0, col0) of
  * the row-major device matrix A_dev[rows][ld] with a tiled tensor map and the four rows r[0..3] at col0
  * with a tile::gather4 map (both 128-byte swizzled) and writes the raw shared-memory images to
@@ -214,16 +237,35 @@ int slm_intercepts(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,
                    const double* B_dev, int64_t ldz, int32_t K, double* intercept_dev,
                    void* stream);
 
+/* Second-order phase of the batched solve (pure group penalties): ONE
+ * lock-step damped Newton step on the active groups of k columns, in this library's kernels --
+ * Hessian assembly from the Gram, batched blocked Cholesky (trailing updates on the tensor-core
+ * GEMM), blocked triangular solves, Armijo line search on objective differences.
+ * Column c works on Gram fold_host[c] with nobs_dev[c] rows; X_dev [k][ldv] (ldv = round_up(p, 8))
+ * holds its point in solver feature order and is updated in place when a step is accepted;
+ * W2_dev / D2_dev [k][n_groups] are its group and ridge weights (D2_dev may be NULL); gptr_dev
+ * [n_groups+1], gid_dev [p] describe the groups.  out_dev [k][4] = {accepted, step length,
+ * Newton decrement -grad'd, factorisation failed}.  Only enqueues work on the stream. */
+size_t slm_newton_workspace(int64_t p, int32_t n_groups, int32_t k, int n_folds);
+int slm_newton_step(slm_ctx* ctx, const double* G_dev, int64_t g_stride, int64_t pa, int64_t p, int n_folds,
+                    int32_t k, const int32_t* fold_host, const double* nobs_dev, double* X_dev,
+                    const double* W2_dev, const double* D2_dev, const int32_t* gptr_dev, const int32_t* gid_dev,
+                    int32_t n_groups, void* work_dev, size_t work_bytes, double* out_dev, void* stream);
+
 /* Unpenalised least squares on a Gram (OrdinaryLeastSquares, reference model/_ols.py:57-65:
  * argmin 1/(2n) ||X b - y||^2): conjugate gradients on G b = c, c = row p of the Gram, every
  * product G d through the tensor-core apply.  From b = 0 the iterates stay in range(G), so a
  * rank-deficient (p > n) consistent system converges to its minimum-norm solution.  Stops on
  * ||c - G b|| <= tol ||c|| (checked against the recomputed residual) or after max_iter products.
  * X8_dev: [p][8] out, the solution is column 0 (stride 8: the layout slm_intercepts and
- * slm_cv_score take with ldz = 8).  iters_host / relres_host may be NULL.  Synchronises. */
+ * slm_cv_score take with ldz = 8).  iters_host / relres_host may be NULL.  Synchronises.
+ * shift_dev (may be NULL): p non-negative numbers added to the diagonal of G -- the ridge
+ * n * delta_g(j) of a penalised estimator called with alpha = 0 (valid in the reference,
+ * _lasso.py:77-79: the interval is closed at 0), whose columns the host routes here because the
+ * duality-gap test of the proximal iterations degenerates without a penalty. */
 size_t slm_gram_cg_workspace(int64_t p);
-int slm_gram_cg(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p, double tol,
-                int32_t max_iter, void* work_dev, size_t work_bytes, double* X8_dev,
+int slm_gram_cg(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p, const double* shift_dev,
+                double tol, int32_t max_iter, void* work_dev, size_t work_bytes, double* X8_dev,
                 int32_t* iters_host, double* relres_host, void* stream);
 
 /* plain batched tensor-core apply GZ_f = G_f Z_f (exposed for tests / roofline runs) */

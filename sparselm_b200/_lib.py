@@ -78,6 +78,10 @@ SYMBOLS = {
     "slm_tri_size": (c_i64, [c_i64]),
     "slm_tri_pack": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_vp]),
     "slm_tri_unpack": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp]),
+    "slm_tri_complement": (ctypes.c_int, [c_vp, c_vp, c_i64, ctypes.c_int, c_vp, c_i64, c_vp]),
+    "slm_gram_allreduce": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_vp]),
+    "slm_allreduce_sum": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "slm_gather_results": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "slm_tma_probe": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i32, c_i32, ctypes.POINTER(c_i32), c_vp, c_vp]),
     "slm_gram_center": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp]),
     "slm_gram_gather": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp]),
@@ -91,8 +95,11 @@ SYMBOLS = {
     "slm_cv_score": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "slm_intercepts": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "slm_gram_apply": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_i64, c_vp, c_vp]),
+    "slm_newton_workspace": (c_sz, [c_i64, c_i32, c_i32, ctypes.c_int]),
+    "slm_newton_step": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_i32, ctypes.POINTER(c_i32), c_vp, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_sz, c_vp, c_vp]),
     "slm_gram_cg_workspace": (c_sz, [c_i64]),
-    "slm_gram_cg": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_dbl, c_i32, c_vp, c_sz, c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp]),
+    "slm_gram_cg": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_vp, c_dbl, c_i32, c_vp, c_sz, c_vp, ctypes.POINTER(c_i32), ctypes.POINTER(c_dbl), c_vp]),
     "slm_rowsparse_workspace": (c_sz, [c_i64, c_i64, ctypes.c_int]),
     "slm_gram_apply_rowsparse": (ctypes.c_int, [c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.POINTER(c_i32), c_vp, c_i64, c_vp, ctypes.c_int, c_vp, c_sz, c_vp]),
     "slm_apply_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),

@@ -28,11 +28,12 @@ __device__ __forceinline__ double cg_block_sum(double v, double* red) {
     return t;
 }
 
-// r = c - G x (GX8 == NULL: x = 0, r = c), d = r
+// r = c - (G + diag(shift)) x (GX8 == NULL: x = 0, r = c), d = r.  shift (may be NULL): the ridge
+// n * delta_g(j) of an unpenalised ridged problem (alpha = 0, delta > 0).
 __global__ void __launch_bounds__(CG_T) cg_start_kernel(const double* __restrict__ G, long long pa, int p,
                                                         double* __restrict__ X8, const double* __restrict__ GX8,
-                                                        double* __restrict__ R, double* __restrict__ D8,
-                                                        double* __restrict__ sc) {
+                                                        const double* __restrict__ shift, double* __restrict__ R,
+                                                        double* __restrict__ D8, double* __restrict__ sc) {
     __shared__ double red[CG_T / 32];
     const double* __restrict__ c = G + (long long)p * pa;
     double rs = 0.0, cc = 0.0;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(CG_T) cg_start_kernel(const double* __restrict
         const double cj = c[j];
         double r = cj;
         if (GX8)
-            r -= GX8[(long long)j * 8];
+            r -= GX8[(long long)j * 8] + (shift ? shift[j] * X8[(long long)j * 8] : 0.0);
         else
             X8[(long long)j * 8] = 0.0;
         R[j] = r;
@@ -57,14 +58,17 @@ __global__ void __launch_bounds__(CG_T) cg_start_kernel(const double* __restrict
     }
 }
 
-// one CG step given GD8 = G d
+// one CG step given GD8 = G d (the operator is G + diag(shift))
 __global__ void __launch_bounds__(CG_T) cg_step_kernel(int p, double* __restrict__ X8, double* __restrict__ R,
                                                        double* __restrict__ D8, const double* __restrict__ GD8,
-                                                       double* __restrict__ sc) {
+                                                       const double* __restrict__ shift, double* __restrict__ sc) {
     __shared__ double red[CG_T / 32];
     const double rs = sc[0];
     double dgd = 0.0;
-    for (int j = threadIdx.x; j < p; j += CG_T) dgd += D8[(long long)j * 8] * GD8[(long long)j * 8];
+    for (int j = threadIdx.x; j < p; j += CG_T) {
+        const double d = D8[(long long)j * 8];
+        dgd += d * (GD8[(long long)j * 8] + (shift ? shift[j] * d : 0.0));
+    }
     dgd = cg_block_sum(dgd, red);
     // d in the null space of G (or r = 0): nothing left to gain along d
     const double a = (dgd > 0.0 && rs > 0.0) ? rs / dgd : 0.0;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(CG_T) cg_step_kernel(int p, double* __restrict
     for (int j = threadIdx.x; j < p; j += CG_T) {
         const long long e = (long long)j * 8;
         X8[e] += a * D8[e];
-        const double r = R[j] - a * GD8[e];
+        const double r = R[j] - a * (GD8[e] + (shift ? shift[j] * D8[e] : 0.0));
         R[j] = r;
         rsn += r * r;
     }

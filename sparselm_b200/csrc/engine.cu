@@ -29,6 +29,7 @@
 #include "whiten_kernels.cuh"
 #include "cg_kernels.cuh"
 #include "coop_kernels.cuh"
+#include "newton_kernels.cuh"
 
 using namespace slm;
 
@@ -618,6 +619,34 @@ __global__ void tri_unpack_kernel(const double* __restrict__ buf, long long b_st
     G[(long long)blockIdx.z * g_stride + i * pa + j] = v;
 }
 
+// packed upper triangles of the F fold blocks -> the F training Grams (sum of the OTHER blocks, fixed
+// order, no subtraction) and the total, full symmetric matrices: tri_unpack + gram_complement in one
+// pass over the reduced buffer (the sharded build's tail: 1.1 GB of traffic instead of 2.4 GB at C3)
+__global__ void tri_complement_kernel(const double* __restrict__ buf, long long b_stride, long long pa, int nb,
+                                      double* __restrict__ G, long long g_stride) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = blockIdx.y;
+    if (j >= pa || j < i) return;
+    const long long t = tri_off(i, pa) + (j - i);
+    double vals[SLM_MAX_FOLDS];
+    double tot = 0.0;
+    for (int f = 0; f < nb; ++f) {
+        vals[f] = buf[(long long)f * b_stride + t];
+        tot += vals[f];
+    }
+    for (int f = 0; f <= nb; ++f) {
+        double acc = tot;
+        if (f < nb) {
+            acc = 0.0;
+            for (int g = 0; g < nb; ++g)
+                if (g != f) acc += vals[g];
+        }
+        double* Gf = G + (long long)f * g_stride;
+        Gf[i * pa + j] = acc;
+        if (j != i) Gf[j * pa + i] = acc;
+    }
+}
+
 __global__ void gram_center_kernel(double* __restrict__ G, long long pa, int p) {
     // rows/cols 0..p (features and y); ones row p+1 kept intact
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1144,6 +1173,17 @@ int slm_tma_probe(slm_ctx* ctx, const double* A, int64_t rows, int64_t ld, int32
     return 0;
 }
 
+int slm_tri_complement(slm_ctx* ctx, const double* buf, int64_t pa, int n_blocks, double* G, int64_t g_stride,
+                       void* stream) {
+    if (!ctx || !G || !buf) return fail(ctx, 1, "slm_tri_complement: null argument");
+    if (n_blocks < 1 || n_blocks > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_tri_complement: n_blocks out of range");
+    if (pa <= 0) return 0;
+    dim3 grid((unsigned)((pa + 255) / 256), (unsigned)pa);
+    tri_complement_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(buf, slm_tri_size(pa), pa, n_blocks, G, g_stride);
+    LAUNCH_OK("tri_complement_kernel");
+    return 0;
+}
+
 int slm_gram_center(slm_ctx* ctx, double* G, int64_t pa, int64_t p, void* stream) {
     if (!ctx || !G) return fail(ctx, 1, "slm_gram_center: null argument");
     // NOTE: every thread reads the (unmodified) ones row; rows 0..p are updated
@@ -1173,8 +1213,9 @@ int slm_gram_apply(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, 
 // ---- unpenalised least squares: conjugate gradients on the Gram ------------------------
 size_t slm_gram_cg_workspace(int64_t p) { return (size_t)(3 * 8 * p + p + 8) * sizeof(double); }
 
-int slm_gram_cg(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, double tol, int32_t max_iter, void* work,
-                size_t work_bytes, double* X8, int32_t* iters_host, double* relres_host, void* stream) {
+int slm_gram_cg(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const double* shift, double tol,
+                int32_t max_iter, void* work, size_t work_bytes, double* X8, int32_t* iters_host,
+                double* relres_host, void* stream) {
     if (!ctx || !G || !work || !X8) return fail(ctx, 1, "slm_gram_cg: null argument");
     if (pa % 2 || pa < p + 1) return fail(ctx, 1, "slm_gram_cg: pa must be even and hold the X^T y row");
     if (work_bytes < slm_gram_cg_workspace(p)) return fail(ctx, 1, "slm_gram_cg: workspace too small");
@@ -1188,7 +1229,7 @@ int slm_gram_cg(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, double tol
     const int32_t K1 = 1;
     CUDA_OK(cudaMemsetAsync(work, 0, slm_gram_cg_workspace(p), s));
     CUDA_OK(cudaMemsetAsync(X8, 0, sizeof(double) * 8 * (size_t)p, s));
-    cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, nullptr, R, D8, sc);
+    cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, nullptr, shift, R, D8, sc);
     LAUNCH_OK("cg_start_kernel");
     auto scalars = [&]() -> int {  // sc -> host
         CUDA_OK(cudaMemcpyAsync(ctx->h_scal, sc, sizeof(double) * 3, cudaMemcpyDeviceToHost, s));
@@ -1213,14 +1254,14 @@ int slm_gram_cg(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, double tol
             }
             int rc = apply_batched(ctx, G, pa * pa, pa, p, 1, &K1, D8, 8, GD8, s, -1.0, FAM_LIPS);
             if (rc) return rc;
-            cg_step_kernel<<<1, CG_T, 0, s>>>((int)p, X8, R, D8, GD8, sc);
+            cg_step_kernel<<<1, CG_T, 0, s>>>((int)p, X8, R, D8, GD8, shift, sc);
             LAUNCH_OK("cg_step_kernel");
         }
         // the recurrence drifts from the true residual: recompute c - G x and, if it is not
         // there yet, restart the recurrence from x (residual replacement)
         int rc = apply_batched(ctx, G, pa * pa, pa, p, 1, &K1, X8, 8, GX8, s, -1.0, FAM_LIPS);
         if (rc) return rc;
-        cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, GX8, R, D8, sc);
+        cg_start_kernel<<<1, CG_T, 0, s>>>(G, pa, (int)p, X8, GX8, shift, R, D8, sc);
         LAUNCH_OK("cg_start_kernel");
         if (int rc2 = scalars()) return rc2;
         rel = ctx->h_scal[1] > 0.0 ? sqrt(ctx->h_scal[0] / ctx->h_scal[1]) : 0.0;
@@ -1804,6 +1845,137 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     return 0;
 }
 
+
+// ---- second-order phase: one lock-step Newton step of k columns (newton_kernels.cuh) ------------
+static inline int64_t nw_ldh(int64_t p) { return round_up(p, 8); }
+static inline int nw_panels(int64_t p) { return (int)((p + NW_NB - 1) / NW_NB); }
+
+size_t slm_newton_workspace(int64_t p, int32_t n_groups, int32_t k, int n_folds) {
+    const size_t ldh = (size_t)nw_ldh(p), kk = (size_t)k;
+    const size_t ldz = (size_t)round_up(k, 8);
+    size_t d = kk * ldh * ldh;                          // H
+    d += kk * (size_t)nw_panels(p) * NW_NB * NW_NB;     // inverses of the diagonal blocks
+    d += 2 * kk * NW_NB * ldh;                          // panel, transposed (+ negated): GEMM operands
+    d += 6 * kk * ldh;                                  // U, KK, DP, GS, GRAD, DIR
+    d += (size_t)round_up((int64_t)(kk * (size_t)n_groups), 2);  // NRM (even: what follows stays 16-byte aligned)
+    d += 2 * (size_t)n_folds * (size_t)p * ldz;         // Z, GZ of the Gram apply
+    return d * sizeof(double) + (3 * kk + 64) * sizeof(int) + 256;
+}
+
+int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_folds,
+                    int32_t k, const int32_t* fold_host, const double* nobs_dev, double* X, const double* W2,
+                    const double* D2, const int32_t* gptr, const int32_t* gid, int32_t n_groups, void* work,
+                    size_t work_bytes, double* out, void* stream) {
+    if (!ctx || !G || !fold_host || !nobs_dev || !X || !W2 || !gptr || !gid || !work || !out)
+        return fail(ctx, 1, "slm_newton_step: null argument");
+    if (k <= 0) return 0;
+    if (n_folds < 1 || n_folds > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_newton_step: n_folds out of range");
+    if (work_bytes < slm_newton_workspace(p, n_groups, k, n_folds))
+        return fail(ctx, 1, "slm_newton_step: workspace too small");
+    if (n_groups > 6000) return fail(ctx, 1, "slm_newton_step: too many groups for the line-search kernel");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ldh = nw_ldh(p), ldv = ldh, ldz = round_up(k, 8);
+    const int npan = nw_panels(p);
+    double* H = (double*)work;
+    double* INV = H + (size_t)k * ldh * ldh;
+    double* PT = INV + (size_t)k * npan * NW_NB * NW_NB;
+    double* NPT = PT + (size_t)k * NW_NB * ldh;
+    double* U = NPT + (size_t)k * NW_NB * ldh;
+    double* KK = U + (size_t)k * ldv;
+    double* DP = KK + (size_t)k * ldv;
+    double* GS = DP + (size_t)k * ldv;
+    double* GRAD = GS + (size_t)k * ldv;
+    double* DIR = GRAD + (size_t)k * ldv;
+    double* NRM = DIR + (size_t)k * ldv;
+    double* Z = NRM + (size_t)round_up((int64_t)k * n_groups, 2);
+    double* GZ = Z + (size_t)n_folds * p * ldz;
+    int* fold_dev = (int*)(GZ + (size_t)n_folds * p * ldz);
+    int* slot_dev = fold_dev + k;
+    int* info = slot_dev + k;
+
+    // columns of a fold take consecutive slots of that fold's block in the apply layout
+    std::vector<int32_t> fs(2 * (size_t)k), Kf(n_folds, 0);
+    for (int c = 0; c < k; ++c) {
+        const int f = fold_host[c];
+        if (f < 0 || f >= n_folds) return fail(ctx, 1, "slm_newton_step: fold index out of range");
+        fs[c] = f;
+        fs[k + c] = Kf[f]++;
+    }
+    CUDA_OK(cudaMemcpyAsync(fold_dev, fs.data(), sizeof(int32_t) * 2 * (size_t)k, cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)k, s));
+    CUDA_OK(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)n_folds * p * ldz, s));
+    CUDA_OK(cudaMemsetAsync(PT, 0, sizeof(double) * 2 * (size_t)k * NW_NB * ldh, s));
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_OK(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NW_TILE_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NW_TILE_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(newton_linesearch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+        attr_done = true;
+    }
+    const dim3 vgrid((unsigned)((p + NW_T - 1) / NW_T), (unsigned)k);
+    newton_prepare_kernel<<<k, NW_T, 0, s>>>((int)p, n_groups, gptr, X, ldv, W2, D2, NRM, U, KK, DP);
+    newton_pack_kernel<<<vgrid, NW_T, 0, s>>>((int)p, fold_dev, slot_dev, X, ldv, Z, ldz);
+    LAUNCH_OK("newton prepare/pack kernels");
+    if (int rc = apply_batched(ctx, G, g_stride, pa, p, n_folds, Kf.data(), Z, ldz, GZ, s, -1.0, FAM_LIPS)) return rc;
+    newton_grad_kernel<<<vgrid, NW_T, 0, s>>>((int)p, G, g_stride, pa, fold_dev, slot_dev, nobs_dev, X, GZ, ldz, ldv, KK,
+                                              DP, GS, GRAD);
+    const dim3 hgrid((unsigned)((ldh + NW_T - 1) / NW_T), (unsigned)ldh, (unsigned)k);
+    newton_hessian_kernel<<<hgrid, NW_T, 0, s>>>((int)p, G, g_stride, pa, fold_dev, nobs_dev, gid, U, KK, DP, ldv, H, ldh);
+    LAUNCH_OK("newton grad/hessian kernels");
+    ctx->launches += 3;
+
+    // blocked Cholesky, all k matrices in lock step
+    for (int pn = 0; pn < npan; ++pn) {
+        const int j0 = pn * NW_NB, nb = (int)std::min<int64_t>(NW_NB, p - j0);
+        chol_diag_kernel<<<k, NW_T, NW_TILE_SMEM, s>>>(H, ldh, j0, nb, INV, npan, pn, info);
+        LAUNCH_OK("chol_diag_kernel");
+        const int64_t rows = p - j0 - nb;
+        if (rows <= 0) break;
+        const dim3 pgrid((unsigned)((rows + NW_NB - 1) / NW_NB), (unsigned)k);
+        chol_panel_kernel<<<pgrid, NW_T, NW_TILE_SMEM, s>>>(H, ldh, (int)p, j0, nb, INV, npan, pn, PT, NPT, ldh);
+        LAUNCH_OK("chol_panel_kernel");
+        // trailing update H22 -= L21 L21' on the tensor-core GEMM: C += (-L21')' (L21')
+        for (int c0 = 0; c0 < k; c0 += kMaxGemmProblems) {
+            const int nc = std::min<int>(k - c0, kMaxGemmProblems);
+            GemmBatch b;
+            memset(&b, 0, sizeof(b));
+            b.n_problems = nc;
+            b.accumulate = 1;
+            for (int i = 0; i < nc; ++i) {
+                const int64_t c = c0 + i, off = j0 + nb;
+                GemmProblem& pr = b.pr[i];
+                pr.P = NPT + c * NW_NB * ldh + off;
+                pr.Q = PT + c * NW_NB * ldh + off;
+                pr.C = H + c * ldh * ldh + off * ldh + off;
+                pr.ldp = pr.ldq = ldh;
+                pr.ldc = ldh;
+                pr.qlim = (int)(ldh - off);
+                pr.M = pr.N = (int)round_up(rows, 2);  // an odd tail adds the (zero) padding row / column
+                pr.Kd = nb;
+            }
+            FamTimer tm(ctx, FAM_LIPS, s, 0.0);
+            cudaError_t e = launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
+            if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("newton trailing update: ") + cudaGetErrorString(e));
+            ctx->launches++;
+        }
+    }
+    const size_t solve_smem = sizeof(double) * ((size_t)ldh + NW_NB + (NW_T / 32) * NW_NB);
+    if (solve_smem > 98304 || 2 * sizeof(double) * (size_t)n_groups > 98304)
+        return fail(ctx, 1, "slm_newton_step: design too large for the solve / line-search kernels");
+    static bool attr2 = false;
+    if (!attr2) {
+        CUDA_OK(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
+        attr2 = true;
+    }
+    chol_solve_kernel<<<k, NW_T, solve_smem, s>>>(H, ldh, (int)p, INV, npan, GRAD, DIR, ldv);
+    newton_linesearch_kernel<<<k, NW_T, 2 * sizeof(double) * (size_t)n_groups, s>>>(
+        (int)p, n_groups, gptr, X, DIR, GS, GRAD, U, KK, DP, ldv, W2, NRM, info, out);
+    LAUNCH_OK("newton solve / line-search kernels");
+    ctx->launches += 1;
+    return 0;
+}
+
 int slm_adaptive_update(slm_ctx* ctx, const double* B, int64_t p, int64_t ldz, int32_t K, int32_t n_groups,
                         const int32_t* gptr, const double* gw, const double* a1, const double* a2,
                         const double* alpha, double eps, double* W1, double* W2, double* dnorm,
@@ -1917,3 +2089,67 @@ int slm_coef_unwhiten(slm_ctx* ctx, const double* Bg, int64_t p, int64_t ldz, in
 }
 
 }  // extern "C"
+
+// ---- collectives of the sharded search on the caller's NCCL communicator -------------------------------
+// SURVEY 8b / north_star: "X row-sharded, partial Grams combined with an NCCL all-reduce", "NCCL all-gather
+// of CV scores and coefficients".  The library does not link against NCCL: the entry points are looked up in
+// the process (the host already loaded the NCCL its communicator belongs to -- torch's bundled one when the
+// communicator comes from torch.distributed), so communicator and functions always match.
+#include <dlfcn.h>
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*NcclAllGatherFn)(const void*, void*, size_t, int, void*, cudaStream_t);
+typedef const char* (*NcclErrFn)(int);
+static void* nccl_sym(const char* name) {
+    void* fn = dlsym(RTLD_DEFAULT, name);
+    if (!fn) {
+        static void* h = nullptr;
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (h) fn = dlsym(h, name);
+    }
+    return fn;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;  // ncclDataType_t / ncclRedOp_t values of nccl.h (stable ABI)
+
+static int nccl_fail(slm_ctx* ctx, const char* what, int rc) {
+    NcclErrFn es = (NcclErrFn)nccl_sym("ncclGetErrorString");
+    return fail(ctx, 200 + rc, std::string(what) + ": " + (es ? es(rc) : "NCCL error"));
+}
+
+extern "C" int slm_allreduce_sum(slm_ctx* ctx, void* nccl_comm, double* buf, int64_t count, void* stream) {
+    if (!ctx || !nccl_comm || !buf) return fail(ctx, 1, "slm_allreduce_sum: null argument");
+    NcclAllReduceFn ar = (NcclAllReduceFn)nccl_sym("ncclAllReduce");
+    if (!ar) return fail(ctx, 9, "slm_allreduce_sum: NCCL is not loaded in this process");
+    if (count <= 0) return 0;
+    int rc = ar(buf, buf, (size_t)count, kNcclFloat64, kNcclSum, nccl_comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(ctx, "ncclAllReduce", rc);
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int slm_gather_results(slm_ctx* ctx, void* nccl_comm, const double* send, double* recv,
+                                  int64_t count_per_rank, void* stream) {
+    if (!ctx || !nccl_comm || !send || !recv) return fail(ctx, 1, "slm_gather_results: null argument");
+    NcclAllGatherFn ag = (NcclAllGatherFn)nccl_sym("ncclAllGather");
+    if (!ag) return fail(ctx, 9, "slm_gather_results: NCCL is not loaded in this process");
+    if (count_per_rank <= 0) return 0;
+    int rc = ag(send, recv, (size_t)count_per_rank, kNcclFloat64, nccl_comm, (cudaStream_t)stream);
+    if (rc) return nccl_fail(ctx, "ncclAllGather", rc);
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int slm_tri_complement(slm_ctx* ctx, const double* buf, int64_t pa, int n_blocks, double* G,
+                                  int64_t g_stride, void* stream);
+
+// partial fold blocks G[n_blocks][pa][pa] of this rank -> training Grams + total of ALL ranks in
+// G[n_blocks + 1][pa][pa]: pack the upper triangles, one all-reduce, unpack + complement in one pass
+extern "C" int slm_gram_allreduce(slm_ctx* ctx, void* nccl_comm, double* G, int64_t g_stride, int64_t pa,
+                                  int n_blocks, double* buf, void* stream) {
+    if (!ctx || !G || !buf) return fail(ctx, 1, "slm_gram_allreduce: null argument");
+    if (n_blocks < 1 || n_blocks > SLM_MAX_FOLDS) return fail(ctx, 1, "slm_gram_allreduce: n_blocks out of range");
+    if (int rc = slm_tri_pack(ctx, G, g_stride, pa, n_blocks, buf, stream)) return rc;
+    if (nccl_comm)  // NULL: single rank, the complement alone
+        if (int rc = slm_allreduce_sum(ctx, nccl_comm, buf, (int64_t)n_blocks * slm_tri_size(pa), stream)) return rc;
+    return slm_tri_complement(ctx, buf, pa, n_blocks, G, g_stride, stream);
+}
+

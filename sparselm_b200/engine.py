@@ -387,10 +387,10 @@ class Engine:
                                          self._ptr(GZ), self.stream), "slm_gram_apply")
         return GZ
 
-    def gram_cg(self, G, p, tol=1e-13, max_iter=None):
+    def gram_cg(self, G, p, tol=1e-13, max_iter=None, shift=None):
         """Least-squares coefficients of ONE Gram G [pa, pa]: conjugate gradients on
-        G b = c (c = row p), products on the tensor-core apply.  Returns (X8, iters, relres):
-        X8 is [p, 8] with the solution in column 0."""
+        (G + diag(shift)) b = c (c = row p), products on the tensor-core apply.  Returns
+        (X8, iters, relres): X8 is [p, 8] with the solution in column 0."""
         torch = self.torch
         pa = G.shape[-1]
         if max_iter is None:
@@ -399,7 +399,8 @@ class Engine:
         work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         X8 = torch.empty((p, 8), dtype=torch.float64, device=self.device)
         iters, rel = ctypes.c_int32(0), ctypes.c_double(0.0)
-        self._ck(self.lib.slm_gram_cg(self.h, self._ptr(G), pa, p, float(tol), int(max_iter), self._ptr(work), nbytes,
+        self._ck(self.lib.slm_gram_cg(self.h, self._ptr(G), pa, p, self._ptr(shift), float(tol), int(max_iter),
+                                      self._ptr(work), nbytes,
                                       self._ptr(X8), ctypes.byref(iters), ctypes.byref(rel), self.stream),
                  "slm_gram_cg")
         return X8, int(iters.value), float(rel.value)
@@ -467,6 +468,7 @@ class Engine:
         fold_rows = shard.fold_row_ranges(row_ptr) if sharded else \
             [(int(row_ptr[f]), int(row_ptr[f + 1])) for f in range(F)]
         partial = False  # did the prepare routine leave rows of unscored folds unpacked?
+        self._complemented = False  # set by the sharded reduce when it already produced training Grams + total
         if on_host and row_perm is None and n >= 4096:
             Xa, allG, partial = self._prepare_pipelined(X, y, sw, col_perm, row_ptr, fold_rows,
                                                         shard if sharded else None, score_folds if sharded else None)
@@ -479,7 +481,8 @@ class Engine:
         pa = Xa.shape[1]
         if F > 1:
             G_train, G_full = allG[:F], allG[F]
-            self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
+            if not self._complemented:
+                self.gram_complement(allG, F, out=G_full)  # blocks -> training Grams
             n_train = (n - np.diff(row_ptr)).astype(np.float64)
         else:
             G_full = allG[0]
@@ -565,24 +568,38 @@ class Engine:
         allG = torch.zeros((F + (1 if F > 1 else 0), pa, pa), dtype=torch.float64, device=self.device)
         for f, (lo, hi) in enumerate(fold_rows):
             self._gram_block_into(Xa, lo, hi, allG[f])
-        self._allreduce_grams(allG[:F], shard)
+        self._complemented = self._allreduce_grams(allG, F, shard)
         return Xa, allG, partial
 
-    def _allreduce_grams(self, G, shard):
-        """Sum the partial Gram blocks G [F, pa, pa] over the ranks: upper triangles packed into
-        one buffer, ONE NCCL all-reduce, unpack + mirror.  (Measured on B200/NVLink: NCCL's
-        bandwidth is bound by the CTAs it gets -- about 20 GB/s each, 24 to saturate -- and the
-        FP64 build wants every SM, so overlapping the two only slows both; half the bytes in one
-        full-speed collective after the builds is faster at every rank count.)"""
+    def _allreduce_grams(self, allG, F, shard):
+        """Sum the partial Gram blocks allG[:F] over the ranks: upper triangles packed into one buffer,
+        ONE NCCL all-reduce.  For F > 1 the reduced buffer is unpacked straight into the F training
+        Grams + the total (allG[:F+1], slm_tri_complement) and True is returned: the caller skips its own
+        complement pass.  The collective runs on the caller's NCCL communicator inside the engine
+        (slm_gram_allreduce) when the process group exposes it, through torch.distributed otherwise.
+        (Measured on B200/NVLink: NCCL's bandwidth is bound by the CTAs it gets and the FP64 build
+        wants every SM, so overlapping the two only slows both; half the bytes in one full-speed
+        collective after the builds is faster at every rank count.)"""
         torch = self.torch
-        F, pa = G.shape[0], G.shape[-1]
+        pa = allG.shape[-1]
+        nb = max(F, 1)
         tri = int(self.lib.slm_tri_size(pa))
-        buf = torch.empty((F, tri), dtype=torch.float64, device=self.device)
-        self._ck(self.lib.slm_tri_pack(self.h, self._ptr(G), pa * pa, pa, F, self._ptr(buf), self.stream),
+        buf = torch.empty((nb, tri), dtype=torch.float64, device=self.device)
+        comm = shard.comm_ptr(self.device)
+        if F > 1 and comm is not None:
+            self._ck(self.lib.slm_gram_allreduce(self.h, ctypes.c_void_p(comm), self._ptr(allG), pa * pa, pa, F,
+                                                 self._ptr(buf), self.stream), "slm_gram_allreduce")
+            return True
+        self._ck(self.lib.slm_tri_pack(self.h, self._ptr(allG), pa * pa, pa, nb, self._ptr(buf), self.stream),
                  "slm_tri_pack")
         shard.allreduce_sum_(buf)
-        self._ck(self.lib.slm_tri_unpack(self.h, self._ptr(buf), pa, F, self._ptr(G), pa * pa, self.stream),
+        if F > 1:
+            self._ck(self.lib.slm_tri_complement(self.h, self._ptr(buf), pa, F, self._ptr(allG), pa * pa, self.stream),
+                     "slm_tri_complement")
+            return True
+        self._ck(self.lib.slm_tri_unpack(self.h, self._ptr(buf), pa, nb, self._ptr(allG), pa * pa, self.stream),
                  "slm_tri_unpack")
+        return False
 
     def _pack_rows(self, Xd, yd, swd, cp, a, b, Xa):
         """Xa[a:b] = [X | y | 1 | 0] of the device-resident rows a..b (identity row order)."""
@@ -662,7 +679,7 @@ class Engine:
                 self._gram_block_into(Xa, lo, hi, allG[f], accumulate=f in started)
                 started.add(f)
         if shard is not None:
-            self._allreduce_grams(allG[:max(F, 1)] if F > 1 else allG[:1], shard)
+            self._complemented = self._allreduce_grams(allG, F, shard)
         return Xa, allG, bool(F > 1 and score_folds is not None)
 
     # ---- K5-K8: batched solve ------------------------------------------------
@@ -743,6 +760,10 @@ class Engine:
         bt.n_iter_dev, bt.status_dev = n_iter.data_ptr(), status.data_ptr()
 
         ad = g0.adaptive
+        # columns without any l1 / group penalty (alpha = 0 is valid in the reference, _lasso.py:77-79):
+        # the duality-gap test of the proximal iterations degenerates there, so they are solved as
+        # (ridged) least squares by conjugate gradients on the same Gram and frozen in the batch
+        unpen = self._solve_unpenalised(Gs, p, n_obs, grids, g0, B, rbuf, F, ldz, ncol, tol)
         nctx = None
         if newton is None:
             newton = 160 < p <= 2048
@@ -750,14 +771,19 @@ class Engine:
             no_l1 = not np.any(np.concatenate([np.asarray(g.lam1, dtype=float).ravel() for g in grids]) != 0.0)
             if no_l1 and (ad is None or ad.get("a1") is None) and g0.gptr is not None:
                 gid = torch.from_numpy(np.repeat(np.arange(Gn), np.diff(np.asarray(g0.gptr))).astype(np.int64)).to(dev)
-                nctx = dict(Gs=Gs, B=B, gid=gid, n_obs=[float(v) for v in n_obs], Ks=Ks, status=status, n_iter=n_iter,
+                nctx = dict(Gs=Gs, B=B, gid=gid, gid32=gid.to(torch.int32), gptr_dev=gptr_dev,
+                            n_obs=[float(v) for v in n_obs], Ks=Ks, status=status, n_iter=n_iter,
                             primal=primal, get_W2=lambda: W2, D2=D2, p=p, ldz=ldz, F=F, tol=tol, floor_rel=floor_rel,
                             stats={"phases": 0, "factorizations": 0, "newton_columns": 0, "ms": 0.0})
         n_pass = np.ones((F, ldz), dtype=np.int64)
         total_iters = 0
         if ad is None:
             bt.W1_dev, bt.skip_dev = 0, 0
-            total_iters = self._run_batch(bt, nctx)
+            skip0 = None
+            if unpen is not None:
+                skip0 = torch.from_numpy(unpen.astype(np.int32)).to(dev)
+                bt.skip_dev = skip0.data_ptr()
+            total_iters = self._run_batch(bt, nctx, base_skip=skip0)
         else:
             max_pass = int(ad["max_iter"])
             use_w1 = ad.get("a1") is not None
@@ -784,6 +810,10 @@ class Engine:
             conv = np.zeros((F, ldz), dtype=bool)
             for f in range(F):
                 conv[f, Ks[f]:] = True
+            if unpen is not None:  # alpha = 0: the weights stay zero, the reference stops after one solve
+                conv |= unpen
+                n_pass[unpen] = 1
+                skip.copy_(torch.from_numpy(conv.astype(np.int32)))
             for ps in range(max_pass):
                 bt.W1_dev = 0 if W1 is None else W1.data_ptr()
                 bt.skip_dev = skip.data_ptr()
@@ -819,6 +849,48 @@ class Engine:
         }
         return res
 
+    def _solve_unpenalised(self, Gs, p, n_obs, grids, g0, B, rbuf, F, ldz, ncol, tol):
+        """Conjugate gradients for the columns whose penalty has no l1 / group part; fills B and the
+        result buffer (gap 0, status, iterations) and returns their [F, ldz] mask (None: there are none)."""
+        torch = self.torch
+        mask = np.zeros((F, ldz), dtype=bool)
+        for f, g in enumerate(grids):
+            if g.K == 0:
+                continue
+            z = np.asarray(g.lam1, dtype=float) == 0.0
+            if g.W2 is not None:
+                z &= ~np.any(np.asarray(g.W2) != 0.0, axis=0)
+            if g.adaptive is not None:
+                z &= np.asarray(g.adaptive["alpha"], dtype=float) == 0.0
+            mask[f, : g.K] = z
+        if not mask.any():
+            return None
+        gptr = np.arange(p + 1) if g0.gptr is None else np.asarray(g0.gptr)
+        sizes = np.diff(gptr)
+        gap = rbuf[: 8 * ncol].view(torch.float64).view(F, ldz)
+        primal = rbuf[8 * ncol: 16 * ncol].view(torch.float64).view(F, ldz)
+        n_iter = rbuf[16 * ncol: 20 * ncol].view(torch.int32).view(F, ldz)
+        status = rbuf[20 * ncol:].view(torch.int32).view(F, ldz)
+        for f, g in enumerate(grids):
+            done = {}
+            for k in np.flatnonzero(mask[f]):
+                d2 = None if g.D2 is None else np.asarray(g.D2)[:, k]
+                key = None if d2 is None or not np.any(d2) else d2.tobytes()
+                if key not in done:
+                    shift = None if key is None else self.to_device(np.repeat(float(n_obs[f]) * d2, sizes))
+                    X8, iters, rel = self.gram_cg(Gs[f], p, tol=min(1e-13, 1e-3 * tol), shift=shift)
+                    b = X8[:, 0]
+                    cvec = Gs[f][p, :p]
+                    obj = (Gs[f][p, p] - (cvec * b).sum()) / (2.0 * float(n_obs[f]))  # = 1/(2n)||y - Xb||^2 + ridge at the optimum
+                    done[key] = (b, iters, int(rel > 1e-9), obj)
+                b, iters, st, obj = done[key]
+                B[f, :, k] = b
+                n_iter[f, k] = iters
+                status[f, k] = st
+                primal[f, k] = obj
+                gap[f, k] = 0.0
+        return mask
+
     def _run_batch(self, bt, nctx, base_skip=None):
         """One slm_solve_batch call -- or, with a Newton context, stretches of iterations with a
         lock-step Newton phase (newton.newton_phase) on the still unconverged columns in between.
@@ -827,7 +899,7 @@ class Engine:
         if nctx is None:
             self._ck(self.lib.slm_solve_batch(self.h, ctypes.byref(bt), self.stream), "slm_solve_batch")
             return bt.iters_run
-        from .newton import newton_phase
+        from .newton import newton_phase, newton_phase_device
 
         torch = self.torch
         F, ldz, p, Ks = nctx["F"], nctx["ldz"], nctx["p"], nctx["Ks"]
@@ -870,7 +942,7 @@ class Engine:
                 floor = max(nctx["floor_rel"], 4e-15 / nctx["tol"])
                 yty = Gs[:, p, p].cpu().numpy()
                 scale = np.array([max(abs(prim[f, k]), floor * yty[f] / (2.0 * nctx["n_obs"][f])) for f, k in zip(fi, ki)])
-                # chunks of columns: four [k, p, p] FP64 temporaries at most ~16 GB
+                # chunks of columns: one [k, p, p] FP64 Hessian / factor at most ~16 GB
                 chunk = max(1, int(16e9 // (32.0 * p * p)))
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
@@ -882,7 +954,11 @@ class Engine:
                     d2 = None if D2 is None else D2[fc, :, kc]
                     nn = torch.tensor([nctx["n_obs"][f] for f in fi[c0:c0 + chunk]], dtype=torch.float64, device=self.device)
                     sc = torch.from_numpy(scale[c0:c0 + chunk]).to(self.device)
-                    Xn, info = newton_phase(Gs, fc, nn, X, w2, d2, nctx["gid"], sc, nctx["tol"])
+                    if "gptr_dev" in nctx and os.environ.get("SLM_NEWTON_TORCH", "0") != "1":
+                        Xn, info = newton_phase_device(self, Gs, fc, nn, X, w2, d2, nctx["gptr_dev"], nctx["gid32"], sc,
+                                                       nctx["tol"])
+                    else:  # SLM_NEWTON_TORCH=1: the torch / cuSOLVER model of the same iteration (A/B runs)
+                        Xn, info = newton_phase(Gs, fc, nn, X, w2, d2, nctx["gid"], sc, nctx["tol"])
                     B[fc, :, kc] = Xn
                     nf = ~info["finished"].cpu().numpy()
                     fails[fi[c0:c0 + chunk][nf], ki[c0:c0 + chunk][nf]] += 1

@@ -179,13 +179,19 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     n, p = X.shape
     n_splits, n_cand = len(test_folds), len(specs)
     yv = np.asarray(y, dtype=np.float64)
+    torch = engine.torch
     # one scorer name, or {metric name: scorer name}: every device scorer derives from the same
     # two residual sums, so a multi-metric search costs nothing extra on the GPU
     multi = not isinstance(scoring, str)
     metrics = dict(scoring) if multi else {"score": scoring}
-    test_tabs = {m: np.full((n_cand, n_splits), np.nan) for m in metrics}
-    train_tabs = {m: np.full((n_cand, n_splits), np.nan) for m in metrics} if return_train_score else None
-    train_scores = train_tabs  # (None check below)
+    sharded = shard is not None and shard.world > 1
+    # residual sums per (candidate, fold): sum of squares and of absolute values over the test rows
+    # (and over the training rows when train scores are asked for).  A sharded search fills in the
+    # sums of ITS rows of every fold (scoring is row-sharded like the Gram build) and the tables are
+    # summed over the ranks; the metrics are formed from the complete sums afterwards.
+    want_train = bool(return_train_score)
+    SSE, SAE = np.zeros((n_cand, n_splits)), np.zeros((n_cand, n_splits))
+    TSSE, TSAE = (np.zeros((n_cand, n_splits)), np.zeros((n_cand, n_splits))) if want_train else (None, None)
     fit_time = np.zeros(n_cand)
     score_time = np.zeros(n_cand)
     info = dict(n_iter=np.zeros((n_cand, n_splits), dtype=int), status=np.zeros((n_cand, n_splits), dtype=int),
@@ -208,14 +214,19 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         # batch columns in order of increasing penalty strength (dense iterates first): the
         # row-sparse apply shares one support list per chunk of adjacent columns
         idxs = np.asarray(sorted(idxs, key=lambda ci: (specs[ci].strength, ci)))
-        if shard is not None and shard.world > 1:
-            mine = shard.my_columns(n_splits, len(idxs))  # per fold: positions in idxs this rank solves
+        K = len(idxs)
+        if sharded:
+            from .parallel import assign_columns
+
+            owner = assign_columns(n_splits, K, shard.world)  # owner[f][k]: rank that solves column k of fold f
+            mine = [np.flatnonzero(owner[f] == shard.rank) for f in range(n_splits)]
         else:
-            mine = [np.arange(len(idxs))] * n_splits
+            owner = None
+            mine = [np.arange(K)] * n_splits
         if fkey not in fds:
-            score_folds = None
-            if shard is not None and shard.world > 1 and train_scores is None and cache is None:
-                score_folds = {f for f in range(n_splits) if len(mine[f])}  # rows this rank has to hold
+            # a sharded rank only needs its own slice of every fold's rows on the device (Gram build
+            # and scoring are both row-sharded); a LineSearchCV cache keeps the whole design
+            score_folds = set() if (sharded and cache is None) else None
             fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard, sample_weight,
                                       score_folds)
         fd = fds[fkey]
@@ -223,40 +234,29 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         out = solve_specs(engine, fd, [[specs[idxs[k]] for k in mine[f]] for f in range(n_splits)], **opts)
         t1 = time.perf_counter()
         warm.add(out["B"], idxs, mine)
-        K = len(idxs)
-        icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
         wtd = bool(fd.extra.get("weighted"))
-        for f in range(n_splits):  # rows a sharded prepare did not expect to need
-            if len(mine[f]) or train_scores is not None:
-                engine.ensure_fold_rows(fd, X, yv, f)
-        if train_scores is not None:
-            for f in range(n_splits):
-                engine.ensure_fold_rows(fd, X, yv, f)
-        sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], len(mine[f]), icpt(f),
-                                  rows_scaled=wtd)
-                  for f in range(n_splits)]
-        sc = engine.torch.stack(sc_dev).cpu().numpy()  # one D2H for all folds
-        if train_scores is not None:
-            tsc = np.zeros_like(sc)
-            for f in range(n_splits):
-                for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
-                    if r1 > r0 and len(mine[f]):
-                        tsc[f] += engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], len(mine[f]),
-                                                  icpt(f), rows_scaled=wtd).cpu().numpy()
+        if not sharded:
+            icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
+            sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], K, icpt(f),
+                                      rows_scaled=wtd) for f in range(n_splits)]
+            sc = torch.stack(sc_dev).cpu().numpy()[:, :, :K]  # one D2H for all folds: [n_splits, 2, K]
+            tsc = None
+            if want_train:
+                tsc = np.zeros_like(sc)
+                for f in range(n_splits):
+                    for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
+                        if r1 > r0:
+                            tsc[f] += engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], K, icpt(f),
+                                                      rows_scaled=wtd).cpu().numpy()[:, :K]
+        else:
+            sc, tsc = _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, wtd, want_train)
         t2 = time.perf_counter()
         for f in range(n_splits):
-            nt = len(test_folds[f])
+            SSE[idxs, f], SAE[idxs, f] = sc[f, 0], sc[f, 1]
+            if want_train:
+                TSSE[idxs, f], TSAE[idxs, f] = tsc[f, 0], tsc[f, 1]
             kf = len(mine[f])
             ci = idxs[mine[f]]
-            for m, scorer in metrics.items():
-                test_tabs[m][ci, f] = _metric(scorer, sc[f, 0, :kf], sc[f, 1, :kf], nt, sst_test[f])
-            if train_scores is not None:
-                ntr = n - nt
-                s_tr = tot_sum - float(yv[test_folds[f]].sum())
-                q_tr = tot_sq - float((yv[test_folds[f]] ** 2).sum())
-                for m, scorer in metrics.items():
-                    train_tabs[m][ci, f] = _metric(scorer, tsc[f, 0, :kf], tsc[f, 1, :kf], ntr,
-                                                   q_tr - s_tr * s_tr / ntr)
             info["n_iter"][ci, f] = out["n_iter"][f, :kf]
             info["status"][ci, f] = out["status"][f, :kf]
             info["gap"][ci, f] = out["gap"][f, :kf]
@@ -267,11 +267,9 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         iters_run += int(out["iters_run"])
         for k, v in (out.get("newton") or {}).items():  # second-order phase of this rank's batches (engine._run_batch)
             newton_stats[k] = newton_stats.get(k, 0) + v
-    if shard is not None and shard.world > 1:
-        # the only data-path exchange of the sharded grid: one sum of the zero-padded tables
-        tabs = [np.nan_to_num(test_tabs[m], nan=0.0) for m in metrics]
-        if train_scores is not None:
-            tabs += [np.nan_to_num(train_tabs[m], nan=0.0) for m in metrics]
+    if sharded:
+        # the last exchange of the sharded grid: one sum of the residual-sum and info tables
+        tabs = [SSE, SAE] + ([TSSE, TSAE] if want_train else [])
         keys = list(info)
         tabs += [info[k].astype(np.float64) for k in keys] + [np.array([[float(n_unconverged)]])]
         flat = shard.allreduce_sum_numpy(np.concatenate([t.ravel() for t in tabs]), engine.device)
@@ -279,19 +277,82 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         for t in tabs:
             parts.append(flat[o:o + t.size].reshape(t.shape))
             o += t.size
-        for m in metrics:
-            test_tabs[m] = parts.pop(0)
-        if train_scores is not None:
-            for m in metrics:
-                train_tabs[m] = parts.pop(0)
+        SSE, SAE = parts.pop(0), parts.pop(0)
+        if want_train:
+            TSSE, TSAE = parts.pop(0), parts.pop(0)
         for k in keys:
             info[k] = parts.pop(0).astype(info[k].dtype)
         n_unconverged = int(round(float(parts.pop(0)[0, 0])))
+    test_tabs = {m: np.empty((n_cand, n_splits)) for m in metrics}
+    train_tabs = {m: np.empty((n_cand, n_splits)) for m in metrics} if want_train else None
+    for f in range(n_splits):
+        nt = len(test_folds[f])
+        for m, scorer in metrics.items():
+            test_tabs[m][:, f] = _metric(scorer, SSE[:, f], SAE[:, f], nt, sst_test[f])
+        if want_train:
+            ntr = n - nt
+            s_tr = tot_sum - float(yv[test_folds[f]].sum())
+            q_tr = tot_sq - float((yv[test_folds[f]] ** 2).sum())
+            for m, scorer in metrics.items():
+                train_tabs[m][:, f] = _metric(scorer, TSSE[:, f], TSAE[:, f], ntr, q_tr - s_tr * s_tr / ntr)
     test_scores = test_tabs if multi else test_tabs["score"]
-    if train_scores is not None:
+    train_scores = None
+    if want_train:
         train_scores = train_tabs if multi else train_tabs["score"]
     return dict(test_scores=test_scores, train_scores=train_scores, fit_time=fit_time, score_time=score_time,
                 info=info, fds=fds, n_unconverged=n_unconverged, iters_run=iters_run, warm=warm, newton=newton_stats)
+
+
+def _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, wtd, want_train):
+    """Row-sharded scoring of a sharded grid (north_star: "NCCL all-gather of CV scores and
+    coefficients").  Every rank publishes the coefficients (+ intercepts) of the columns it solved,
+    ONE all-gather makes all K x n_splits solutions resident everywhere (C3: 10 MB per rank), and each
+    rank forms the residual sums of ITS slice of every fold's rows -- the slice it uploaded for the
+    Gram build, so a host-resident design crosses the bus once, 1/world per rank.  Returns this
+    rank's partial sums [n_splits, 2, K] (test rows) and the same for the training rows (or None)."""
+    import ctypes
+
+    torch = engine.torch
+    W = shard.world
+    cap = max(int((owner == r).sum(axis=1).max()) for r in range(W))
+    ldg = max(8, (cap + 7) // 8 * 8)
+    send = torch.zeros((n_splits, p + 1, ldg), dtype=torch.float64, device=engine.device)
+    for f in range(n_splits):
+        kf = len(mine[f])
+        if kf:
+            send[f, :p, :kf] = out["coef"][f][:, :kf]
+            send[f, p, :kf] = out["intercept"][f][:kf]
+    recv = torch.empty((W,) + tuple(send.shape), dtype=torch.float64, device=engine.device)
+    comm = shard.comm_ptr(engine.device)
+    if comm is not None:
+        engine._ck(engine.lib.slm_gather_results(engine.h, ctypes.c_void_p(comm), engine._ptr(send), engine._ptr(recv),
+                                                 send.numel(), engine.stream), "slm_gather_results")
+    else:
+        shard.all_gather_(send, recv)
+    rows = shard.fold_row_ranges(fd.row_ptr)
+    part = torch.zeros((n_splits, 2, K), dtype=torch.float64, device=engine.device)
+    tpart = torch.zeros((n_splits, 2, K), dtype=torch.float64, device=engine.device) if want_train else None
+    cols_dev = {}
+    for f in range(n_splits):
+        for r in range(W):
+            cols = np.flatnonzero(owner[f] == r)
+            kf = len(cols)
+            if kf == 0:
+                continue
+            cd = cols_dev.setdefault((f, r), torch.from_numpy(cols).to(engine.device))
+            Bfr, icpt = recv[r, f, :p], (recv[r, f, p] if fd.fit_intercept else None)
+            lo, hi = rows[f]
+            if hi > lo:
+                part[f][:, cd] = engine.cv_score(fd.Xa, p, lo, hi, Bfr, kf, icpt, rows_scaled=wtd)[:, :kf]
+            if want_train:
+                for f2 in range(n_splits):
+                    lo2, hi2 = rows[f2]
+                    if f2 != f and hi2 > lo2:
+                        tpart[f][:, cd] += engine.cv_score(fd.Xa, p, lo2, hi2, Bfr, kf, icpt, rows_scaled=wtd)[:, :kf]
+    if want_train:
+        both = torch.stack([part, tpart]).cpu().numpy()
+        return both[0], both[1]
+    return part.cpu().numpy(), None
 
 
 class GridSearchCV(_SkGridSearchCV):
@@ -405,11 +466,10 @@ class GridSearchCV(_SkGridSearchCV):
                     cache = getattr(self, "_fd_cache", None)
                     shard = getattr(self, "_shard", None)
                     score_folds = None
-                    if shard is not None and shard.world > 1 and not self.return_train_score and cache is None:
-                        # host rows this rank needs: its slices for the Gram build + the test
-                        # folds of the columns it will solve (anything else is fetched on demand)
-                        mine = shard.my_columns(len(splits), len(candidates))
-                        score_folds = {f for f in range(len(splits)) if len(mine[f])}
+                    if shard is not None and shard.world > 1 and cache is None:
+                        # host rows this rank needs: its slice of every fold (Gram build and scoring
+                        # are both row-sharded)
+                        score_folds = set()
                     pre_fds[_fold_key(ests[0], specs[0])] = prepare_folds(
                         engine, Xv, yv, [np.asarray(test) for _, test in splits], ests[0], specs[0], cache,
                         None if cache is None else (id(Xv), id(yv), None if sw is None else sw.tobytes()),

@@ -14,11 +14,14 @@ is smooth (||b_g|| > 0 on every active group), so a damped Newton iteration fini
 factorisations.  The conic interior-point solvers behind the reference's cvxpy call
 (_base.py:512-519) are second-order methods too.
 
-What this module does: host-side orchestration on device tensors, all slow columns in lock step
-(one batched Hessian build, one batched Cholesky, one vectorised line search per Newton step).
-The dense factorisation is a plain library call (``torch.linalg.cholesky_ex`` = cuSOLVER potrf);
-everything is written with torch operations so the same code runs on CPU tensors in
-``tests/test_newton.py``.  It never decides convergence: the points go back into the engine's
+What this module does: host-side orchestration, all slow columns in lock step.  On the GPU
+(``newton_phase_device``) every Newton step is ONE call into the engine (``slm_newton_step``,
+csrc/newton_kernels.cuh): Hessian assembly straight from the Gram, a batched blocked Cholesky whose
+trailing updates run on the FP64 tensor-core GEMM, blocked triangular solves and the Armijo line
+search -- no library factorisation, no ``[k, p, p]`` copies of the Gram, no host synchronisation
+inside a step.  ``newton_phase`` is the same iteration written with torch operations
+(``torch.linalg.cholesky_ex``); it runs on CPU tensors in ``tests/test_newton.py`` and is the model the
+kernels are tested against.  It never decides convergence: the points go back into the engine's
 batch and the engine's own duality-gap certificate (exact ``G b``, all groups,
 ``gap_final_kernel``) judges them.  A step on a wrong support only costs time: every accepted step
 decreases phi (Armijo test on the *difference* of objective values, formed without cancellation).
@@ -33,9 +36,12 @@ equal to 3e-8 relative; 1109 factorisations per search, batched cuSOLVER potrf 0
 
 from __future__ import annotations
 
+import os
+import sys
+
 import torch
 
-__all__ = ["newton_phase"]
+__all__ = ["newton_phase", "newton_phase_device"]
 
 
 def _gsum(v, gid, n_groups):
@@ -141,3 +147,68 @@ def newton_phase(Gs, fold, n_obs, X, w2, d2, gid, scale, tol, max_steps=12, chol
         keep = accepted & ~fin & (st < 2)                             # not accepted / crawling: back to the engine
         live = live[keep]
     return X, {"steps": steps, "factorizations": n_fact, "finished": finished}
+
+
+def newton_phase_device(engine, Gs, fold, n_obs, X, w2, d2, gptr_dev, gid_dev, scale, tol, max_steps=12):
+    """The same lock-step iteration as ``newton_phase`` with every step done by the engine's kernels
+    (``slm_newton_step``).  Gs [F, pa, pa] device Grams, fold [K] int64, n_obs [K], X [K, p] start points,
+    w2 [K, Gn], d2 [K, Gn] or None, gptr_dev int32 [Gn+1], gid_dev int32 [p], scale [K], tol.
+    One small device-to-host read per step (accepted / step length / decrement of every column)."""
+    import ctypes
+
+    import numpy as np
+
+    K, p = X.shape
+    Gn = w2.shape[1]
+    dev, dt = X.device, X.dtype
+    F, pa = Gs.shape[0], Gs.shape[-1]
+    ldv = (p + 7) // 8 * 8
+    Xw = torch.zeros((K, ldv), dtype=dt, device=dev)
+    Xw[:, :p] = X
+    fold_h = fold.cpu().numpy().astype(np.int32)
+    steps = torch.zeros(K, dtype=torch.int64)
+    finished = torch.zeros(K, dtype=torch.bool)
+    small_t = torch.zeros(K, dtype=torch.int64)
+    live = torch.arange(K)
+    target = (1e-3 * tol * scale).cpu()
+    n_obs = n_obs.to(dt).contiguous()
+    w2 = w2.contiguous()
+    d2 = None if d2 is None else d2.contiguous()
+    nbytes = engine.lib.slm_newton_workspace(p, Gn, K, F)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.zeros((K, 4), dtype=dt, device=dev)
+    n_fact = 0
+    for _ in range(max_steps):
+        k = int(live.numel())
+        if k == 0:
+            break
+        ld = live.to(dev)
+        xs = Xw.index_select(0, ld).contiguous()
+        fh = np.ascontiguousarray(fold_h[live.numpy()])
+        # the gathered operands are named: a temporary would hand its memory back to the caching allocator
+        # (and to the next temporary) before the call that reads it is enqueued
+        nn_s = n_obs.index_select(0, ld).contiguous()
+        w2_s = w2.index_select(0, ld).contiguous()
+        d2_s = None if d2 is None else d2.index_select(0, ld).contiguous()
+        engine._ck(engine.lib.slm_newton_step(
+            engine.h, engine._ptr(Gs), pa * pa, pa, p, F, k, fh.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+            engine._ptr(nn_s), engine._ptr(xs), engine._ptr(w2_s), engine._ptr(d2_s),
+            engine._ptr(gptr_dev), engine._ptr(gid_dev), Gn, engine._ptr(work), nbytes, engine._ptr(out), engine.stream),
+            "slm_newton_step")
+        info = out[:k].cpu()  # the step's only host synchronisation
+        n_fact += k
+        accepted = info[:, 0] > 0
+        t, dec = info[:, 1], info[:, 2]
+        Xw.index_copy_(0, ld, xs)
+        steps[live] += accepted.to(torch.int64)
+        fin = accepted & (t == 1.0) & (0.5 * dec <= target[live])
+        st = small_t[live]
+        st = torch.where(accepted & (t < 1e-4), st + 1, torch.zeros_like(st))
+        small_t[live] = st
+        finished[live] = fin
+        if os.environ.get("SLM_TRACE"):
+            print(f"[slm newton step] k={k} accepted={int(accepted.sum())} full={int((t == 1.0).sum())} finished={int(fin.sum())} "
+                  f"dec max {float(dec.max()):.3e} min {float(dec.min()):.3e} chol failures {int((info[:, 3] != 0).sum())}",
+                  file=sys.stderr)
+        live = live[accepted & ~fin & (st < 2)]
+    return Xw[:, :p].contiguous(), {"steps": steps.to(dev), "factorizations": n_fact, "finished": finished.to(dev)}

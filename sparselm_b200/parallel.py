@@ -77,6 +77,34 @@ class GridShard:
         owner = assign_columns(n_folds, n_cols, self.world)
         return [np.flatnonzero(owner[f] == self.rank) for f in range(n_folds)]
 
+    def comm_ptr(self, device=None):
+        """The ncclComm_t of the process group (as an integer) for the engine's own collectives
+        (slm_gram_allreduce / slm_allreduce_sum / slm_gather_results), or None when the group is not an
+        initialised NCCL group (gloo on CPU, lazily created communicator): callers then go through
+        torch.distributed."""
+        if self.world == 1:
+            return None
+        if "_comm" not in self.__dict__:
+            ptr = None
+            try:
+                import torch
+                import torch.distributed as dist
+
+                pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+                dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+                ptr = int(pg._get_backend(dev)._comm_ptr())
+            except Exception:
+                ptr = None
+            self.__dict__["_comm"] = ptr or None
+        return self.__dict__["_comm"]
+
+    def all_gather_(self, send, recv):
+        """recv[r] = send of rank r (torch tensors; recv has a leading world dimension)."""
+        import torch.distributed as dist
+
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        return recv
+
     def allreduce_sum_(self, tensor):
         """In-place sum over ranks of a torch tensor (cuda -> NCCL, cpu -> gloo)."""
         if self.world == 1:

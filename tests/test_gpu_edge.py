@@ -134,3 +134,47 @@ def test_two_rows_one_feature_and_wide_single_group():
     est = GroupLasso(groups=np.zeros(33, dtype=int), alpha=0.1, solver_options={"tol": 1e-12}).fit(X, y)
     b_ref, _ = R.fit("GroupLasso", X, y, alpha=0.1, groups=np.zeros(33, dtype=int))
     assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+
+
+def test_alpha_zero_is_unpenalised_least_squares():
+    """alpha = 0 is valid in the reference (_lasso.py:77-79, interval closed at 0): the penalised
+    estimators then solve (ridged) least squares.  Routed to conjugate gradients on the Gram (the
+    duality-gap test of the proximal iterations degenerates without a penalty): no warning, exact
+    answer, also as one candidate of a batched grid and through the adaptive loop."""
+    import warnings
+
+    from sparselm_b200.model import AdaptiveLasso, GroupLasso, Lasso, RidgedGroupLasso
+    from sparselm_b200.model_selection import GridSearchCV
+
+    rng = np.random.default_rng(41)
+    n, p = 200, 30
+    X = rng.standard_normal((n, p))
+    y = X @ rng.standard_normal(p) + 0.5 * rng.standard_normal(n) + 2.0
+    groups = np.repeat(np.arange(6), 5)
+    ols = np.linalg.lstsq(X, y, rcond=None)[0]
+    Xc, yc = X - X.mean(0), y - y.mean()
+    ols_c = np.linalg.lstsq(Xc, yc, rcond=None)[0]
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        est = Lasso(alpha=0.0).fit(X, y)
+        assert est.solver_info_["status"] == 0
+        np.testing.assert_allclose(est.coef_, ols, rtol=0, atol=1e-9 * np.abs(ols).max())
+        est = GroupLasso(groups=groups, alpha=0.0, fit_intercept=True).fit(X, y)
+        np.testing.assert_allclose(est.coef_, ols_c, rtol=0, atol=1e-9 * np.abs(ols_c).max())
+        assert est.intercept_ == pytest.approx(y.mean() - X.mean(0) @ ols_c, rel=1e-9)
+        # ridge only: (X'X + n diag(delta_g)) b = X'y
+        delta = np.array([0.5, 0.0, 1.0, 2.0, 0.1, 0.3])
+        est = RidgedGroupLasso(groups=groups, alpha=0.0, delta=delta).fit(X, y)
+        ridge = np.linalg.solve(X.T @ X + n * np.diag(np.repeat(delta, 5)), X.T @ y)
+        np.testing.assert_allclose(est.coef_, ridge, rtol=0, atol=1e-9 * np.abs(ridge).max())
+        ad = AdaptiveLasso(alpha=0.0).fit(X, y)
+        assert ad.n_iter_ == 1  # the weights stay zero: the reference's loop stops after one solve
+        np.testing.assert_allclose(ad.coef_, ols, rtol=0, atol=1e-9 * np.abs(ols).max())
+        gs = GridSearchCV(Lasso(solver_options={"tol": 1e-12}), {"alpha": [0.0, 0.01, 0.1]}, cv=4).fit(X, y)
+    assert gs.batched_ and (gs.solver_info_["status"] == 0).all()
+    from sklearn.model_selection import KFold
+
+    for f, (tr, te) in enumerate(KFold(4).split(X)):
+        b = np.linalg.lstsq(X[tr], y[tr], rcond=None)[0]
+        ref = -np.sqrt(np.mean((y[te] - X[te] @ b) ** 2))
+        assert gs.cv_results_[f"split{f}_test_score"][0] == pytest.approx(ref, rel=1e-9)

@@ -617,3 +617,33 @@ def test_estimators_match_third_party_conic_solution(case):
     assert est.intercept_ == 0.0
     assert np.abs(est.coef_ - ref).max() <= 1e-6 * np.abs(ref).max()
     assert np.array_equal(np.abs(est.coef_) > 1e-6, np.abs(ref) > 1e-6)
+
+
+# ---- reference tests/test_common.py:95-108: sklearn's conformance checks on every estimator ----------
+_ALL_ESTIMATORS = ["OrdinaryLeastSquares", "Lasso", "GroupLasso", "OverlapGroupLasso", "SparseGroupLasso",
+                   "RidgedGroupLasso", "AdaptiveLasso", "AdaptiveGroupLasso", "AdaptiveOverlapGroupLasso",
+                   "AdaptiveSparseGroupLasso", "AdaptiveRidgedGroupLasso"]
+
+
+@pytest.mark.parametrize("name", _ALL_ESTIMATORS)
+def test_sklearn_check_estimator(name):
+    """check_estimator(estimator_cls(fit_intercept=True)) as the reference runs it.  The constructors
+    that keep the reference's ``**kwargs`` (positional signature parity, _adaptive_lasso.py:110-125,
+    306-324, _lasso.py:344-356) cannot pass sklearn 1.9's set_params(kwargs=...) probe -- neither can
+    the reference's: that one check is an expected failure for them."""
+    import inspect
+
+    from sklearn.utils.estimator_checks import check_estimator
+
+    import sparselm_b200.model as M
+
+    cls = getattr(M, name)
+    expected = {}
+    if any(prm.kind is inspect.Parameter.VAR_KEYWORD for prm in inspect.signature(cls.__init__).parameters.values()):
+        expected["check_do_not_raise_errors_in_init_or_set_params"] = "constructor keeps the reference's **kwargs"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = check_estimator(cls(fit_intercept=True), expected_failed_checks=expected, on_fail=None, on_skip=None)
+    bad = [(r["check_name"], repr(r.get("exception"))[:200]) for r in res if r["status"] == "failed"]
+    assert not bad, bad
+    assert sum(r["status"] == "passed" for r in res) >= 50

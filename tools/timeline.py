@@ -74,7 +74,8 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
 os.makedirs("gpurun_out", exist_ok=True)
-path = f"gpurun_out/timeline{'_e2e' if E2E else ''}_w{world}_r{rank}.json"
+# the chrome trace of rank 0 is kept (gpurun_out/ travels back, 64 MiB at most); other ranks parse theirs from /tmp
+path = f"{'gpurun_out' if rank == 0 else '/tmp'}/timeline{'_e2e' if E2E else ''}_w{world}_r{rank}.json"
 prof.export_chrome_trace(path)
 ev = json.load(open(path))["traceEvents"]
 ks = sorted([e for e in ev if e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in e],
