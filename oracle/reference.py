@@ -18,6 +18,7 @@ What is restated, with the reference lines it follows (paths relative to
 * adaptive reweighting loop             model/_adaptive_lasso.py:206-232
 * adaptive updates (alpha^2 quirk)      model/_adaptive_lasso.py:177-204, 343-374, 654-726
 * standardize=True group norms          model/_lasso.py:249-252, 776-789
+  (SparseGroupLasso + standardize: l1 on b with ||X_g b_g|| group norms, method of multipliers)
 
 The arithmetic of the reference lives in cvxpy (>=1.2, unpinned,
 pyproject.toml:15) and whichever conic solver it selects; neither is under
@@ -298,6 +299,68 @@ def standardize_transform(X, labels, n_groups, ridge_sqrt_delta=None):
     return Xt, rinv
 
 
+
+# --------------------------------------------------------------------------- #
+# SparseGroupLasso with standardize=True (_lasso.py:249-252 + :627-639): the group norm is
+# ||X_g b_g|| while the l1 term stays on b -- not separable in the whitened variables.  Solved by
+# the method of multipliers on the split  s_g = R_g b_g / sqrt(n)  (R_g^2 = X_g^T X_g):
+#   min  1/(2n)||y - Xb||^2 + sum w1|b| + sum sqrt(n) w2_g ||s_g||   s.t.  R b / sqrt(n) = s.
+# The inner problem in (b, s) is a penalised least-squares problem with SEPARABLE penalties on the
+# augmented design [[X, 0], [sqrt(rho) R, -sqrt(n rho) I]] (targets [y; -sqrt(n rho) u]) -- exactly what
+# solve() handles; the scaled multiplier moves by the constraint residual until it vanishes.
+# --------------------------------------------------------------------------- #
+def group_sqrt_blocks(X, labels, n_groups):
+    """blockdiag of the symmetric square roots R_g of X_g^T X_g as one [p, p] matrix."""
+    p = X.shape[1]
+    Rbd = np.zeros((p, p))
+    for gi in range(n_groups):
+        idx = np.flatnonzero(labels == gi)
+        Rg, _, _ = _sym_sqrt(X[:, idx].T @ X[:, idx])
+        Rbd[np.ix_(idx, idx)] = Rg
+    return Rbd
+
+
+def objective_sgl_standardized(X, y, beta, labels, w1, w2):
+    """1/(2n)||Xb - y||^2 + sum w1|b| + sum_g w2_g ||X_g b_g||."""
+    r = X @ beta - y
+    val = float(r @ r) / (2.0 * X.shape[0]) + float(np.asarray(w1) @ np.abs(beta))
+    for gi in range(len(w2)):
+        idx = np.flatnonzero(labels == gi)
+        val += float(w2[gi]) * float(np.linalg.norm(X[:, idx] @ beta[idx]))
+    return val
+
+
+def solve_sgl_standardized(X, y, labels, w1, w2, rho=10.0, tol=1e-12, max_outer=2000, solver_tol=-1.0,
+                           max_sweeps=200000, start=None):
+    """argmin of the standardized sparse-group problem by the method of multipliers.
+    Returns (beta, info) with info = dict(outer, residual, u, z): the state to warm-start from."""
+    n, p = X.shape
+    G = len(w2)
+    Rh = group_sqrt_blocks(X, labels, G) / np.sqrt(n)
+    sr = np.sqrt(n * rho)
+    Xaug = np.block([[X, np.zeros((n, p))], [sr * Rh, -sr * np.eye(p)]])
+    lab2 = np.concatenate([G + np.arange(p), labels]).astype(np.int64)  # b: singleton groups G..G+p-1; s: groups 0..G-1
+    ps = n / (n + p)  # solve() divides the data term by its own row count
+    pen = Penalty(lab2, np.concatenate([w1, np.zeros(p)]) * ps,
+                  np.concatenate([np.sqrt(n) * np.asarray(w2, dtype=float), np.zeros(p)]) * ps, np.zeros(G + p))
+    u = np.zeros(p) if start is None else start["u"].copy()
+    z = None if start is None else start["z"].copy()
+    res, it = np.inf, 0
+    for it in range(1, max_outer + 1):
+        yaug = np.concatenate([y, -sr * u])
+        z, _ = solve(Xaug, yaug, pen, tol=solver_tol, max_sweeps=max_sweeps, beta0=z, check_every=50)
+        r = Rh @ z[:p] - z[p:]
+        u = u + r
+        res = float(np.abs(r).max())
+        if res <= tol * max(1.0, float(np.abs(z[p:]).max())):
+            break
+    beta = z[:p].copy()
+    for gi in range(G):  # a group whose split variable is exactly zero is a zero group (R b = s in the limit)
+        idx = np.flatnonzero(labels == gi)
+        if not np.any(z[p + idx]):
+            beta[idx] = 0.0
+    return beta, {"outer": it, "residual": res, "u": u, "z": z}
+
 # --------------------------------------------------------------------------- #
 # estimators (fit on already validated inputs)
 # --------------------------------------------------------------------------- #
@@ -377,10 +440,12 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
         w1[:] = lam1
         w2[:] = lam2 if adaptive else lam2 * gw  # _adaptive_lasso.py:658-667
 
-    if rinv is not None and base == "SparseGroupLasso":
-        raise NotImplementedError(
-            "oracle: standardize=True is restated for the group / overlap / ridged estimators only: "
-            "the l1 term of SparseGroupLasso is not separable in the whitened variables")
+    # SparseGroupLasso + standardize: l1 on b, group norms ||X_g b_g|| -- solved in b by the method of
+    # multipliers (solve_sgl_standardized), not in whitened variables
+    sgl_std = rinv is not None and base == "SparseGroupLasso"
+    if sgl_std:
+        rinv, Xsolve = None, Xs
+        Rbd_std = group_sqrt_blocks(Xs, labels, G)
 
     # ridged + standardize: the ridge 1/2 delta_g ||R_g^+ gamma_g||^2 is smooth; it is the data
     # term of the rows sqrt(n delta_g) R_g^+ appended to the whitened design (targets 0).  The
@@ -402,7 +467,17 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
 
     update = update_function if update_function is not None else _default_update(alpha)
 
+    alm_state = {}
+
     def solve_once(beta0):
+        if sgl_std:
+            # inner solves run to stationarity (solver_tol < 0): a multiplier iteration cannot push the
+            # constraint residual below the accuracy of its inner solutions
+            b, st = solve_sgl_standardized(Xs, yp, labels, w1, w2, solver_tol=-1.0, max_sweeps=max_sweeps,
+                                           start=alm_state.get("st"))
+            alm_state["st"] = st
+            return b, {"sweeps": st["outer"], "primal": objective_sgl_standardized(Xs, yp, b, labels, w1, w2),
+                       "gap": st["residual"], "status": 0 if st["residual"] <= 1e-9 else 1}
         pen = Penalty(labels, w1 * pen_scale, w2 * pen_scale, dl_solve.copy())
         return solve(Xsolve, ysolve, pen, tol=solver_tol, max_sweeps=max_sweeps, beta0=beta0)
 
@@ -420,6 +495,9 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
             details["passes"].append(info)
             n_iter = i + 1
             norms = np.sqrt(np.bincount(labels, weights=gamma * gamma, minlength=G))
+            if sgl_std:  # the problem's norm expression is ||X_g b_g|| = ||R_g b_g||
+                rb = Rbd_std @ gamma
+                norms = np.sqrt(np.bincount(labels, weights=rb * rb, minlength=G))
             # group_norms.value is the *problem's* norm expression: in whitened
             # variables it equals ||X_g b_g|| when standardize (_adaptive_lasso.py:374)
             if base == "Lasso":
@@ -437,7 +515,7 @@ def fit(name, X, y, *, alpha=1.0, groups=None, group_list=None, group_weights=No
     if beta_indices is not None:
         beta = fold_back(beta, beta_indices, p)
     intercept = float(y_off - X_off @ beta) if fit_intercept else 0.0
-    details.update(n_iter=n_iter, w1=w1, w2=w2, labels=labels, delta=dl,
+    details.update(n_iter=n_iter, w1=w1, w2=w2, labels=labels, delta=dl, sgl_standardized=bool(sgl_std),
                    beta_solve=gamma, X_solve=Xsolve, y_solve=ysolve, pen_scale=pen_scale)
     if return_details:
         return beta, intercept, details

@@ -80,6 +80,7 @@ struct slm_ctx {
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
     // TMA-fed GEMM kernels (gemm_f64_tma.cuh): bit 0 Gram build, bit 1 dense apply, bit 2 row-sparse
     // apply (SLM_TMA / slm_set_option "tma"); encode = cuTensorMapEncodeTiled resolved at run time
+    bool prox2 = false;              // SLM_PROX2=1: one-lane-per-column prox kernels (measured slower: 3.34 vs 2.60 ms per C3 step)
     int tma_mask = 7 + 8;  // + bit 3: wide bands for the gather kernels, bit 4: for the tiled kernels
     void* encode = nullptr;
 };
@@ -929,6 +930,7 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_COOP")) ctx->coop = atoi(e) != 0;
     if (const char* e = getenv("SLM_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char* e = getenv("SLM_TMA")) ctx->tma_mask = atoi(e);
+    if (const char* e = getenv("SLM_PROX2")) ctx->prox2 = atoi(e) != 0;
     {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -999,6 +1001,8 @@ int slm_set_option(slm_ctx* ctx, const char* name, int value) {
         ctx->chunk_w = std::max(8, value / 8 * 8);
     else if (nm == "tma")
         ctx->tma_mask = value;
+    else if (nm == "prox2")
+        ctx->prox2 = value != 0;
     else if (nm == "force_apply_shape")
         ctx->force_apply_shape = value;
     else if (nm == "force_sparse_shape")
@@ -1773,11 +1777,26 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);
-            if (grouped)
-                prox_main_kernel<true><<<cgrid, ST, 0, s>>>(sp, par);
-            else
-                prox_main_kernel<false><<<cgrid, ST, 0, s>>>(sp, par);
-            prox_momentum_kernel<<<mgrid, ST, 0, s>>>(sp, par);
+            if (ctx->prox2) {
+                // one lane per column, 32 columns per block (solver_kernels.cuh, second mapping)
+                SolveDev s2 = sp;
+                s2.gpt = std::max(1, (Gn + PX_W * kMaxChunks - 1) / (PX_W * kMaxChunks));
+                s2.n_chunks = (Gn + PX_W * s2.gpt - 1) / (PX_W * s2.gpt);
+                const dim3 cgrid2((unsigned)((Kmax + PX_C - 1) / PX_C), (unsigned)s2.n_chunks, (unsigned)F);
+                const dim3 mgrid2((unsigned)((Kmax + PX_C - 1) / PX_C), (unsigned)((p + MOM_ROWS - 1) / MOM_ROWS),
+                                  (unsigned)F);
+                if (grouped)
+                    prox_main2_kernel<true><<<cgrid2, PX_W * PX_C, 0, s>>>(s2, par);
+                else
+                    prox_main2_kernel<false><<<cgrid2, PX_W * PX_C, 0, s>>>(s2, par);
+                prox_momentum2_kernel<<<mgrid2, PX_W * PX_C, 0, s>>>(s2, par);
+            } else {
+                if (grouped)
+                    prox_main_kernel<true><<<cgrid, ST, 0, s>>>(sp, par);
+                else
+                    prox_main_kernel<false><<<cgrid, ST, 0, s>>>(sp, par);
+                prox_momentum_kernel<<<mgrid, ST, 0, s>>>(sp, par);
+            }
         }
         LAUNCH_OK("prox kernels");
         ctx->launches++;

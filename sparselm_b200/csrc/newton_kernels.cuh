@@ -161,10 +161,10 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
         for (int i = k + 1 + tid; i < nb; i += NW_T) S[i][k] /= sq;
         __syncthreads();
         // trailing update of the lower triangle: S[i][j] -= S[i][k] S[j][k], k < j <= i < nb
-        const int m = nb - k - 1;
-        for (int e = tid; e < m * m; e += NW_T) {
-            const int i = k + 1 + e / m, j = k + 1 + e % m;
-            if (j <= i) S[i][j] -= S[i][k] * S[j][k];
+        // (threads as a 16 x 16 patch stepping over the triangle: no integer division in the loop)
+        for (int i = k + 1 + (tid >> 4); i < nb; i += 16) {
+            const double sik = S[i][k];
+            for (int j = k + 1 + (tid & 15); j <= i; j += 16) S[i][j] -= sik * S[j][k];
         }
         __syncthreads();
     }

@@ -684,7 +684,7 @@ class Engine:
 
     # ---- K5-K8: batched solve ------------------------------------------------
     def solve(self, G, p, n_obs, lipschitz, grids, B0=None, tol=1e-10, floor_rel=1e-14, max_iter=20000,
-              check_every=10, newton=None):
+              check_every=10, newton=None, W1_init=None):
         """Solve grids[f] (a PenaltyGrid) on Gram G[f] for every f, as one batch.
 
         newton: pure group penalties only (no l1 term) -- columns that have not converged after a
@@ -693,6 +693,9 @@ class Engine:
         160 < p <= 2048: below, the fused small-design kernel iterates at ~0.3 us per iteration;
         above, one p x p factorisation per column and step costs more than the iterations it saves
         unless the problem is known to be ill-conditioned (then pass True).
+
+        W1_init: optional device tensor [F, p, ldz] of per-coordinate l1 weights (instead of the
+        per-column lam1; sparselm_b200/split.py).
 
         Returns dict with B (torch [F,p,ldz]), and numpy [F][K_f] arrays gap, primal,
         n_iter, status, n_pass.
@@ -763,7 +766,8 @@ class Engine:
         # columns without any l1 / group penalty (alpha = 0 is valid in the reference, _lasso.py:77-79):
         # the duality-gap test of the proximal iterations degenerates there, so they are solved as
         # (ridged) least squares by conjugate gradients on the same Gram and frozen in the batch
-        unpen = self._solve_unpenalised(Gs, p, n_obs, grids, g0, B, rbuf, F, ldz, ncol, tol)
+        unpen = None if W1_init is not None else \
+            self._solve_unpenalised(Gs, p, n_obs, grids, g0, B, rbuf, F, ldz, ncol, tol)
         nctx = None
         if newton is None:
             newton = 160 < p <= 2048
@@ -778,7 +782,7 @@ class Engine:
         n_pass = np.ones((F, ldz), dtype=np.int64)
         total_iters = 0
         if ad is None:
-            bt.W1_dev, bt.skip_dev = 0, 0
+            bt.W1_dev, bt.skip_dev = (0 if W1_init is None else W1_init.data_ptr()), 0
             skip0 = None
             if unpen is not None:
                 skip0 = torch.from_numpy(unpen.astype(np.int32)).to(dev)

@@ -171,11 +171,11 @@ class AdaptiveSparseGroupLasso(AdaptiveLasso, SparseGroupLasso):
         _warn_max_iter(self)
 
     def _problem_spec(self, n_features):
-        self._check_standardize(separable=False)
+        std = self._check_standardize(separable=False)
         col_perm, gptr, gw = self._group_spec(n_features)
         lam1, lam2 = (float(v) for v in self._lambdas())
         return ProblemSpec(p=n_features, pe=n_features, lam1=lam1, col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=lam2 + 0.0 * gw, adaptive=_adaptive(self, lam1, lam2),
+                           w2=lam2 + 0.0 * gw, adaptive=_adaptive(self, lam1, lam2), split=std,
                            key=self._structure_key("AdaptiveSparseGroupLasso", n_features) + (_fn_key(self),))
 
 

@@ -51,6 +51,7 @@ class ProblemSpec:
     adaptive: dict | None = None         # a1, a2, alpha, eps, tol, max_iter, update_function
     standardize: bool = False            # group norms ||X_g b_g|| (solved in whitened variables)
     std_delta: np.ndarray | None = None  # (G,) ridge of the standardized ridged variant (then d2 is None)
+    split: bool = False                  # standardized group norms next to an l1 term: sparselm_b200/split.py
     key: tuple = field(default_factory=tuple)  # structure key: specs with equal keys can be batched
 
     @property
@@ -283,6 +284,21 @@ def solve_specs(engine, fd, specs, use_full=False, tol=1e-10, max_iter=None, che
         grids.append(memo[id(fs)])
     Ks = [g.K for g in grids]
     used = [i for i in range(F) if Ks[i] > 0]
+    if s0.split:
+        # SparseGroupLasso(standardize=True): l1 on b next to ||X_g b_g|| group norms -- method of
+        # multipliers around the engine's solves (sparselm_b200/split.py)
+        from ..split import solve_split
+
+        res = solve_split(engine, fd, G, keys, n_obs, fold_specs, tol=tol, max_iter=max_iter, check_every=check_every,
+                          floor_rel=floor_rel)
+        fd.check_finite()
+        coef = res["B"]
+        if fd.fit_intercept:
+            icpt = torch.stack([engine.intercepts(G[f], p, coef[f], Ks[f]) for f in range(F)])
+        else:
+            icpt = torch.zeros((F, res["ldz"]), dtype=torch.float64, device=engine.device)
+        res.update(coef=coef, intercept=icpt)
+        return res
     wctx = None
     if s0.ext_idx is not None:  # overlap: solve on the duplicated-column Gram (_lasso.py:461)
         idx_dev = engine.to_device(np.asarray(s0.ext_idx, dtype=np.int32))

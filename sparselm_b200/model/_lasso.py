@@ -99,15 +99,9 @@ class GroupLasso(Lasso):
     # -- problem description --
     def _check_standardize(self, separable=True):
         """standardize=True (group norms ||X_g b_g||, reference _lasso.py:249-252) is solved in
-        per-group whitened variables.  That needs a penalty that is a function of the group
-        norms alone: the l1 term of the sparse-group estimators is not separable in the
-        whitened variables, so those raise (there is no CPU fallback)."""
-        if self.standardize and not separable:
-            raise NotImplementedError(
-                f"{type(self).__name__}(standardize=True): the l1 term is not separable in the whitened "
-                "group variables the B200 engine solves standardize=True in; not implemented "
-                "(there is no CPU fallback)"
-            )
+        per-group whitened variables when the penalty is a function of the group norms alone.  The
+        l1 term of the sparse-group estimators is not separable in those variables: they go through
+        the method of multipliers of sparselm_b200/split.py (ProblemSpec.split)."""
         return bool(self.standardize)
 
     def _cached_groups(self, n_features):
@@ -241,11 +235,11 @@ class SparseGroupLasso(GroupLasso):
         return self.l1_ratio * self.alpha, (1 - self.l1_ratio) * self.alpha  # _lasso.py:621-624
 
     def _problem_spec(self, n_features):
-        self._check_standardize(separable=False)
+        std = self._check_standardize(separable=False)
         col_perm, gptr, gw = self._group_spec(n_features)
         lam1, lam2 = self._lambdas()
         return ProblemSpec(p=n_features, pe=n_features, lam1=float(lam1), col_perm=col_perm, gptr=gptr, gw=gw,
-                           w2=float(lam2) * gw, key=self._structure_key("SparseGroupLasso", n_features))
+                           w2=float(lam2) * gw, split=std, key=self._structure_key("SparseGroupLasso", n_features))
 
 
 class RidgedGroupLasso(GroupLasso):

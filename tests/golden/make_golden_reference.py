@@ -148,7 +148,7 @@ def solve_generic(sf, p):
         ident = M.shape[0] == len(S) and np.array_equal(M, np.eye(len(S)))
         if not ident:
             if np.any(w1[S] != 0):
-                raise NotImplementedError("l1 term on a group with a non-identity norm matrix")
+                return solve_generic_split(A_all, r_all, w1, groups, used, p)
             Rg, Rinv = _sym_sqrt_and_inv(M.T @ M)  # ||M b|| = ||R b||, gamma = R b
             Xs[:, S] = A_all[:, S] @ Rinv
             backs.append((S, Rinv))
@@ -165,6 +165,58 @@ def solve_generic(sf, p):
     beta = gamma.copy()
     for S, Rinv in backs:
         beta[S] = Rinv @ gamma[S]
+    return beta, info
+
+
+def solve_generic_split(A_all, r_all, w1, groups, used, p, rho=10.0, tol=1e-13, max_outer=5000):
+    """Generic form with an l1 term on coordinates whose group norm has a non-identity matrix
+    (||M b_S||, M'M = R^2): not separable in any single set of variables.  Method of multipliers on
+    s_S = R b_S / sqrt(m) (m = rows of the least-squares part): the inner problem in (b, s) has
+    separable penalties and goes to the same BCD core; the multiplier moves by the constraint
+    residual until it vanishes.  The result is certified by kkt_residual_generic like every other."""
+    import oracle.reference as R
+
+    m = A_all.shape[0]
+    Rbd = np.zeros((p, p))
+    for S, M, v in groups:
+        Rg, _ = _sym_sqrt_and_inv(M.T @ M)
+        Rbd[np.ix_(S, S)] = Rg
+    in_group = used.copy()
+    Rh = Rbd / np.sqrt(m)
+    sr = np.sqrt(m * rho)
+    # columns of s only for grouped coordinates (ungrouped coordinates carry no l2 term)
+    gs = np.flatnonzero(in_group)
+    q = len(gs)
+    Xaug = np.block([[A_all, np.zeros((m, q))], [sr * Rh[np.ix_(gs, np.arange(p))], -sr * np.eye(q)]])
+    nG = len(groups)
+    lab_b = nG + np.arange(p)
+    lab_s = np.empty(q, dtype=np.int64)
+    pos = {int(j): i for i, j in enumerate(gs)}
+    w2 = np.zeros(nG + p)
+    for gi, (S, M, v) in enumerate(groups):
+        lab_s[[pos[int(j)] for j in S]] = gi
+        w2[gi] = np.sqrt(m) * v
+    rows = m + q
+    sc = 1.0 / (2.0 * rows)  # the form is ||A b - r||^2 + pen: oracle data term 1/(2 rows)||.||^2
+    pen = R.Penalty(np.concatenate([lab_b, lab_s]).astype(np.int64), np.concatenate([w1, np.zeros(q)]) * sc,
+                    w2 * sc * 1.0, np.zeros(nG + p))
+    # note: the split adds (rho'/2)-type terms in the same ||.||^2 scaling, so the penalties keep the form's scale
+    u = np.zeros(q)
+    z = None
+    info = {"sweeps": 0, "status": 1}
+    for it in range(max_outer):
+        yaug = np.concatenate([r_all, -sr * u])
+        z, inf = R.solve(Xaug, yaug, pen, tol=-1.0, max_sweeps=5000000, beta0=z, check_every=1000)
+        info["sweeps"] += inf["sweeps"]
+        res = Rh[np.ix_(gs, np.arange(p))] @ z[:p] - z[p:]
+        u = u + res
+        if np.abs(res).max() <= tol * max(1.0, np.abs(z[p:]).max()):
+            info["status"] = 0
+            break
+    beta = z[:p].copy()
+    for S, M, v in groups:  # a group whose split variable is exactly zero is a zero group (R b = s in the limit)
+        if not np.any(z[p + np.array([pos[int(j)] for j in S])]):
+            beta[S] = 0.0
     return beta, info
 
 
@@ -277,6 +329,13 @@ def case_list():
         add("AdaptiveRidgedGroupLasso", dict(groups=GROUPS16, alpha=a, delta=(0.5,), group_weights=GW16))
         add("AdaptiveRidgedGroupLasso", dict(groups=GROUPS16, alpha=a, delta=DELTA6, standardize=True), seed=13,
             fit_intercept=True, weighted=True)
+    # SparseGroupLasso with standardize=True: l1 on b, group norms ||X_g b_g|| (_lasso.py:249-252, :627-639)
+    for a in (0.05, 0.4):
+        add("SparseGroupLasso", dict(groups=GROUPS16, alpha=a, l1_ratio=0.5, standardize=True), seed=19)
+        add("SparseGroupLasso", dict(groups=GROUPS16, alpha=a, l1_ratio=0.3, standardize=True, group_weights=GW16),
+            seed=20, fit_intercept=True, weighted=True)
+        add("AdaptiveSparseGroupLasso", dict(groups=GROUPS16, alpha=min(a, 0.12), l1_ratio=0.5 if a < 0.1 else 0.3,
+                                             standardize=True), seed=21, fit_intercept=True)
     # groups=None / group_list=None degenerate to singleton groups (with the reference's warning)
     add("GroupLasso", dict(groups=None, alpha=0.1), seed=14)
     add("OverlapGroupLasso", dict(group_list=None, alpha=0.1), seed=15)

@@ -213,11 +213,14 @@ def test_standardized_grid_search_matches_per_fit_oracle():
 
 def test_standardize_error_contract(random_model_with_groups):
     X, y, _, groups = random_model_with_groups
-    # the l1 term is not separable in the whitened variables: loud failure, no CPU fallback
-    with pytest.raises(NotImplementedError):
-        SparseGroupLasso(groups=groups, standardize=True).fit(X, y)
-    with pytest.raises(NotImplementedError):
-        AdaptiveSparseGroupLasso(groups=groups, standardize=True).fit(X, y)
+    # the l1 term is not separable in the whitened variables: those two go through the method of
+    # multipliers (sparselm_b200/split.py) and agree with the oracle's own
+    for cls in (SparseGroupLasso, AdaptiveSparseGroupLasso):
+        est = cls(groups=groups, standardize=True, alpha=0.05).fit(X, y)
+        assert est.solver_info_["status"] == 0
+        b_ref, _ = R.fit(cls.__name__, X, y, alpha=0.05, groups=groups, standardize=True)
+        assert np.abs(est.coef_ - b_ref).max() <= 1e-6 * np.abs(b_ref).max()
+        assert np.array_equal(np.abs(est.coef_) > 1e-6, np.abs(b_ref) > 1e-6)
     # a group with linearly dependent columns: ||X_g b_g|| is only a semi-norm
     Xd = X.copy()
     idx = np.flatnonzero(groups == groups[0])
@@ -647,3 +650,21 @@ def test_sklearn_check_estimator(name):
     bad = [(r["check_name"], repr(r.get("exception"))[:200]) for r in res if r["status"] == "failed"]
     assert not bad, bad
     assert sum(r["status"] == "passed" for r in res) >= 50
+
+
+def test_sparse_group_lasso_standardized_grid_search():
+    """SparseGroupLasso(standardize=True) inside GridSearchCV (reference _lasso.py:568-580, 627-639 with
+    the standardized group norms of :239-255): every (alpha, fold) cell against the per-fit oracle."""
+    rng = np.random.default_rng(33)
+    n, p = 90, 18
+    X = rng.standard_normal((n, p))
+    y = X[:, :4] @ [1.5, -2.0, 1.0, 0.5] + 0.4 * rng.standard_normal(n) + 1.0
+    groups = rng.permutation(np.repeat(np.arange(6), 3))
+    alphas = [0.02, 0.08, 0.3]
+    gs = GridSearchCV(SparseGroupLasso(groups=groups, l1_ratio=0.4, standardize=True, fit_intercept=True),
+                      {"alpha": alphas}, cv=3).fit(X, y)
+    assert gs.batched_ and (gs.solver_info_["status"] == 0).all()
+    ref = _cv_reference("SparseGroupLasso", X, y, alphas, 3, groups=groups, l1_ratio=0.4, standardize=True,
+                        fit_intercept=True)
+    got = np.stack([gs.cv_results_[f"split{i}_test_score"] for i in range(3)], axis=1)
+    npt.assert_allclose(got, ref, rtol=1e-6, atol=1e-9)

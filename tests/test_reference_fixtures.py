@@ -50,8 +50,23 @@ def ref_id(case):
     return "-".join(tags) + f"-s{case['seed']}"
 
 
+_FITS = {}
+
+
+def _oracle_fit(case):
+    """The oracle's chain for one fixture case, inner solves run to stationarity (solver_tol < 0: a
+    duality gap of eps still leaves sqrt(eps) in the coefficients; the fixtures are stationary to
+    rounding).  Shared by the two tests below."""
+    key = ref_id(case)
+    if key not in _FITS:
+        X, y, sw = ref_data(case)
+        _FITS[key] = R.fit(case["estimator"], X, y, fit_intercept=case["fit_intercept"], sample_weight=sw,
+                           solver_tol=-1.0, max_sweeps=5000000, return_details=True, **ref_kwargs(case))
+    return _FITS[key]
+
+
 def test_fixture_file_is_certified():
-    assert len(REF["cases"]) >= 50
+    assert len(REF["cases"]) >= 56
     assert REF["worst_kkt_rel"] <= 1e-12
     names = {c["estimator"] for c in REF["cases"]}
     assert names == R.ESTIMATORS
@@ -61,10 +76,7 @@ def test_fixture_file_is_certified():
 def test_oracle_chain_matches_reference_code(case):
     X, y, sw = ref_data(case)
     kw = ref_kwargs(case)
-    # solver_tol < 0: the oracle iterates until a sweep cannot move the iterate (a duality gap of
-    # eps still leaves sqrt(eps) in the coefficients; the fixtures are stationary to rounding)
-    b, icpt, det = R.fit(case["estimator"], X, y, fit_intercept=case["fit_intercept"], sample_weight=sw,
-                         solver_tol=-1.0, max_sweeps=5000000, return_details=True, **kw)
+    b, icpt, det = _oracle_fit(case)
     ref = np.array(case["coef"])
     scale = max(np.abs(ref).max(), 1e-12)
     assert np.abs(b - ref).max() <= 1e-9 * scale + 1e-13
@@ -91,8 +103,14 @@ def test_oracle_objective_is_the_reference_objective(case):
     the oracle's certified minimiser  =>  a minimiser of the reference's problem."""
     X, y, sw = ref_data(case)
     kw = ref_kwargs(case)
-    _, _, det = R.fit(case["estimator"], X, y, fit_intercept=case["fit_intercept"], sample_weight=sw,
-                      return_details=True, **kw)
+    _, _, det = _oracle_fit(case)
+    if det.get("sgl_standardized"):
+        # l1 on b with ||X_g b_g|| group norms: evaluated directly on the preprocessed design
+        Xp, yp, _, _ = R.preprocess(X, y, sw, case["fit_intercept"])
+        for probe in case["objective_probes"]:
+            val = R.objective_sgl_standardized(Xp, yp, np.array(probe["beta"]), det["labels"], det["w1"], det["w2"])
+            assert abs(val - probe["objective"]) <= 1e-11 * max(1.0, abs(probe["objective"]))
+        return
     ps = det["pen_scale"]
     labels, G = det["labels"], len(det["w2"])
     standardized = bool(kw.get("standardize")) and case["estimator"].replace("Adaptive", "") != "Lasso"
