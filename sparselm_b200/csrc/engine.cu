@@ -1874,7 +1874,6 @@ size_t slm_newton_workspace(int64_t p, int32_t n_groups, int32_t k, int n_folds)
     const size_t ldz = (size_t)round_up(k, 8);
     size_t d = kk * ldh * ldh;                          // H
     d += kk * (size_t)nw_panels(p) * NW_NB * NW_NB;     // inverses of the diagonal blocks
-    d += 2 * kk * NW_NB * ldh;                          // panel, transposed (+ negated): GEMM operands
     d += 6 * kk * ldh;                                  // U, KK, DP, GS, GRAD, DIR
     d += (size_t)round_up((int64_t)(kk * (size_t)n_groups), 2);  // NRM (even: what follows stays 16-byte aligned)
     d += 2 * (size_t)n_folds * (size_t)p * ldz;         // Z, GZ of the Gram apply
@@ -1897,9 +1896,7 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
     const int npan = nw_panels(p);
     double* H = (double*)work;
     double* INV = H + (size_t)k * ldh * ldh;
-    double* PT = INV + (size_t)k * npan * NW_NB * NW_NB;
-    double* NPT = PT + (size_t)k * NW_NB * ldh;
-    double* U = NPT + (size_t)k * NW_NB * ldh;
+    double* U = INV + (size_t)k * npan * NW_NB * NW_NB;
     double* KK = U + (size_t)k * ldv;
     double* DP = KK + (size_t)k * ldv;
     double* GS = DP + (size_t)k * ldv;
@@ -1923,7 +1920,6 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
     CUDA_OK(cudaMemcpyAsync(fold_dev, fs.data(), sizeof(int32_t) * 2 * (size_t)k, cudaMemcpyHostToDevice, s));
     CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int) * (size_t)k, s));
     CUDA_OK(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)n_folds * p * ldz, s));
-    CUDA_OK(cudaMemsetAsync(PT, 0, sizeof(double) * 2 * (size_t)k * NW_NB * ldh, s));
 
     static bool attr_done = false;
     if (!attr_done) {
@@ -1952,25 +1948,26 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
         const int64_t rows = p - j0 - nb;
         if (rows <= 0) break;
         const dim3 pgrid((unsigned)((rows + NW_NB - 1) / NW_NB), (unsigned)k);
-        chol_panel_kernel<<<pgrid, NW_T, NW_TILE_SMEM, s>>>(H, ldh, (int)p, j0, nb, INV, npan, pn, PT, NPT, ldh);
+        chol_panel_kernel<<<pgrid, NW_T, NW_TILE_SMEM, s>>>(H, ldh, (int)p, j0, nb, INV, npan, pn);
         LAUNCH_OK("chol_panel_kernel");
-        // trailing update H22 -= L21 L21' on the tensor-core GEMM: C += (-L21')' (L21')
+        // trailing update H22 -= U12' U12 on the tensor-core GEMM: the 64 panel rows are the K-major
+        // operand as they lie in H (SYM: P == Q; negated product; upper tiles only)
         for (int c0 = 0; c0 < k; c0 += kMaxGemmProblems) {
             const int nc = std::min<int>(k - c0, kMaxGemmProblems);
             GemmBatch b;
             memset(&b, 0, sizeof(b));
             b.n_problems = nc;
             b.accumulate = 1;
+            b.negate = 1;
+            b.upper_only = 1;
             for (int i = 0; i < nc; ++i) {
                 const int64_t c = c0 + i, off = j0 + nb;
                 GemmProblem& pr = b.pr[i];
-                pr.P = NPT + c * NW_NB * ldh + off;
-                pr.Q = PT + c * NW_NB * ldh + off;
+                pr.P = pr.Q = H + c * ldh * ldh + (int64_t)j0 * ldh + off;
                 pr.C = H + c * ldh * ldh + off * ldh + off;
-                pr.ldp = pr.ldq = ldh;
-                pr.ldc = ldh;
+                pr.ldp = pr.ldq = pr.ldc = ldh;
                 pr.qlim = (int)(ldh - off);
-                pr.M = pr.N = (int)round_up(rows, 2);  // an odd tail adds the (zero) padding row / column
+                pr.M = pr.N = (int)round_up(rows, 2);  // an odd tail touches the (identity) padding row / column with zeros
                 pr.Kd = nb;
             }
             FamTimer tm(ctx, FAM_LIPS, s, 0.0);

@@ -77,6 +77,8 @@ struct GemmBatch {
     int* flags;  // one int per tile, zero on entry
     int n_flags;
     int accumulate;  // != 0: C += A B (the tile's first writer adds to what C holds)
+    int negate;      // != 0: the product enters with a minus sign (C -= A B with accumulate)
+    int upper_only;  // SYM: only the tiles tn >= tm are written, no mirrored copy (blocked Cholesky)
     // TMA kernels: base matrices of the P / Q operands of every problem and their row counts
     // (NULL: the batch can only run on the cp.async kernel)
     const double *baseP, *baseQ;
@@ -379,6 +381,10 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                 int col = n0 + (wn * NI + j) * 8 + lk * 2;
                 if (row < M && col < N) {  // N is even: col+1 < N too
                     double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    if (batch.negate) {
+                        v0 = -v0;
+                        v1 = -v1;
+                    }
                     double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
                     if (!first_writer || batch.accumulate) {
                         const double2 old = __ldcg(dst);
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                         v1 += old.y;
                     }
                     __stcg(dst, make_double2(v0, v1));
-                    if (SYM && tm != tn) {
+                    if (SYM && tm != tn && !batch.upper_only) {
                         // mirrored copy: same value as the upper entry (kept bit-identical)
                         __stcg(C + (long long)col * ldc + row, v0);
                         __stcg(C + (long long)(col + 1) * ldc + row, v1);

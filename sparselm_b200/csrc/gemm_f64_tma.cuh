@@ -479,6 +479,10 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
                 const int col = n0 + (wn * NI + j) * 8 + lk * 2;
                 if (row < M && col < N) {
                     double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                    if (batch.negate) {
+                        v0 = -v0;
+                        v1 = -v1;
+                    }
                     double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
                     if (!first_writer || batch.accumulate) {
                         const double2 old = __ldcg(dst);
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
                         v1 += old.y;
                     }
                     __stcg(dst, make_double2(v0, v1));
-                    if (SYM && tm != tn) {
+                    if (SYM && tm != tn && !batch.upper_only) {
                         __stcg(C + (long long)col * ldc + row, v0);
                         __stcg(C + (long long)(col + 1) * ldc + row, v1);
                     }

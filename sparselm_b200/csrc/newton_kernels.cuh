@@ -1,8 +1,8 @@
 // Second-order phase of the batched solve (ill-conditioned pure-group problems, DESIGN section 2
 // item 13): one lock-step damped Newton step on the active groups of k slow columns, entirely in
 // this file's kernels -- Hessian assembly straight from the Gram, a batched blocked Cholesky
-// factorisation (64-wide panels: diagonal block factored and inverted in shared memory, panel
-// through the inverse, trailing update on the FP64 tensor-core GEMM of gemm_f64.cuh), blocked
+// factorisation H = U'U (64-wide panels: diagonal block factored and inverted in shared memory, the row
+// panel through the inverse, trailing update on the FP64 tensor-core GEMM straight from those rows), blocked
 // triangular solves, and the Armijo line search with objective differences formed without
 // cancellation.  (Round 1 did these steps with torch operations and cuSOLVER's potrf.)
 //
@@ -11,7 +11,7 @@
 //     grad   = (Gx - c)/n + w_g x_g/||x_g|| + d_g x_g
 //     H      = G_AA/n + blockdiag_g( w_g/||x_g|| (I - u_g u_g') ) + diag(d),   u_g = x_g/||x_g||
 // Layouts: X, GX, U, KK, DP, GRAD, DIR are [k][ldv] (one row per column, solver feature order);
-// H is [k][ldh][ldh] row-major, lower triangle = the factor after factorisation; group tables W2,
+// H is [k][ldh][ldh] row-major, upper triangle = the factor U after factorisation; group tables W2,
 // D2, NRM are [k][Gn].
 #pragma once
 #include <cuda_runtime.h>
@@ -132,9 +132,15 @@ __global__ void __launch_bounds__(NW_T) newton_hessian_kernel(int p, const doubl
     Hc[(long long)i * ldh + j] = v;
 }
 
-// ---- blocked Cholesky ------------------------------------------------------------------------------
-// diagonal block [j0, j0+nb): factor in shared memory, write L (lower) back, invert it, keep the
-// inverse in INV[c][panel][NB][NB] (row-major, lower triangular).  info[c] != 0: not positive definite.
+// ---- blocked Cholesky, upper form H = U'U ------------------------------------------------------
+// Working on the UPPER triangle of the row-major matrix keeps every bulk access on contiguous row
+// segments: the panel to the right of a diagonal block is 64 full rows, and those rows ARE the
+// K-major operands of the trailing update  H22 -= U12' U12  on the tensor-core GEMM (SYM, negate,
+// upper tiles only: no transposed copies, no mirrored scattered stores).
+//
+// diagonal block [j0, j0+nb): factor in shared memory (A = U'U, U upper), write U back, invert it,
+// keep the inverse in INV[c][panel][NB][NB] (row-major, upper triangular).  info[c] != 0: not
+// positive definite.
 __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H, long long ldh, int j0, int nb,
                                                          double* __restrict__ INV, int npanels, int panel,
                                                          int* __restrict__ info) {
@@ -145,9 +151,11 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
     const int c = blockIdx.x, tid = threadIdx.x;
     double* Hc = H + (long long)c * ldh * ldh + (long long)j0 * ldh + j0;
     if (tid == 0) bad = 0;
+    // S holds the block TRANSPOSED (S[j][i] = A[i][j], i <= j): the factorisation below is the
+    // familiar lower one on S, i.e. S = U'
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) {
-        const int i = e / NW_NB, j = e % NW_NB;
-        S[i][j] = (i < nb && j < nb && j <= i) ? Hc[(long long)i * ldh + j] : (i == j ? 1.0 : 0.0);
+        const int i = e / NW_NB, j = e % NW_NB;  // consecutive threads: consecutive columns of a row (coalesced)
+        S[j][i] = (i < nb && j < nb && i <= j) ? Hc[(long long)i * ldh + j] : (i == j ? 1.0 : 0.0);
     }
     __syncthreads();
     for (int k = 0; k < nb; ++k) {
@@ -160,8 +168,7 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
         if (tid == 0) S[k][k] = sq;
         for (int i = k + 1 + tid; i < nb; i += NW_T) S[i][k] /= sq;
         __syncthreads();
-        // trailing update of the lower triangle: S[i][j] -= S[i][k] S[j][k], k < j <= i < nb
-        // (threads as a 16 x 16 patch stepping over the triangle: no integer division in the loop)
+        // trailing update of the lower triangle of S (threads as a 16 x 16 patch: no integer division)
         for (int i = k + 1 + (tid >> 4); i < nb; i += 16) {
             const double sik = S[i][k];
             for (int j = k + 1 + (tid & 15); j <= i; j += 16) S[i][j] -= sik * S[j][k];
@@ -170,63 +177,58 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
     }
     for (int e = tid; e < nb * nb; e += NW_T) {
         const int i = e / nb, j = e % nb;
-        if (j <= i) Hc[(long long)i * ldh + j] = S[i][j];
+        if (i <= j) Hc[(long long)i * ldh + j] = S[j][i];  // U[i][j] = S[j][i]
     }
-    // V = L^{-1}: column q by forward substitution (thread q), rows sequential
+    // V = S^{-1} (lower) = U^{-T}: column q by forward substitution (thread q)
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) V[e / NW_NB][e % NW_NB] = 0.0;
     __syncthreads();
     if (tid < nb) {
         const int q = tid;
         for (int i = q; i < nb; ++i) {
-            double s = (i == q) ? 1.0 : 0.0;
-            for (int m = q; m < i; ++m) s -= S[i][m] * V[m][q];
-            V[i][q] = s / S[i][i];
+            double a = (i == q) ? 1.0 : 0.0;
+            for (int m = q; m < i; ++m) a -= S[i][m] * V[m][q];
+            V[i][q] = a / S[i][i];
         }
     }
     __syncthreads();
+    // stored as U^{-1} (upper): INV[i][j] = V[j][i]
     double* out = INV + ((long long)c * npanels + panel) * NW_NB * NW_NB;
-    for (int e = tid; e < NW_NB * NW_NB; e += NW_T) out[e] = V[e / NW_NB][e % NW_NB];
+    for (int e = tid; e < NW_NB * NW_NB; e += NW_T) out[e] = V[e % NW_NB][e / NW_NB];
     if (tid == 0 && bad) info[c] = 1;
 }
 
-// panel below the diagonal block: L21 = A21 L11^{-T}, i.e. out[r][q] = sum_{m <= q} A[r][m] inv[q][m].
-// Written in place and, transposed, into the GEMM operands of the trailing update:
-// PT[c][q][r] = out, NPT[c][q][r] = -out (row r counted from the top of the matrix).
+// panel to the right of the diagonal block, in place: U12 = U11^{-T} A12, i.e.
+// out[q][x] = sum_{m <= q} inv[m][q] A[m][x]  (inv = U11^{-1}, upper).  One block per 64 columns.
 __global__ void __launch_bounds__(NW_T) chol_panel_kernel(double* __restrict__ H, long long ldh, int p, int j0, int nb,
-                                                          const double* __restrict__ INV, int npanels, int panel,
-                                                          double* __restrict__ PT, double* __restrict__ NPT,
-                                                          long long ldpt) {
+                                                          const double* __restrict__ INV, int npanels, int panel) {
     extern __shared__ double nw_sh[];
     double (*A)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh);
     double (*Vi)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh + NW_NB * (NW_NB + 1));
     const int c = blockIdx.y, tid = threadIdx.x;
-    const int r0 = j0 + nb + blockIdx.x * NW_NB;  // first row of this tile
-    if (r0 >= p) return;
-    const int nr = min(NW_NB, p - r0);
+    const int x0 = j0 + nb + blockIdx.x * NW_NB;  // first column of this tile
+    if (x0 >= p) return;
+    const int nx = min(NW_NB, p - x0);
     double* Hc = H + (long long)c * ldh * ldh;
     const double* inv = INV + ((long long)c * npanels + panel) * NW_NB * NW_NB;
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) {
-        const int i = e / NW_NB, j = e % NW_NB;
-        A[i][j] = (i < nr && j < nb) ? Hc[(long long)(r0 + i) * ldh + j0 + j] : 0.0;
-        Vi[i][j] = inv[e];
+        const int m = e / NW_NB, x = e % NW_NB;  // rows of the panel are contiguous: coalesced
+        A[m][x] = (m < nb && x < nx) ? Hc[(long long)(j0 + m) * ldh + x0 + x] : 0.0;
+        Vi[m][x] = inv[e];
     }
     __syncthreads();
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) {
-        const int r = e % NW_NB, q = e / NW_NB;  // consecutive threads: consecutive rows (coalesced PT writes)
-        if (r >= nr || q >= nb) continue;
-        double s = 0.0;
-        for (int m = 0; m <= q; ++m) s += A[r][m] * Vi[q][m];
-        Hc[(long long)(r0 + r) * ldh + j0 + q] = s;
-        const long long t = ((long long)c * NW_NB + q) * ldpt + r0 + r;
-        PT[t] = s;
-        NPT[t] = -s;
+        const int q = e / NW_NB, x = e % NW_NB;
+        if (q >= nb || x >= nx) continue;
+        double a = 0.0;
+        for (int m = 0; m <= q; ++m) a += Vi[m][q] * A[m][x];
+        Hc[(long long)(j0 + q) * ldh + x0 + x] = a;
     }
 }
 
-// solve L L' d = rhs for every column with the blocked factor: forward (y = L^{-1} rhs) and backward
-// (d = L^{-T} y) substitution by panels; the diagonal blocks through their stored inverses.
-// rhs = -GRAD; DIR receives d (inactive coordinates: rhs = 0 -> d = 0).  A warp reads contiguous
-// row segments of the factor (lanes over columns), partial sums meet in shared memory.
+// solve U'U d = rhs for every column with the blocked factor: forward (U'y = rhs) and backward (U d = y)
+// substitution by panels; the diagonal blocks through their stored inverses.  rhs = -GRAD; DIR
+// receives d (inactive coordinates: rhs = 0 -> d = 0).  A warp reads contiguous row segments of the
+// factor (lanes over columns), partial sums meet in shared memory.
 __global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restrict__ H, long long ldh, int p,
                                                           const double* __restrict__ INV, int npanels,
                                                           const double* __restrict__ GRAD, double* __restrict__ DIR,
@@ -240,31 +242,11 @@ __global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restri
     const double* Hc = H + (long long)c * ldh * ldh;
     for (int j = tid; j < p; j += NW_T) y[j] = -GRAD[(long long)c * ldv + j];
     __syncthreads();
-    // forward: t = rhs_j - L[j-rows, 0:j0] y[0:j0]; y_j = inv_jj t
+    // forward: y_j = U_jj^{-T} (rhs_j - sum_{i < j} U[i-rows][j-cols]' y_i)
     for (int pn = 0; pn < npanels; ++pn) {
         const int j0 = pn * NW_NB, nb = min(NW_NB, p - j0);
-        for (int r = warp; r < nb; r += NWARP) {
-            const double* row = Hc + (long long)(j0 + r) * ldh;
-            double acc = 0.0;
-            for (int m = lane; m < j0; m += 32) acc += row[m] * y[m];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) t[r] = y[j0 + r] - acc;
-        }
-        __syncthreads();
-        const double* inv = INV + ((long long)c * npanels + pn) * NW_NB * NW_NB;
-        double s = 0.0;
-        if (tid < nb)
-            for (int m = 0; m <= tid; ++m) s += inv[tid * NW_NB + m] * t[m];
-        __syncthreads();
-        if (tid < nb) y[j0 + tid] = s;
-        __syncthreads();
-    }
-    // backward: d_j = inv_jj' (y_j - sum_{i > j} L[i][j-cols]' d_i)
-    for (int pn = npanels - 1; pn >= 0; --pn) {
-        const int j0 = pn * NW_NB, nb = min(NW_NB, p - j0);
         double a0 = 0.0, a1 = 0.0;  // columns j0 + lane, j0 + lane + 32
-        for (int i = j0 + nb + warp; i < p; i += NWARP) {
+        for (int i = warp; i < j0; i += NWARP) {
             const double* row = Hc + (long long)i * ldh + j0;
             const double yi = y[i];
             if (lane < nb) a0 += row[lane] * yi;
@@ -281,11 +263,31 @@ __global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restri
         }
         __syncthreads();
         const double* inv = INV + ((long long)c * npanels + pn) * NW_NB * NW_NB;
-        double s = 0.0;
+        double a = 0.0;
         if (tid < nb)
-            for (int m = tid; m < nb; ++m) s += inv[m * NW_NB + tid] * t[m];
+            for (int m = 0; m <= tid; ++m) a += inv[m * NW_NB + tid] * t[m];  // (U^{-T} t)_q = sum_{m <= q} inv[m][q] t_m
         __syncthreads();
-        if (tid < nb) y[j0 + tid] = s;
+        if (tid < nb) y[j0 + tid] = a;
+        __syncthreads();
+    }
+    // backward: d_j = U_jj^{-1} (y_j - U[j-rows][right cols] d_right)
+    for (int pn = npanels - 1; pn >= 0; --pn) {
+        const int j0 = pn * NW_NB, nb = min(NW_NB, p - j0);
+        for (int r = warp; r < nb; r += NWARP) {
+            const double* row = Hc + (long long)(j0 + r) * ldh;
+            double acc = 0.0;
+            for (int m = j0 + nb + lane; m < p; m += 32) acc += row[m] * y[m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) t[r] = y[j0 + r] - acc;
+        }
+        __syncthreads();
+        const double* inv = INV + ((long long)c * npanels + pn) * NW_NB * NW_NB;
+        double a = 0.0;
+        if (tid < nb)
+            for (int m = tid; m < nb; ++m) a += inv[tid * NW_NB + m] * t[m];  // upper: row q, columns m >= q
+        __syncthreads();
+        if (tid < nb) y[j0 + tid] = a;
         __syncthreads();
     }
     for (int j = tid; j < p; j += NW_T) DIR[(long long)c * ldv + j] = y[j];
