@@ -241,15 +241,16 @@ static bool make_map(slm_ctx* ctx, CUtensorMap* map, const double* base, long lo
     return r == CUDA_SUCCESS;
 }
 
-// can this batch run on the TMA kernels?  Fills prow0 / qrow0 / qcol0 of every problem.
+// can this batch run on the TMA kernels?  Fills prow0 / pcol0 / qrow0 / qcol0 of every problem.
 static bool tma_prepare(slm_ctx* ctx, GemmBatch& b, int family_bit) {
     if (!(ctx->tma_mask & family_bit) || !ctx->encode || !b.baseP || !b.baseQ) return false;
     for (int i = 0; i < b.n_problems; ++i) {
         GemmProblem& pr = b.pr[i];
         if (pr.ldp != b.pr[0].ldp || pr.ldq != b.pr[0].ldq) return false;
         const long long dp = pr.P - b.baseP, dq = pr.Q - b.baseQ;
-        if (dp < 0 || dq < 0 || dp % pr.ldp != 0) return false;
+        if (dp < 0 || dq < 0 || ((dp % pr.ldp) & 1) || ((dq % pr.ldq) & 1)) return false;  // box starts are 16-byte aligned
         pr.prow0 = (int)(dp / pr.ldp);
+        pr.pcol0 = (int)(dp % pr.ldp);
         pr.qrow0 = (int)(dq / pr.ldq);
         pr.qcol0 = (int)(dq % pr.ldq);
         if ((long long)pr.prow0 + pr.Kd > (1LL << 30) || (long long)pr.qrow0 + pr.Kd > (1LL << 30)) return false;
@@ -1877,7 +1878,7 @@ size_t slm_newton_workspace(int64_t p, int32_t n_groups, int32_t k, int n_folds)
     d += 6 * kk * ldh;                                  // U, KK, DP, GS, GRAD, DIR
     d += (size_t)round_up((int64_t)(kk * (size_t)n_groups), 2);  // NRM (even: what follows stays 16-byte aligned)
     d += 2 * (size_t)n_folds * (size_t)p * ldz;         // Z, GZ of the Gram apply
-    return d * sizeof(double) + (3 * kk + 64) * sizeof(int) + 256;
+    return d * sizeof(double) + (4 * kk + kk * ldh + 64) * sizeof(int) + 256;  // fold, slot, info, MS, ACT
 }
 
 int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa, int64_t p, int n_folds,
@@ -1892,11 +1893,10 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
         return fail(ctx, 1, "slm_newton_step: workspace too small");
     if (n_groups > 6000) return fail(ctx, 1, "slm_newton_step: too many groups for the line-search kernel");
     cudaStream_t s = (cudaStream_t)stream;
-    const int64_t ldh = nw_ldh(p), ldv = ldh, ldz = round_up(k, 8);
-    const int npan = nw_panels(p);
+    const int64_t ldv = nw_ldh(p), ldz = round_up(k, 8);
     double* H = (double*)work;
-    double* INV = H + (size_t)k * ldh * ldh;
-    double* U = INV + (size_t)k * npan * NW_NB * NW_NB;
+    double* INV = H + (size_t)k * ldv * ldv;
+    double* U = INV + (size_t)k * nw_panels(p) * NW_NB * NW_NB;
     double* KK = U + (size_t)k * ldv;
     double* DP = KK + (size_t)k * ldv;
     double* GS = DP + (size_t)k * ldv;
@@ -1908,6 +1908,8 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
     int* fold_dev = (int*)(GZ + (size_t)n_folds * p * ldz);
     int* slot_dev = fold_dev + k;
     int* info = slot_dev + k;
+    int* MS = info + k;      // active coordinates per column
+    int* ACT = MS + k;       // [k][ldv] their indices, ascending
 
     // columns of a fold take consecutive slots of that fold's block in the apply layout
     std::vector<int32_t> fs(2 * (size_t)k), Kf(n_folds, 0);
@@ -1929,54 +1931,80 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
         attr_done = true;
     }
     const dim3 vgrid((unsigned)((p + NW_T - 1) / NW_T), (unsigned)k);
-    newton_prepare_kernel<<<k, NW_T, 0, s>>>((int)p, n_groups, gptr, X, ldv, W2, D2, NRM, U, KK, DP);
+    newton_prepare_kernel<<<k, NW_T, 0, s>>>((int)p, n_groups, gptr, X, ldv, W2, D2, NRM, U, KK, DP, ACT, MS);
+    std::vector<int> ms((size_t)k);
+    CUDA_OK(cudaMemcpyAsync(ms.data(), MS, sizeof(int) * (size_t)k, cudaMemcpyDeviceToHost, s));
     newton_pack_kernel<<<vgrid, NW_T, 0, s>>>((int)p, fold_dev, slot_dev, X, ldv, Z, ldz);
     LAUNCH_OK("newton prepare/pack kernels");
     if (int rc = apply_batched(ctx, G, g_stride, pa, p, n_folds, Kf.data(), Z, ldz, GZ, s, -1.0, FAM_LIPS)) return rc;
     newton_grad_kernel<<<vgrid, NW_T, 0, s>>>((int)p, G, g_stride, pa, fold_dev, slot_dev, nobs_dev, X, GZ, ldz, ldv, KK,
                                               DP, GS, GRAD);
-    const dim3 hgrid((unsigned)((ldh + NW_T - 1) / NW_T), (unsigned)ldh, (unsigned)k);
-    newton_hessian_kernel<<<hgrid, NW_T, 0, s>>>((int)p, G, g_stride, pa, fold_dev, nobs_dev, gid, U, KK, DP, ldv, H, ldh);
+    // the host learns the matrix sizes (the gradient's Gram apply runs meanwhile): the factorisation works on
+    // the active coordinates of every column, sum_c m_c^3/3 flops instead of k p^3/3
+    CUDA_OK(cudaStreamSynchronize(s));
+    int m_max = 0;
+    for (int c = 0; c < k; ++c) m_max = std::max(m_max, ms[c]);
+    const int64_t ldh = std::max<int64_t>(8, nw_ldh(m_max));
+    const int npan = std::max(1, nw_panels(m_max));
+    if (m_max > 0) {
+        const dim3 hgrid((unsigned)((ldh + NW_T - 1) / NW_T), (unsigned)ldh, (unsigned)k);
+        newton_hessian_kernel<<<hgrid, NW_T, 0, s>>>((int)p, G, g_stride, pa, fold_dev, nobs_dev, gid, U, KK, DP, ldv, ACT, MS,
+                                                     H, ldh);
+    }
     LAUNCH_OK("newton grad/hessian kernels");
     ctx->launches += 3;
 
-    // blocked Cholesky, all k matrices in lock step
+    // blocked Cholesky, all k matrices in lock step (a matrix that ended before the panel sits out)
     for (int pn = 0; pn < npan; ++pn) {
-        const int j0 = pn * NW_NB, nb = (int)std::min<int64_t>(NW_NB, p - j0);
-        chol_diag_kernel<<<k, NW_T, NW_TILE_SMEM, s>>>(H, ldh, j0, nb, INV, npan, pn, info);
+        const int j0 = pn * NW_NB;
+        chol_diag_kernel<<<k, NW_T, NW_TILE_SMEM, s>>>(H, ldh, j0, MS, INV, npan, pn, info);
         LAUNCH_OK("chol_diag_kernel");
-        const int64_t rows = p - j0 - nb;
-        if (rows <= 0) break;
-        const dim3 pgrid((unsigned)((rows + NW_NB - 1) / NW_NB), (unsigned)k);
-        chol_panel_kernel<<<pgrid, NW_T, NW_TILE_SMEM, s>>>(H, ldh, (int)p, j0, nb, INV, npan, pn);
+        const int64_t rows_max = (int64_t)m_max - j0 - NW_NB;
+        if (rows_max <= 0) break;
+        const dim3 pgrid((unsigned)((rows_max + NW_NB - 1) / NW_NB), (unsigned)k);
+        chol_panel_kernel<<<pgrid, NW_T, NW_TILE_SMEM, s>>>(H, ldh, j0, MS, INV, npan, pn);
         LAUNCH_OK("chol_panel_kernel");
         // trailing update H22 -= U12' U12 on the tensor-core GEMM: the 64 panel rows are the K-major
         // operand as they lie in H (SYM: P == Q; negated product; upper tiles only)
-        for (int c0 = 0; c0 < k; c0 += kMaxGemmProblems) {
-            const int nc = std::min<int>(k - c0, kMaxGemmProblems);
-            GemmBatch b;
-            memset(&b, 0, sizeof(b));
-            b.n_problems = nc;
-            b.accumulate = 1;
-            b.negate = 1;
-            b.upper_only = 1;
-            for (int i = 0; i < nc; ++i) {
-                const int64_t c = c0 + i, off = j0 + nb;
-                GemmProblem& pr = b.pr[i];
-                pr.P = pr.Q = H + c * ldh * ldh + (int64_t)j0 * ldh + off;
-                pr.C = H + c * ldh * ldh + off * ldh + off;
-                pr.ldp = pr.ldq = pr.ldc = ldh;
-                pr.qlim = (int)(ldh - off);
-                pr.M = pr.N = (int)round_up(rows, 2);  // an odd tail touches the (identity) padding row / column with zeros
-                pr.Kd = nb;
-            }
+        GemmBatch b;
+        int np_ = 0;
+        auto flush = [&]() -> int {
+            if (np_ == 0) return 0;
+            b.n_problems = np_;
+            b.baseP = b.baseQ = H;
+            b.rowsP = b.rowsQ = (int64_t)k * ldh;
             FamTimer tm(ctx, FAM_LIPS, s, 0.0);
-            cudaError_t e = launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
+            // TMA-fed like the Gram build (the producer warp runs ahead into the next tile's panel rows while
+            // the consumers are in the epilogue of the current one); cp.async kernel when TMA is switched off
+            cudaError_t e = tma_prepare(ctx, b, 1) ? launch_gemm_tma_t<2, 4, 8, 4, true, 1, false, 32, 3>(ctx, b, s)
+                                                   : launch_gemm_t<2, 4, 8, 4, false, true, 1>(ctx, b, s);
             if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("newton trailing update: ") + cudaGetErrorString(e));
             ctx->launches++;
+            np_ = 0;
+            return 0;
+        };
+        for (int c = 0; c < k; ++c) {
+            const int64_t off = j0 + NW_NB, rows = (int64_t)ms[c] - off;
+            if (rows <= 0) continue;
+            if (np_ == 0) {
+                memset(&b, 0, sizeof(b));
+                b.accumulate = 1;
+                b.negate = 1;
+                b.upper_only = 1;
+            }
+            GemmProblem& pr = b.pr[np_++];
+            pr.P = pr.Q = H + (int64_t)c * ldh * ldh + (int64_t)j0 * ldh + off;
+            pr.C = H + (int64_t)c * ldh * ldh + off * ldh + off;
+            pr.ldp = pr.ldq = pr.ldc = ldh;
+            pr.qlim = (int)(ldh - off);
+            pr.M = pr.N = (int)round_up(rows, 2);  // an odd tail touches the (identity) padding row / column with zeros
+            pr.Kd = NW_NB;
+            if (np_ == kMaxGemmProblems)
+                if (int rc = flush()) return rc;
         }
+        if (int rc = flush()) return rc;
     }
-    const size_t solve_smem = sizeof(double) * ((size_t)ldh + NW_NB + (NW_T / 32) * NW_NB);
+    const size_t solve_smem = sizeof(double) * ((size_t)ldh + NW_NB + (NW_TS / 32) * NW_NB);
     if (solve_smem > 98304 || 2 * sizeof(double) * (size_t)n_groups > 98304)
         return fail(ctx, 1, "slm_newton_step: design too large for the solve / line-search kernels");
     static bool attr2 = false;
@@ -1984,7 +2012,7 @@ int slm_newton_step(slm_ctx* ctx, const double* G, int64_t g_stride, int64_t pa,
         CUDA_OK(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304));
         attr2 = true;
     }
-    chol_solve_kernel<<<k, NW_T, solve_smem, s>>>(H, ldh, (int)p, INV, npan, GRAD, DIR, ldv);
+    chol_solve_kernel<<<k, NW_TS, solve_smem, s>>>(H, ldh, (int)p, ACT, MS, INV, npan, GRAD, DIR, ldv);
     newton_linesearch_kernel<<<k, NW_T, 2 * sizeof(double) * (size_t)n_groups, s>>>(
         (int)p, n_groups, gptr, X, DIR, GS, GRAD, U, KK, DP, ldv, W2, NRM, info, out);
     LAUNCH_OK("newton solve / line-search kernels");

@@ -60,7 +60,7 @@ struct GemmProblem {
     int tile_begin;  // first global tile index of this problem
     // TMA kernels (gemm_f64_tma.cuh): the operands are addressed through tensor maps over the whole
     // matrices baseP / baseQ of the batch; a problem starts at these rows / this column of them
-    int prow0, qrow0, qcol0;
+    int prow0, qrow0, qcol0, pcol0;
 };
 
 struct GemmBatch {

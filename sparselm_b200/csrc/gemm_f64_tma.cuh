@@ -117,7 +117,7 @@ struct TmaCfg {
 // A operand K-major only (Gram build, Gram apply).  SYM / KSPARSE as in gemm_f64_kernel.
 // mapP / mapQ: 2-D tensor maps over the whole operand matrices (P: [rows][ldp], Q: [rows][ldq]),
 // box [BK][16] for the tiled mode, [1][16] for the gather mode.  A problem addresses its rows
-// through prow0 / qrow0 and its Q columns through qcol0.
+// through prow0 / qrow0 and its first P / Q columns through pcol0 / qcol0.
 template <int WARPS_M, int WARPS_N, int MI, int NI, int BK, int STAGES, bool SYM, int MINB, bool KSPARSE, bool WIDE>
 __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
     gemm_f64_tma_kernel(const __grid_constant__ GemmBatch batch, const __grid_constant__ CUtensorMap mapP,
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             const GemmProblem& pr = batch.pr[sg.pi];
             int tm, tn;
             tile_coords(pr, sg.tl, tm, tn);
-            const int m0 = tm * BM, n0 = pr.qcol0 + tn * BN;
+            const int m0 = pr.pcol0 + tm * BM, n0 = pr.qcol0 + tn * BN;
             const int prow0 = pr.prow0, qrow0 = pr.qrow0;
             const int* __restrict__ kidx = pr.kidx;
 #pragma unroll 1

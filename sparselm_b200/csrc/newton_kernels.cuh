@@ -10,9 +10,12 @@
 //     phi(x) = 1/(2n) x'Gx - c'x/n + sum_g w_g ||x_g|| + 1/2 sum_g d_g ||x_g||^2
 //     grad   = (Gx - c)/n + w_g x_g/||x_g|| + d_g x_g
 //     H      = G_AA/n + blockdiag_g( w_g/||x_g|| (I - u_g u_g') ) + diag(d),   u_g = x_g/||x_g||
-// Layouts: X, GX, U, KK, DP, GRAD, DIR are [k][ldv] (one row per column, solver feature order);
-// H is [k][ldh][ldh] row-major, upper triangle = the factor U after factorisation; group tables W2,
-// D2, NRM are [k][Gn].
+// The system is factored on the ACTIVE coordinates only: column c has m_c of them (ACT[c][0..m_c), ascending),
+// its matrix is the m_c x m_c compaction H[act][act] -- the factorisation costs sum_c m_c^3/3 instead of k p^3/3,
+// and every kernel of the panel loop takes the per-column size from MS[c].
+// Layouts: X, GX, U, KK, DP, GRAD, DIR are [k][ldv] (one row per column, solver feature order); ACT is
+// [k][ldv] int; H is [k][ldh][ldh] row-major over the compacted coordinates (ldh from the largest m_c), upper
+// triangle = the factor U after factorisation; group tables W2, D2, NRM are [k][Gn].
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -41,9 +44,12 @@ __global__ void __launch_bounds__(NW_T) newton_prepare_kernel(int p, int Gn, con
                                                               const double* __restrict__ X, long long ldv,
                                                               const double* __restrict__ W2, const double* __restrict__ D2,
                                                               double* __restrict__ NRM, double* __restrict__ U,
-                                                              double* __restrict__ KK, double* __restrict__ DP) {
+                                                              double* __restrict__ KK, double* __restrict__ DP,
+                                                              int* __restrict__ ACT, int* __restrict__ MS) {
     const int c = blockIdx.x;
     const double* x = X + (long long)c * ldv;
+    __shared__ int wtot[NW_T / 32];
+    __shared__ int base_s;
     for (int g = threadIdx.x; g < Gn; g += NW_T) {
         const int ja = gptr[g], jb = gptr[g + 1];
         double ss = 0.0;
@@ -65,6 +71,28 @@ __global__ void __launch_bounds__(NW_T) newton_prepare_kernel(int p, int Gn, con
             }
         }
     }
+    // ordered list of the active coordinates (block-wide compaction, 256 coordinates per round)
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();  // also orders the KK writes above before the reads below
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j0 = 0; j0 < p; j0 += NW_T) {
+        const int j = j0 + threadIdx.x;
+        const bool on = j < p && KK[(long long)c * ldv + j] >= 0.0;
+        const unsigned bal = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) wtot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s, tot = 0;
+#pragma unroll
+        for (int w = 0; w < NW_T / 32; ++w) {
+            if (w < warp) off += wtot[w];
+            tot += wtot[w];
+        }
+        if (on) ACT[(long long)c * ldv + off + __popc(bal & ((1u << lane) - 1u))] = j;
+        __syncthreads();
+        if (threadIdx.x == 0) base_s += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) MS[c] = base_s;
 }
 
 // X[c][j] -> Z[fold[c]][j][slot[c]] (the Gram apply's feature-major layout; Z zero-filled by the caller)
@@ -104,31 +132,32 @@ __global__ void __launch_bounds__(NW_T) newton_grad_kernel(int p, const double* 
     GRAD[e] = gs + (kk + DP[e]) * X[e];
 }
 
-// H[c][i][j] (all entries; symmetric)
+// H[c][i][j] over the compacted coordinates i, j < m_c (original indices ACT[c][i], ACT[c][j]): the upper
+// triangle and a band of 127 entries below the diagonal (the 128 x 128 diagonal tiles of the trailing updates
+// are read whole); identity on the padding up to the next multiple of 8.
 __global__ void __launch_bounds__(NW_T) newton_hessian_kernel(int p, const double* __restrict__ G, long long g_stride,
                                                               long long pa, const int* __restrict__ fold,
                                                               const double* __restrict__ nobs,
                                                               const int* __restrict__ gid, const double* __restrict__ U,
                                                               const double* __restrict__ KK, const double* __restrict__ DP,
-                                                              long long ldv, double* __restrict__ H, long long ldh) {
+                                                              long long ldv, const int* __restrict__ ACT,
+                                                              const int* __restrict__ MS, double* __restrict__ H,
+                                                              long long ldh) {
     const int c = blockIdx.z, i = blockIdx.y;
     const int j = blockIdx.x * NW_T + threadIdx.x;
-    if (j >= ldh || i >= ldh) return;
+    const int m = MS[c], mp = (m + 7) / 8 * 8;
+    if (j >= mp || i >= mp || j < i - 127) return;  // the 128 x 128 diagonal tiles of the trailing updates start at any multiple of 64
     double* Hc = H + (long long)c * ldh * ldh;
-    if (i >= p || j >= p) {  // padding rows / columns: identity
+    if (i >= m || j >= m) {  // padding rows / columns: identity
         Hc[(long long)i * ldh + j] = (i == j) ? 1.0 : 0.0;
         return;
     }
-    const long long ei = (long long)c * ldv + i, ej = (long long)c * ldv + j;
-    const double kki = KK[ei], kkj = KK[ej];
-    double v = 0.0;
-    if (kki >= 0.0 && kkj >= 0.0) {
-        v = G[(long long)fold[c] * g_stride + (long long)i * pa + j] / nobs[c];
-        if (gid[i] == gid[j]) v -= kki * U[ei] * U[ej];
-        if (i == j) v += kki + DP[ei];
-    } else if (i == j) {
-        v = 1.0;
-    }
+    const int oi = ACT[(long long)c * ldv + i], oj = ACT[(long long)c * ldv + j];
+    const long long ei = (long long)c * ldv + oi, ej = (long long)c * ldv + oj;
+    const double kki = KK[ei];
+    double v = G[(long long)fold[c] * g_stride + (long long)oi * pa + oj] / nobs[c];
+    if (gid[oi] == gid[oj]) v -= kki * U[ei] * U[ej];
+    if (i == j) v += kki + DP[ei];
     Hc[(long long)i * ldh + j] = v;
 }
 
@@ -141,56 +170,139 @@ __global__ void __launch_bounds__(NW_T) newton_hessian_kernel(int p, const doubl
 // diagonal block [j0, j0+nb): factor in shared memory (A = U'U, U upper), write U back, invert it,
 // keep the inverse in INV[c][panel][NB][NB] (row-major, upper triangular).  info[c] != 0: not
 // positive definite.
-__global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H, long long ldh, int j0, int nb,
-                                                         double* __restrict__ INV, int npanels, int panel,
-                                                         int* __restrict__ info) {
+//
+// The 64 x 64 block is itself factored by 16-wide sub-blocks so that the kernel is not a chain of 64
+// barrier-separated rank-1 steps: one warp factors a 16 x 16 diagonal sub-block in registers (row r in
+// lane r, columns exchanged by shuffles) and inverts it the same way; the whole CTA then applies that
+// inverse to the rows below and updates the rest (two small products, 4 barriers per sub-block).  The
+// inverse of the 64 x 64 factor is assembled from the four 16 x 16 inverses by block substitution.
+constexpr int NW_SB = 16;
+__global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H, long long ldh, int j0,
+                                                         const int* __restrict__ MS, double* __restrict__ INV,
+                                                         int npanels, int panel, int* __restrict__ info) {
     extern __shared__ double nw_sh[];
     double (*S)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh);
     double (*V)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh + NW_NB * (NW_NB + 1));
+    __shared__ double DI[NW_NB / NW_SB][NW_SB][NW_SB + 1];  // inverses of the diagonal sub-blocks (lower)
+    __shared__ double TT[3][NW_SB][NW_SB + 1];
     __shared__ int bad;
-    const int c = blockIdx.x, tid = threadIdx.x;
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = min(NW_NB, MS[c] - j0);
+    if (nb <= 0) return;  // this column's matrix ended before the panel
     double* Hc = H + (long long)c * ldh * ldh + (long long)j0 * ldh + j0;
     if (tid == 0) bad = 0;
     // S holds the block TRANSPOSED (S[j][i] = A[i][j], i <= j): the factorisation below is the
-    // familiar lower one on S, i.e. S = U'
+    // familiar lower one on S, i.e. S = L = U'.  Identity beyond nb.
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) {
         const int i = e / NW_NB, j = e % NW_NB;  // consecutive threads: consecutive columns of a row (coalesced)
         S[j][i] = (i < nb && j < nb && i <= j) ? Hc[(long long)i * ldh + j] : (i == j ? 1.0 : 0.0);
+        V[i][j] = 0.0;
     }
     __syncthreads();
-    for (int k = 0; k < nb; ++k) {
-        const double piv = S[k][k];
-        if (!(piv > 0.0)) {
-            if (tid == 0) bad = 1;
+    for (int kb = 0; kb < NW_NB / NW_SB; ++kb) {
+        const int b0 = kb * NW_SB;
+        if (warp == 0) {
+            const int r = lane & (NW_SB - 1);  // lanes 16..31 mirror lanes 0..15 (their results are not stored)
+            double d[NW_SB];
+#pragma unroll
+            for (int q = 0; q < NW_SB; ++q) d[q] = (q <= r) ? S[b0 + r][b0 + q] : 0.0;
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NW_SB; ++k) {
+                const double piv = __shfl_sync(0xffffffffu, d[k], k);
+                ok = ok && (piv > 0.0);
+                const double sq = piv > 0.0 ? sqrt(piv) : 1.0;
+                const double rs = 1.0 / sq;
+                if (r == k) d[k] = sq;
+                else if (r > k) d[k] *= rs;
+#pragma unroll
+                for (int q = k + 1; q < NW_SB; ++q) {
+                    const double lqk = __shfl_sync(0xffffffffu, d[k], q);
+                    if (r >= q) d[q] -= d[k] * lqk;
+                }
+            }
+            if (!ok && lane == 0) bad = 1;
+            if (lane < NW_SB) {
+#pragma unroll
+                for (int q = 0; q < NW_SB; ++q)
+                    if (q <= r) S[b0 + r][b0 + q] = d[q];
+            }
+            // inverse of the sub-block: lane r computes column r of L^{-1} by forward substitution
+            double x[NW_SB];
+#pragma unroll
+            for (int i = 0; i < NW_SB; ++i) {
+                const double lii = __shfl_sync(0xffffffffu, d[i], i);
+                double acc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+                for (int m = 0; m < i; ++m) {
+                    const double lim = __shfl_sync(0xffffffffu, d[m], i);
+                    acc -= lim * x[m];  // x[m] = 0 for m < r
+                }
+                x[i] = (i >= r) ? acc / lii : 0.0;
+            }
+            if (lane < NW_SB) {
+#pragma unroll
+                for (int i = 0; i < NW_SB; ++i) DI[kb][i][r] = x[i];
+            }
         }
         __syncthreads();
-        const double sq = piv > 0.0 ? sqrt(piv) : 1.0;
-        if (tid == 0) S[k][k] = sq;
-        for (int i = k + 1 + tid; i < nb; i += NW_T) S[i][k] /= sq;
-        __syncthreads();
-        // trailing update of the lower triangle of S (threads as a 16 x 16 patch: no integer division)
-        for (int i = k + 1 + (tid >> 4); i < nb; i += 16) {
-            const double sik = S[i][k];
-            for (int j = k + 1 + (tid & 15); j <= i; j += 16) S[i][j] -= sik * S[j][k];
+        const int below = NW_NB - b0 - NW_SB;  // rows under the sub-block
+        if (below > 0) {
+            // rows below: L[r][b0 + q] = sum_{m <= q} A[r][b0 + m] DI[q][m]   (A D^{-T})
+            double outv[3];
+            int cnt = 0;
+            for (int e = tid; e < below * NW_SB; e += NW_T, ++cnt) {
+                const int r = b0 + NW_SB + e / NW_SB, q = e % NW_SB;
+                double a = 0.0;
+                for (int m = 0; m <= q; ++m) a += S[r][b0 + m] * DI[kb][q][m];
+                outv[cnt] = a;
+            }
+            __syncthreads();
+            cnt = 0;
+            for (int e = tid; e < below * NW_SB; e += NW_T, ++cnt) S[b0 + NW_SB + e / NW_SB][b0 + e % NW_SB] = outv[cnt];
+            __syncthreads();
+            // rest of the block: S[r][q] -= sum_m L[r][b0 + m] L[q][b0 + m]  (lower triangle, r >= q)
+            for (int e = tid; e < below * below; e += NW_T) {
+                const int r = b0 + NW_SB + e / below, q = b0 + NW_SB + e % below;
+                if (q > r) continue;
+                double a = 0.0;
+#pragma unroll
+                for (int m = 0; m < NW_SB; ++m) a += S[r][b0 + m] * S[q][b0 + m];
+                S[r][q] -= a;
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
     for (int e = tid; e < nb * nb; e += NW_T) {
         const int i = e / nb, j = e % nb;
-        if (i <= j) Hc[(long long)i * ldh + j] = S[j][i];  // U[i][j] = S[j][i]
+        if (i <= j) Hc[(long long)i * ldh + j] = S[j][i];  // U[i][j] = L[j][i]
     }
-    // V = S^{-1} (lower) = U^{-T}: column q by forward substitution (thread q)
-    for (int e = tid; e < NW_NB * NW_NB; e += NW_T) V[e / NW_NB][e % NW_NB] = 0.0;
-    __syncthreads();
-    if (tid < nb) {
-        const int q = tid;
-        for (int i = q; i < nb; ++i) {
-            double a = (i == q) ? 1.0 : 0.0;
-            for (int m = q; m < i; ++m) a -= S[i][m] * V[m][q];
-            V[i][q] = a / S[i][i];
+    // V = L^{-1} (lower) by blocks: V_ii = DI_i, V_ij = -DI_i sum_{j <= m < i} L_im V_mj, by distance i - j
+    constexpr int NSB = NW_NB / NW_SB;
+    {
+        const int a = tid / NW_SB, b = tid % NW_SB;  // 256 threads = one 16 x 16 block
+        for (int i = 0; i < NSB; ++i) V[i * NW_SB + a][i * NW_SB + b] = DI[i][a][b];
+        __syncthreads();
+        for (int dist = 1; dist < NSB; ++dist) {
+            for (int j = 0; j + dist < NSB; ++j) {
+                const int i = j + dist;
+                double t = 0.0;
+                for (int m = j; m < i; ++m)
+#pragma unroll
+                    for (int q = 0; q < NW_SB; ++q) t += S[i * NW_SB + a][m * NW_SB + q] * V[m * NW_SB + q][j * NW_SB + b];
+                TT[j][a][b] = t;
+            }
+            __syncthreads();
+            for (int j = 0; j + dist < NSB; ++j) {
+                const int i = j + dist;
+                double v = 0.0;
+#pragma unroll
+                for (int q = 0; q < NW_SB; ++q) v += DI[i][a][q] * TT[j][q][b];
+                V[i * NW_SB + a][j * NW_SB + b] = -v;
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
     // stored as U^{-1} (upper): INV[i][j] = V[j][i]
     double* out = INV + ((long long)c * npanels + panel) * NW_NB * NW_NB;
     for (int e = tid; e < NW_NB * NW_NB; e += NW_T) out[e] = V[e % NW_NB][e / NW_NB];
@@ -199,12 +311,16 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
 
 // panel to the right of the diagonal block, in place: U12 = U11^{-T} A12, i.e.
 // out[q][x] = sum_{m <= q} inv[m][q] A[m][x]  (inv = U11^{-1}, upper).  One block per 64 columns.
-__global__ void __launch_bounds__(NW_T) chol_panel_kernel(double* __restrict__ H, long long ldh, int p, int j0, int nb,
-                                                          const double* __restrict__ INV, int npanels, int panel) {
+__global__ void __launch_bounds__(NW_T) chol_panel_kernel(double* __restrict__ H, long long ldh, int j0,
+                                                          const int* __restrict__ MS, const double* __restrict__ INV,
+                                                          int npanels, int panel) {
     extern __shared__ double nw_sh[];
     double (*A)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh);
     double (*Vi)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh + NW_NB * (NW_NB + 1));
     const int c = blockIdx.y, tid = threadIdx.x;
+    const int p = MS[c];
+    const int nb = min(NW_NB, p - j0);
+    if (nb <= 0) return;
     const int x0 = j0 + nb + blockIdx.x * NW_NB;  // first column of this tile
     if (x0 >= p) return;
     const int nx = min(NW_NB, p - x0);
@@ -226,24 +342,32 @@ __global__ void __launch_bounds__(NW_T) chol_panel_kernel(double* __restrict__ H
 }
 
 // solve U'U d = rhs for every column with the blocked factor: forward (U'y = rhs) and backward (U d = y)
-// substitution by panels; the diagonal blocks through their stored inverses.  rhs = -GRAD; DIR
-// receives d (inactive coordinates: rhs = 0 -> d = 0).  A warp reads contiguous row segments of the
-// factor (lanes over columns), partial sums meet in shared memory.
-__global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restrict__ H, long long ldh, int p,
-                                                          const double* __restrict__ INV, int npanels,
-                                                          const double* __restrict__ GRAD, double* __restrict__ DIR,
-                                                          long long ldv) {
-    extern __shared__ double sh[];  // y[ldh] + t[NB] + part[8][NB]
+// substitution by panels; the diagonal blocks through their stored inverses.  rhs = -GRAD on the active
+// coordinates; DIR receives d scattered back (inactive coordinates: 0).  A warp reads contiguous row segments
+// of the factor (lanes over columns), partial sums meet in shared memory.  One block of NW_TS threads per
+// column: the kernel streams m_c^2 x 8 bytes of the factor per column and is bound by the loads one block
+// keeps in flight.
+constexpr int NW_TS = 1024;
+__global__ void __launch_bounds__(NW_TS) chol_solve_kernel(const double* __restrict__ H, long long ldh, int pfull,
+                                                           const int* __restrict__ ACT, const int* __restrict__ MS,
+                                                           const double* __restrict__ INV, int npanels,
+                                                           const double* __restrict__ GRAD, double* __restrict__ DIR,
+                                                           long long ldv) {
+    extern __shared__ double sh[];  // y[ldh] + t[NB] + part[NWARP][NB]
     double* y = sh;
     double* t = sh + ldh;
     double* part = t + NW_NB;
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARP = NW_T / 32;
+    constexpr int NWARP = NW_TS / 32;
+    const int p = MS[c];
+    const int* act = ACT + (long long)c * ldv;
     const double* Hc = H + (long long)c * ldh * ldh;
-    for (int j = tid; j < p; j += NW_T) y[j] = -GRAD[(long long)c * ldv + j];
+    for (int j = tid; j < pfull; j += NW_TS) DIR[(long long)c * ldv + j] = 0.0;
+    for (int j = tid; j < p; j += NW_TS) y[j] = -GRAD[(long long)c * ldv + act[j]];
     __syncthreads();
+    const int np = (p + NW_NB - 1) / NW_NB;
     // forward: y_j = U_jj^{-T} (rhs_j - sum_{i < j} U[i-rows][j-cols]' y_i)
-    for (int pn = 0; pn < npanels; ++pn) {
+    for (int pn = 0; pn < np; ++pn) {
         const int j0 = pn * NW_NB, nb = min(NW_NB, p - j0);
         double a0 = 0.0, a1 = 0.0;  // columns j0 + lane, j0 + lane + 32
         for (int i = warp; i < j0; i += NWARP) {
@@ -271,7 +395,7 @@ __global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restri
         __syncthreads();
     }
     // backward: d_j = U_jj^{-1} (y_j - U[j-rows][right cols] d_right)
-    for (int pn = npanels - 1; pn >= 0; --pn) {
+    for (int pn = np - 1; pn >= 0; --pn) {
         const int j0 = pn * NW_NB, nb = min(NW_NB, p - j0);
         for (int r = warp; r < nb; r += NWARP) {
             const double* row = Hc + (long long)(j0 + r) * ldh;
@@ -290,7 +414,7 @@ __global__ void __launch_bounds__(NW_T) chol_solve_kernel(const double* __restri
         if (tid < nb) y[j0 + tid] = a;
         __syncthreads();
     }
-    for (int j = tid; j < p; j += NW_T) DIR[(long long)c * ldv + j] = y[j];
+    for (int j = tid; j < p; j += NW_TS) DIR[(long long)c * ldv + act[j]] = y[j];
 }
 
 // Armijo backtracking on phi(x + t d) - phi(x) (formed without cancellation), one block per column.

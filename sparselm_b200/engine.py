@@ -183,6 +183,9 @@ class Engine:
     LIPSCHITZ_ITERS = 12
     PIPELINE_BLOCK_BYTES = 64 << 20  # rows of a host design travel and enter the Gram in blocks of this size
     LIPSCHITZ_MARGIN = 1.10
+    # second-order phase (_run_batch): iterations before the first Newton phase / between two phases
+    NEWTON_FIRST = int(os.environ.get("SLM_NEWTON_FIRST", 500))
+    NEWTON_LATER = int(os.environ.get("SLM_NEWTON_LATER", 200))
 
     def __init__(self, device: int | None = None):
         import torch
@@ -908,7 +911,7 @@ class Engine:
         torch = self.torch
         F, ldz, p, Ks = nctx["F"], nctx["ldz"], nctx["p"], nctx["Ks"]
         B, Gs, status, n_iter = nctx["B"], nctx["Gs"], nctx["status"], nctx["n_iter"]
-        budget, first, later, max_phases = int(bt.max_iter), 500, 200, 12
+        budget, first, later, max_phases = int(bt.max_iter), self.NEWTON_FIRST, self.NEWTON_LATER, 12
         skip_ph = torch.zeros((F, ldz), dtype=torch.int32, device=self.device)
         if base_skip is not None:
             skip_ph.copy_(base_skip)

@@ -208,7 +208,8 @@ def newton_phase_device(engine, Gs, fold, n_obs, X, w2, d2, gptr_dev, gid_dev, s
         finished[live] = fin
         if os.environ.get("SLM_TRACE"):
             print(f"[slm newton step] k={k} accepted={int(accepted.sum())} full={int((t == 1.0).sum())} finished={int(fin.sum())} "
-                  f"dec max {float(dec.max()):.3e} min {float(dec.min()):.3e} chol failures {int((info[:, 3] != 0).sum())}",
+                  f"dec max {float(dec.max()):.3e} min {float(dec.min()):.3e} chol failures {int((info[:, 3] != 0).sum())} "
+                  f"active coordinates of p={p}: max {int((xs[:, :p] != 0).sum(1).max())} mean {float((xs[:, :p] != 0).sum(1).double().mean()):.0f}",
                   file=sys.stderr)
         live = live[accepted & ~fin & (st < 2)]
     return Xw[:, :p].contiguous(), {"steps": steps.to(dev), "factorizations": n_fact, "finished": finished.to(dev)}

@@ -108,6 +108,24 @@ for g, a, b in sorted(gaps, reverse=True)[:25]:
     lines.append(f"  {g:9.1f}  {a} -> {b}")
 lines.append(f"  gaps > 20us: {sum(1 for g in gaps if g[0] > 20)} totalling {sum(g[0] for g in gaps if g[0] > 20) / 1e3:.3f} ms;"
              f" gaps <= 20us: {sum(1 for g in gaps if g[0] <= 20)} totalling {sum(g[0] for g in gaps if g[0] <= 20) / 1e3:.3f} ms")
+# what the host was doing during the large gaps: CPU-side events overlapping each gap window
+cpu = [e for e in ev if e.get("cat") in ("cpu_op", "cuda_runtime", "user_annotation", "python_function") and "dur" in e]
+lines.append("  host activity inside the gaps > 20us (name: us overlapped)")
+gi = []
+end = None
+for i, e in enumerate(ks):
+    s_, d_ = e["ts"], e["dur"]
+    if end is not None and s_ - end > 20:
+        gi.append((end, s_, ks[i - 1]["name"][:40], e["name"][:40]))
+    end = s_ + d_ if end is None else max(end, s_ + d_)
+for a, b, pn, nn in sorted(gi, key=lambda g: g[0] - g[1])[:14]:
+    acts = {}
+    for c in cpu:
+        o = min(b, c["ts"] + c["dur"]) - max(a, c["ts"])
+        if o > 2:
+            acts[c["name"][:48]] = acts.get(c["name"][:48], 0.0) + o
+    top = sorted(acts.items(), key=lambda kv: -kv[1])[:7]
+    lines.append(f"  gap {b - a:8.1f} us  [{pn} -> {nn}]: " + "; ".join(f"{k}: {v:.0f}" for k, v in top))
 for r in range(world):
     barrier()
     if r == rank:
