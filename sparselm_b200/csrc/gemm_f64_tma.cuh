@@ -366,6 +366,17 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
         for (int i = 0; i < MI; ++i)
 #pragma unroll
             for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        if (batch.accumulate) {
+            // the tile of the accumulated-into matrix is wanted in the epilogue: start bringing it to L2 now
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) {
+                    const int row = m0 + (wm * MI + i) * 8 + lx, col = n0 + (wn * NI + j) * 8 + lk * 2;
+                    if (row < M && col < N)
+                        asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pr.C + (long long)row * ldc + col));
+                }
+        }
 
 #pragma unroll 1
         for (int kt = sg.kt0; kt < sg.kt1; ++kt, ++it_global) {
@@ -471,28 +482,44 @@ __global__ void __launch_bounds__((WARPS_M * WARPS_N + 4) * 32, MINB)
             }
             asm volatile("bar.sync 1, %0;\n" ::"r"(NCW * 32) : "memory");
         }
+        // the earlier partial sum / the accumulated-into matrix is read in batches of one row block (NI
+        // independent loads in flight) BEFORE any store of that block: written load-add-store element by
+        // element, every load waits behind the previous store (the compiler cannot reorder them: the pointers
+        // may alias) and the epilogue costs MI * NI serialised memory round trips
+        const bool need_old = !first_writer || batch.accumulate;
+        constexpr int JB = NI < 4 ? NI : 4;  // loads in flight per batch (more would cost registers the main loop needs)
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
             const int row = m0 + (wm * MI + i) * 8 + lx;
 #pragma unroll
-            for (int j = 0; j < NI; ++j) {
-                const int col = n0 + (wn * NI + j) * 8 + lk * 2;
-                if (row < M && col < N) {
-                    double v0 = acc[i][j][0], v1 = acc[i][j][1];
-                    if (batch.negate) {
-                        v0 = -v0;
-                        v1 = -v1;
-                    }
-                    double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
-                    if (!first_writer || batch.accumulate) {
-                        const double2 old = __ldcg(dst);
-                        v0 += old.x;
-                        v1 += old.y;
-                    }
-                    __stcg(dst, make_double2(v0, v1));
-                    if (SYM && tm != tn && !batch.upper_only) {
-                        __stcg(C + (long long)col * ldc + row, v0);
-                        __stcg(C + (long long)(col + 1) * ldc + row, v1);
+            for (int j0 = 0; j0 < NI; j0 += JB) {
+                double2 old[JB];
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    const int col = n0 + (wn * NI + j0 + jj) * 8 + lk * 2;
+                    old[jj] = make_double2(0.0, 0.0);
+                    if (j0 + jj < NI && need_old && row < M && col < N)
+                        old[jj] = __ldcg(reinterpret_cast<const double2*>(C + (long long)row * ldc + col));
+                }
+#pragma unroll
+                for (int jj = 0; jj < JB; ++jj) {
+                    const int j = j0 + jj;
+                    const int col = n0 + (wn * NI + j) * 8 + lk * 2;
+                    if (j < NI && row < M && col < N) {  // N is even: col+1 < N too
+                        double v0 = acc[i][j < NI ? j : 0][0], v1 = acc[i][j < NI ? j : 0][1];
+                        if (batch.negate) {
+                            v0 = -v0;
+                            v1 = -v1;
+                        }
+                        v0 += old[jj].x;
+                        v1 += old[jj].y;
+                        double2* dst = reinterpret_cast<double2*>(C + (long long)row * ldc + col);
+                        __stcg(dst, make_double2(v0, v1));
+                        if (SYM && tm != tn && !batch.upper_only) {
+                            // mirrored copy: same value as the upper entry (kept bit-identical)
+                            __stcg(C + (long long)col * ldc + row, v0);
+                            __stcg(C + (long long)(col + 1) * ldc + row, v1);
+                        }
                     }
                 }
             }

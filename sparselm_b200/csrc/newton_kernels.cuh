@@ -173,9 +173,10 @@ __global__ void __launch_bounds__(NW_T) newton_hessian_kernel(int p, const doubl
 //
 // The 64 x 64 block is itself factored by 16-wide sub-blocks so that the kernel is not a chain of 64
 // barrier-separated rank-1 steps: one warp factors a 16 x 16 diagonal sub-block in registers (row r in
-// lane r, columns exchanged by shuffles) and inverts it the same way; the whole CTA then applies that
-// inverse to the rows below and updates the rest (two small products, 4 barriers per sub-block).  The
-// inverse of the 64 x 64 factor is assembled from the four 16 x 16 inverses by block substitution.
+// lane r, columns exchanged by shuffles; one rsqrt per pivot, no division), the rows below are solved
+// against it one thread per row (forward substitution in registers), the rest is updated by the whole
+// CTA (3 barriers per sub-block).  The four 16 x 16 inverses are then formed by four warps at once and
+// the inverse of the 64 x 64 factor is assembled from them by block substitution.
 constexpr int NW_SB = 16;
 __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H, long long ldh, int j0,
                                                          const int* __restrict__ MS, double* __restrict__ INV,
@@ -183,8 +184,10 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
     extern __shared__ double nw_sh[];
     double (*S)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh);
     double (*V)[NW_NB + 1] = reinterpret_cast<double (*)[NW_NB + 1]>(nw_sh + NW_NB * (NW_NB + 1));
-    __shared__ double DI[NW_NB / NW_SB][NW_SB][NW_SB + 1];  // inverses of the diagonal sub-blocks (lower)
-    __shared__ double TT[3][NW_SB][NW_SB + 1];
+    constexpr int NSB = NW_NB / NW_SB;
+    __shared__ double DI[NSB][NW_SB][NW_SB + 1];  // inverses of the diagonal sub-blocks (lower)
+    __shared__ double TT[NSB - 1][NW_SB][NW_SB + 1];
+    __shared__ double RD[NW_NB];  // reciprocals of the diagonal of L
     __shared__ int bad;
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = min(NW_NB, MS[c] - j0);
@@ -199,26 +202,28 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
         V[i][j] = 0.0;
     }
     __syncthreads();
-    for (int kb = 0; kb < NW_NB / NW_SB; ++kb) {
+    for (int kb = 0; kb < NSB; ++kb) {
         const int b0 = kb * NW_SB;
         if (warp == 0) {
             const int r = lane & (NW_SB - 1);  // lanes 16..31 mirror lanes 0..15 (their results are not stored)
+            // entries right of the diagonal (q > r) are dead weight: never read by another lane, never stored --
+            // the updates below run on them unconditionally, so the loop is free of per-lane branches
             double d[NW_SB];
 #pragma unroll
-            for (int q = 0; q < NW_SB; ++q) d[q] = (q <= r) ? S[b0 + r][b0 + q] : 0.0;
+            for (int q = 0; q < NW_SB; ++q) d[q] = S[b0 + r][b0 + q];
             bool ok = true;
+            double myrs = 1.0;
 #pragma unroll
             for (int k = 0; k < NW_SB; ++k) {
                 const double piv = __shfl_sync(0xffffffffu, d[k], k);
                 ok = ok && (piv > 0.0);
-                const double sq = piv > 0.0 ? sqrt(piv) : 1.0;
-                const double rs = 1.0 / sq;
-                if (r == k) d[k] = sq;
-                else if (r > k) d[k] *= rs;
+                const double rs = piv > 0.0 ? rsqrt(piv) : 1.0;
+                d[k] *= rs;  // lane k: piv * rsqrt(piv) = sqrt(piv)
+                myrs = (r == k) ? rs : myrs;
 #pragma unroll
                 for (int q = k + 1; q < NW_SB; ++q) {
                     const double lqk = __shfl_sync(0xffffffffu, d[k], q);
-                    if (r >= q) d[q] -= d[k] * lqk;
+                    d[q] = fma(-d[k], lqk, d[q]);
                 }
             }
             if (!ok && lane == 0) bad = 1;
@@ -226,40 +231,27 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
 #pragma unroll
                 for (int q = 0; q < NW_SB; ++q)
                     if (q <= r) S[b0 + r][b0 + q] = d[q];
-            }
-            // inverse of the sub-block: lane r computes column r of L^{-1} by forward substitution
-            double x[NW_SB];
-#pragma unroll
-            for (int i = 0; i < NW_SB; ++i) {
-                const double lii = __shfl_sync(0xffffffffu, d[i], i);
-                double acc = (i == r) ? 1.0 : 0.0;
-#pragma unroll
-                for (int m = 0; m < i; ++m) {
-                    const double lim = __shfl_sync(0xffffffffu, d[m], i);
-                    acc -= lim * x[m];  // x[m] = 0 for m < r
-                }
-                x[i] = (i >= r) ? acc / lii : 0.0;
-            }
-            if (lane < NW_SB) {
-#pragma unroll
-                for (int i = 0; i < NW_SB; ++i) DI[kb][i][r] = x[i];
+                RD[b0 + r] = myrs;
             }
         }
         __syncthreads();
         const int below = NW_NB - b0 - NW_SB;  // rows under the sub-block
         if (below > 0) {
-            // rows below: L[r][b0 + q] = sum_{m <= q} A[r][b0 + m] DI[q][m]   (A D^{-T})
-            double outv[3];
-            int cnt = 0;
-            for (int e = tid; e < below * NW_SB; e += NW_T, ++cnt) {
-                const int r = b0 + NW_SB + e / NW_SB, q = e % NW_SB;
-                double a = 0.0;
-                for (int m = 0; m <= q; ++m) a += S[r][b0 + m] * DI[kb][q][m];
-                outv[cnt] = a;
+            // rows below: L[r][b0 + q] by forward substitution against the sub-block, one thread per row
+            if (tid < below) {
+                const int r = b0 + NW_SB + tid;
+                double a[NW_SB];
+#pragma unroll
+                for (int q = 0; q < NW_SB; ++q) a[q] = S[r][b0 + q];
+#pragma unroll
+                for (int m = 0; m < NW_SB; ++m) {
+                    a[m] *= RD[b0 + m];
+#pragma unroll
+                    for (int q = m + 1; q < NW_SB; ++q) a[q] -= a[m] * S[b0 + q][b0 + m];
+                }
+#pragma unroll
+                for (int q = 0; q < NW_SB; ++q) S[r][b0 + q] = a[q];
             }
-            __syncthreads();
-            cnt = 0;
-            for (int e = tid; e < below * NW_SB; e += NW_T, ++cnt) S[b0 + NW_SB + e / NW_SB][b0 + e % NW_SB] = outv[cnt];
             __syncthreads();
             // rest of the block: S[r][q] -= sum_m L[r][b0 + m] L[q][b0 + m]  (lower triangle, r >= q)
             for (int e = tid; e < below * below; e += NW_T) {
@@ -277,8 +269,30 @@ __global__ void __launch_bounds__(NW_T) chol_diag_kernel(double* __restrict__ H,
         const int i = e / nb, j = e % nb;
         if (i <= j) Hc[(long long)i * ldh + j] = S[j][i];  // U[i][j] = L[j][i]
     }
+    // inverses of the four diagonal sub-blocks, one warp each: lane r forms column r of L_D^{-1} by forward
+    // substitution, the rows of L_D come from the other lanes' registers
+    if (warp < NSB) {
+        const int b0 = warp * NW_SB, r = lane & (NW_SB - 1);
+        double d[NW_SB], x[NW_SB];
+#pragma unroll
+        for (int q = 0; q < NW_SB; ++q) d[q] = S[b0 + r][b0 + q];
+#pragma unroll
+        for (int i = 0; i < NW_SB; ++i) {
+            double acc = (i == r) ? 1.0 : 0.0;
+#pragma unroll
+            for (int m = 0; m < i; ++m) {
+                const double lim = __shfl_sync(0xffffffffu, d[m], i);
+                acc -= lim * x[m];  // x[m] = 0 for m < r
+            }
+            x[i] = (i >= r) ? acc * RD[b0 + i] : 0.0;
+        }
+        if (lane < NW_SB) {
+#pragma unroll
+            for (int i = 0; i < NW_SB; ++i) DI[warp][i][r] = x[i];
+        }
+    }
+    __syncthreads();
     // V = L^{-1} (lower) by blocks: V_ii = DI_i, V_ij = -DI_i sum_{j <= m < i} L_im V_mj, by distance i - j
-    constexpr int NSB = NW_NB / NW_SB;
     {
         const int a = tid / NW_SB, b = tid % NW_SB;  // 256 threads = one 16 x 16 block
         for (int i = 0; i < NSB; ++i) V[i * NW_SB + a][i * NW_SB + b] = DI[i][a][b];

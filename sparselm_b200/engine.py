@@ -184,8 +184,10 @@ class Engine:
     PIPELINE_BLOCK_BYTES = 64 << 20  # rows of a host design travel and enter the Gram in blocks of this size
     LIPSCHITZ_MARGIN = 1.10
     # second-order phase (_run_batch): iterations before the first Newton phase / between two phases
-    NEWTON_FIRST = int(os.environ.get("SLM_NEWTON_FIRST", 500))
-    NEWTON_LATER = int(os.environ.get("SLM_NEWTON_LATER", 200))
+    # (measured on BASELINE configs[3], profiles/r02o_newton_tuning.txt: 500/200 469 ms, 300/200 430 ms, 300/100 422 ms,
+    # 200/100 457 ms per search)
+    NEWTON_FIRST = int(os.environ.get("SLM_NEWTON_FIRST", 300))
+    NEWTON_LATER = int(os.environ.get("SLM_NEWTON_LATER", 100))
 
     def __init__(self, device: int | None = None):
         import torch

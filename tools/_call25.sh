@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-for cfg in "500 200" "300 200" "300 100" "200 100" "150 80" "100 50"; do
+for cfg in "400 200" "300 200" "300 100" "250 100" "200 100" "200 200"; do
   set -- $cfg
   SLM_NEWTON_FIRST=$1 SLM_NEWTON_LATER=$2 timeout 200 python bench.py --workload c4 --steps 2 --warmup 1 --no-cpu > gpurun_out/tune_c4_$1_$2.json 2> gpurun_out/tune_c4_$1_$2.err
   python - <<PY
