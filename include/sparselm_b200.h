@@ -234,6 +234,17 @@ int slm_cv_score(slm_ctx* ctx, const double* Xa_dev, int64_t lda, int64_t p, int
                  const double* intercept_dev, int32_t rows_scaled, double* yhat_dev,
                  double* out_dev, void* stream);
 
+/* n scoring problems in one tensor-core launch (row-sharded scoring of a sharded grid: this rank's slice of
+ * every fold's rows x the columns each rank solved on that fold).  All arrays are HOST arrays of length n;
+ * B[i] / intercept[i] / yhat[i] / out[i] are device pointers.  Problem i scores rows [r0[i], r1[i]) of Xa
+ * against the K[i] columns of B[i] ([p][ldb[i]], ldb even, B[i] 16-byte aligned); yhat[i] is scratch
+ * [(r1-r0) + 256][ldy[i]] (ldy a multiple of 8, >= K[i] rounded up to 8); out[i] is [2][ldy[i]] as in
+ * slm_cv_score.  intercept may be NULL (no intercepts at all) or hold NULL entries. */
+int slm_cv_score_many(slm_ctx* ctx, const double* Xa_dev, int64_t lda, int64_t p, int32_t n,
+                      const int64_t* r0, const int64_t* r1, const double* const* B_dev, const int64_t* ldb,
+                      const int32_t* K, const double* const* intercept_dev, int32_t rows_scaled,
+                      double* const* yhat_dev, const int64_t* ldy, double* const* out_dev, void* stream);
+
 /* intercept[k] = ybar - mu^T B[:,k] from the (uncentred) training Gram's ones row
  * (LinearModel._set_intercept, _base.py:202). */
 int slm_intercepts(slm_ctx* ctx, const double* G_dev, int64_t pa, int64_t p,

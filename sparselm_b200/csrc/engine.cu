@@ -2081,6 +2081,65 @@ int slm_cv_score(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int64_t
     return 0;
 }
 
+// several scoring problems in one GEMM launch (the row-sharded scoring of a sharded grid holds a dozen small
+// ones: a slice of every fold's rows x the columns every rank solved on that fold)
+int slm_cv_score_many(slm_ctx* ctx, const double* Xa, int64_t lda, int64_t p, int32_t n, const int64_t* r0,
+                      const int64_t* r1, const double* const* B, const int64_t* ldb, const int32_t* K,
+                      const double* const* icpt, int32_t rows_scaled, double* const* yhat, const int64_t* ldy,
+                      double* const* out, void* stream) {
+    if (!ctx || !Xa || !r0 || !r1 || !B || !ldb || !K || !yhat || !ldy || !out)
+        return fail(ctx, 1, "slm_cv_score_many: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += kMaxGemmProblems) {
+        const int nb = std::min<int>(n - i0, kMaxGemmProblems);
+        GemmBatch b;
+        memset(&b, 0, sizeof(b));
+        ProblemDims pd[kMaxGemmProblems];
+        int np = 0;
+        double flops = 0.0;
+        for (int i = i0; i < i0 + nb; ++i) {
+            const int64_t m = r1[i] - r0[i];
+            if (m <= 0 || K[i] <= 0) continue;
+            if (!B[i] || !yhat[i] || !out[i] || (ldb[i] & 1) || (ldy[i] % 8) || ((uintptr_t)B[i] & 15))
+                return fail(ctx, 1, "slm_cv_score_many: bad problem (null pointer, odd leading dimension or unaligned B)");
+            GemmProblem& pr = b.pr[np];
+            pr.P = Xa + r0[i] * lda;
+            pr.Q = B[i];
+            pr.C = yhat[i];
+            pr.ldp = lda;
+            pr.ldq = ldb[i];
+            pr.ldc = ldy[i];
+            pr.M = (int)m;
+            pr.N = (int)std::min<int64_t>(round_up(K[i], 8), ldy[i]);
+            pr.qlim = pr.N;
+            pr.Kd = (int)p;
+            pd[np] = {pr.M, pr.N};
+            flops += 2.0 * (double)m * (double)p * (double)K[i];
+            ++np;
+        }
+        if (np == 0) continue;
+        b.n_problems = np;
+        const int sid = pick_shape(kScoreShapes, kNumScoreShapes, pd, np, ctx->sm_count);
+        {
+            FamTimer tm(ctx, FAM_SCORE, s, flops);
+            cudaError_t e = launch_score_shape(ctx, sid, b, s);
+            if (e != cudaSuccess) return fail(ctx, 100 + (int)e, std::string("score gemm: ") + cudaGetErrorString(e));
+            ctx->launches++;
+        }
+        for (int i = i0; i < i0 + nb; ++i) {
+            const int64_t m = r1[i] - r0[i];
+            if (m <= 0 || K[i] <= 0) continue;
+            double* part = yhat[i] + m * ldy[i];
+            dim3 grid((unsigned)((K[i] + 7) / 8), SCORE_RB);
+            score_partial_kernel<<<grid, 256, 0, s>>>(Xa, lda, (int)p, r0[i], m, yhat[i], ldy[i], K[i], icpt ? icpt[i] : nullptr,
+                                                      rows_scaled, part);
+            score_final_kernel<<<(unsigned)((K[i] + 127) / 128), 128, 0, s>>>(part, ldy[i], K[i], out[i]);
+        }
+        LAUNCH_OK("score kernels");
+    }
+    return 0;
+}
+
 int slm_intercepts(slm_ctx* ctx, const double* G, int64_t pa, int64_t p, const double* B, int64_t ldz,
                    int32_t K, double* icpt, void* stream) {
     if (!ctx || !G || !B || !icpt) return fail(ctx, 1, "slm_intercepts: null argument");

@@ -1110,6 +1110,36 @@ class Engine:
         return out
 
 
+    def cv_score_many(self, Xa, p, items, rows_scaled=False):
+        """Residual sums of several (row range, coefficient block) pairs in ONE tensor-core launch.
+        items: list of (r0, r1, B, K, intercept) with B a device view [p, >= K] whose row stride is even and
+        whose first element is 16-byte aligned (a column slice of a wider table is fine), intercept a device
+        view [K] or None.  Returns a device tensor [len(items), 2, ldo] (sse, sae in the first K entries)."""
+        torch = self.torch
+        n = len(items)
+        ldo = max([max(8, _round_up(int(it[3]), 8)) for it in items], default=8)
+        ldys = [ldo] * n  # one leading dimension for every problem: slot i of the result is a plain [2, ldo] block
+        out = torch.zeros((max(n, 1), 2, ldo), dtype=torch.float64, device=self.device)
+        if n == 0:
+            return out
+        rows = [max(0, int(it[1]) - int(it[0])) for it in items]
+        offs = np.concatenate([[0], np.cumsum([(m + 256) * ld for m, ld in zip(rows, ldys)])]).astype(np.int64)
+        yhat = torch.empty(int(offs[-1]), dtype=torch.float64, device=self.device)
+        i64, i32, vp = ctypes.c_int64 * n, ctypes.c_int32 * n, ctypes.c_void_p * n
+        r0 = i64(*[int(it[0]) for it in items])
+        r1 = i64(*[int(it[1]) for it in items])
+        Bp = vp(*[it[2].data_ptr() for it in items])
+        ldb = i64(*[int(it[2].stride(0)) for it in items])
+        K = i32(*[int(it[3]) for it in items])
+        ic = vp(*[(None if it[4] is None else it[4].data_ptr()) for it in items])
+        yp = vp(*[yhat.data_ptr() + 8 * int(o) for o in offs[:-1]])
+        ldy = i64(*ldys)
+        op = vp(*[out.data_ptr() + 8 * i * 2 * ldo for i in range(n)])
+        self._ck(self.lib.slm_cv_score_many(self.h, self._ptr(Xa), Xa.shape[1], p, n, r0, r1, Bp, ldb, K, ic,
+                                            1 if rows_scaled else 0, yp, ldy, op, self.stream), "slm_cv_score_many")
+        return out
+
+
 _engines: dict = {}
 
 

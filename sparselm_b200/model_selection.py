@@ -225,8 +225,10 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
             mine = [np.arange(K)] * n_splits
         if fkey not in fds:
             # a sharded rank only needs its own slice of every fold's rows on the device (Gram build
-            # and scoring are both row-sharded); a LineSearchCV cache keeps the whole design
-            score_folds = set() if (sharded and cache is None) else None
+            # and scoring are both row-sharded) when the design comes from the host; a design that is already
+            # device-resident, or the cached one of a LineSearchCV, is kept whole
+            x_dev = isinstance(X, torch.Tensor) and X.is_cuda
+            score_folds = set() if (sharded and cache is None and not x_dev) else None
             fds[fkey] = prepare_folds(engine, X, yv, test_folds, e0, s0, cache, cache_key, shard, sample_weight,
                                       score_folds)
         fd = fds[fkey]
@@ -235,19 +237,30 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
         t1 = time.perf_counter()
         warm.add(out["B"], idxs, mine)
         wtd = bool(fd.extra.get("weighted"))
-        if not sharded:
+        if not sharded or fd.extra.get("partial_folds") is None:
+            # every row is resident: each rank scores the columns it solved on whole folds (a sharded grid then
+            # needs no exchange of coefficients; the partial tables are summed with the info tables below).
+            # All (fold, row range) problems go through one batched scoring launch.
             icpt = (lambda f: out["intercept"][f]) if fd.fit_intercept else (lambda f: None)
-            sc_dev = [engine.cv_score(fd.Xa, p, fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], K, icpt(f),
-                                      rows_scaled=wtd) for f in range(n_splits)]
-            sc = torch.stack(sc_dev).cpu().numpy()[:, :, :K]  # one D2H for all folds: [n_splits, 2, K]
-            tsc = None
-            if want_train:
-                tsc = np.zeros_like(sc)
-                for f in range(n_splits):
+            items, where = [], []
+            for f in range(n_splits):
+                kf = len(mine[f])
+                if kf == 0:
+                    continue
+                items.append((fd.row_ptr[f], fd.row_ptr[f + 1], out["coef"][f], kf, icpt(f)))
+                where.append((0, f))
+                if want_train:
                     for r0, r1 in ((0, fd.row_ptr[f]), (fd.row_ptr[f + 1], n)):
                         if r1 > r0:
-                            tsc[f] += engine.cv_score(fd.Xa, p, r0, r1, out["coef"][f], K, icpt(f),
-                                                      rows_scaled=wtd).cpu().numpy()[:, :K]
+                            items.append((r0, r1, out["coef"][f], kf, icpt(f)))
+                            where.append((1, f))
+            sc = np.zeros((n_splits, 2, K))
+            tsc = np.zeros((n_splits, 2, K)) if want_train else None
+            if items:
+                res = engine.cv_score_many(fd.Xa, p, items, rows_scaled=wtd).cpu().numpy()  # one D2H
+                for i, (kind, f) in enumerate(where):
+                    tgt = sc if kind == 0 else tsc
+                    tgt[f][:, mine[f]] += res[i][:, :len(mine[f])]
         else:
             sc, tsc = _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, wtd, want_train)
         t2 = time.perf_counter()
@@ -314,14 +327,20 @@ def _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, 
 
     torch = engine.torch
     W = shard.world
-    cap = max(int((owner == r).sum(axis=1).max()) for r in range(W))
-    ldg = max(8, (cap + 7) // 8 * 8)
-    send = torch.zeros((n_splits, p + 1, ldg), dtype=torch.float64, device=engine.device)
+    # send layout: [p + 1][ldg], the columns this rank solved, fold after fold, every fold's group padded to a
+    # multiple of 8 columns (only what was solved travels: C3 on 8 ranks, 2.6 MB per rank)
+    kfr = np.array([[int((owner[f] == r).sum()) for f in range(n_splits)] for r in range(W)])  # [W, n_splits]
+    pad = (kfr + 7) // 8 * 8
+    off = np.concatenate([np.zeros((W, 1), dtype=np.int64), np.cumsum(pad, axis=1)], axis=1)  # [W, n_splits + 1]
+    ldg = max(8, int(off[:, -1].max()))
+    send = torch.zeros((p + 1, ldg), dtype=torch.float64, device=engine.device)
     for f in range(n_splits):
         kf = len(mine[f])
         if kf:
-            send[f, :p, :kf] = out["coef"][f][:, :kf]
-            send[f, p, :kf] = out["intercept"][f][:kf]
+            o = int(off[shard.rank, f])
+            send[:p, o:o + kf] = out["coef"][f][:, :kf]
+            if fd.fit_intercept:
+                send[p, o:o + kf] = out["intercept"][f][:kf]
     recv = torch.empty((W,) + tuple(send.shape), dtype=torch.float64, device=engine.device)
     comm = shard.comm_ptr(engine.device)
     if comm is not None:
@@ -330,29 +349,36 @@ def _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, 
     else:
         shard.all_gather_(send, recv)
     rows = shard.fold_row_ranges(fd.row_ptr)
-    part = torch.zeros((n_splits, 2, K), dtype=torch.float64, device=engine.device)
-    tpart = torch.zeros((n_splits, 2, K), dtype=torch.float64, device=engine.device) if want_train else None
-    cols_dev = {}
+    # every (fold, solving rank) group against this rank's slice of the fold's rows -- and, for train scores,
+    # against its slices of the other folds -- as ONE batched scoring launch
+    items, where = [], []
     for f in range(n_splits):
         for r in range(W):
-            cols = np.flatnonzero(owner[f] == r)
-            kf = len(cols)
+            kf = int(kfr[r, f])
             if kf == 0:
                 continue
-            cd = cols_dev.setdefault((f, r), torch.from_numpy(cols).to(engine.device))
-            Bfr, icpt = recv[r, f, :p], (recv[r, f, p] if fd.fit_intercept else None)
+            o = int(off[r, f])
+            Bfr = recv[r, :p, o:o + int(pad[r, f])]
+            icpt = recv[r, p, o:o + kf] if fd.fit_intercept else None
+            cols = np.flatnonzero(owner[f] == r)
             lo, hi = rows[f]
             if hi > lo:
-                part[f][:, cd] = engine.cv_score(fd.Xa, p, lo, hi, Bfr, kf, icpt, rows_scaled=wtd)[:, :kf]
+                items.append((lo, hi, Bfr, kf, icpt))
+                where.append((0, f, cols))
             if want_train:
                 for f2 in range(n_splits):
                     lo2, hi2 = rows[f2]
                     if f2 != f and hi2 > lo2:
-                        tpart[f][:, cd] += engine.cv_score(fd.Xa, p, lo2, hi2, Bfr, kf, icpt, rows_scaled=wtd)[:, :kf]
-    if want_train:
-        both = torch.stack([part, tpart]).cpu().numpy()
-        return both[0], both[1]
-    return part.cpu().numpy(), None
+                        items.append((lo2, hi2, Bfr, kf, icpt))
+                        where.append((1, f, cols))
+    part = np.zeros((n_splits, 2, K))
+    tpart = np.zeros((n_splits, 2, K)) if want_train else None
+    if items:
+        res = engine.cv_score_many(fd.Xa, p, items, rows_scaled=wtd).cpu().numpy()  # one D2H
+        for i, (kind, f, cols) in enumerate(where):
+            tgt = part if kind == 0 else tpart
+            tgt[f][:, cols] += res[i][:, :len(cols)]
+    return part, tpart
 
 
 class GridSearchCV(_SkGridSearchCV):
