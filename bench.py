@@ -773,21 +773,24 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     gb = tim["gram_build"]
     build_tf = gb["flops"] / (gb["ms"] * 1e-3) / 1e12 if gb["ms"] > 0 else None
     src = "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"
+    roof_build = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel<SYM> (Gram build, TMA-fed FP64 DMMA, SYRK flop count)",
+                  "achieved": build_tf, "peak": peak, "unit": "TFLOP/s", "frac": build_tf / peak if build_tf else None,
+                  "peak_source": src, "avg_launch_ms": gb["ms"] / max(gb["launches"], 1),
+                  "launches_per_step": gb["launches"] / args.steps, "traffic": None}
+    roof_apply = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (row-sparse Gram apply, TMA gather4-fed FP64 DMMA)",
+                  "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                  "peak_source": src, "dense_equivalent_tflops": dense_equiv,
+                  "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
+                  "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
+                  "traffic": traffic, "traffic_source": traffic_src}
+    # the roofline object describes the kernel family with the largest share of the step (tall designs: the Gram
+    # build; C3 on one GPU: build and apply are within a few per cent of each other); the other tensor-core
+    # family is reported next to it with the same fields
     if gb["ms"] > ap["ms"]:
-        # tall designs: the dominant kernel is the Gram build (SYRK count n pa (pa+1))
-        roof = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel<SYM> (Gram build, TMA-fed FP64 DMMA, SYRK flop count)",
-                "achieved": build_tf, "peak": peak, "unit": "TFLOP/s", "frac": build_tf / peak if build_tf else None,
-                "peak_source": src, "avg_launch_ms": gb["ms"] / max(gb["launches"], 1),
-                "launches_per_step": gb["launches"] / args.steps, "traffic": None,
-                "gram_apply_tflops": achieved, "step_ms_by_kernel_family": step_ms}
+        roof = dict(roof_build, gram_apply_tflops=achieved, second_kernel=roof_apply)
     else:
-        roof = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (row-sparse Gram apply, TMA gather4-fed FP64 DMMA)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "peak_source": src, "dense_equivalent_tflops": dense_equiv,
-                "support_fraction": (exec_flops / dense_flops) if dense_flops > 0 else None,
-                "avg_launch_ms": apply_ms, "launches_per_step": ap["launches"] / args.steps,
-                "traffic": traffic, "traffic_source": traffic_src, "gram_build_tflops": build_tf,
-                "step_ms_by_kernel_family": step_ms}
+        roof = dict(roof_apply, gram_build_tflops=build_tf, second_kernel=roof_build)
+    roof["step_ms_by_kernel_family"] = step_ms
     nw = res.get("newton") or {}
     if nw.get("factorizations"):  # second-order phase of the last timed step (csrc/newton_kernels.cuh)
         torch_model = os.environ.get("SLM_NEWTON_TORCH", "0") == "1"

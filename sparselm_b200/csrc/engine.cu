@@ -80,6 +80,7 @@ struct slm_ctx {
     int force_syrk_shape = -1;   // tuning/testing hook (SLM_FORCE_SYRK_SHAPE)
     // TMA-fed GEMM kernels (gemm_f64_tma.cuh): bit 0 Gram build, bit 1 dense apply, bit 2 row-sparse
     // apply (SLM_TMA / slm_set_option "tma"); encode = cuTensorMapEncodeTiled resolved at run time
+    bool fused_prox = true;          // SLM_FUSED_PROX=0: the two-kernel iteration (prox_main + prox_momentum on the extrapolated point)
     bool prox2 = false;              // SLM_PROX2=1: one-lane-per-column prox kernels (measured slower: 3.34 vs 2.60 ms per C3 step)
     int tma_mask = 7 + 8;  // + bit 3: wide bands for the gather kernels, bit 4: for the tiled kernels
     void* encode = nullptr;
@@ -932,6 +933,7 @@ int slm_create(int device, slm_ctx** out) {
     if (const char* e = getenv("SLM_TRACE")) ctx->trace = atoi(e) != 0;
     if (const char* e = getenv("SLM_TMA")) ctx->tma_mask = atoi(e);
     if (const char* e = getenv("SLM_PROX2")) ctx->prox2 = atoi(e) != 0;
+    if (const char* e = getenv("SLM_FUSED_PROX")) ctx->fused_prox = atoi(e) != 0;
     {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -1004,6 +1006,8 @@ int slm_set_option(slm_ctx* ctx, const char* name, int value) {
         ctx->tma_mask = value;
     else if (nm == "prox2")
         ctx->prox2 = value != 0;
+    else if (nm == "fused_prox")
+        ctx->fused_prox = value != 0;
     else if (nm == "force_apply_shape")
         ctx->force_apply_shape = value;
     else if (nm == "force_sparse_shape")
@@ -1378,7 +1382,7 @@ size_t slm_solve_workspace(int64_t p, int64_t ldz, int n_folds, int n_groups) {
     size_t nblk = (size_t)ldz / 8;
     size_t lists = (size_t)n_folds * nblk * ((size_t)p + 1) * sizeof(int);
     size_t zflag = round_up((int64_t)((size_t)n_folds * (size_t)p * nblk), 16);
-    return 5 * state + cols * (4 * sizeof(double) + 3 * sizeof(int)) + part + 64 * sizeof(int) + 256 + lists +
+    return 5 * state + cols * (5 * sizeof(double) + 3 * sizeof(int)) + part + 64 * sizeof(int) + 256 + lists +
            zflag + 64;
 }
 
@@ -1403,7 +1407,8 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     double* Bw = T + state;
     double* theta = Bw + state;       // [2][cols]
     double* tmom = theta + 2 * cols;  // [2][cols]
-    double* part = tmom + 2 * cols;   // [F][n_chunks][NQ][ldz]
+    double* rst = tmom + 2 * cols;    // [cols]
+    double* part = rst + cols;        // [F][n_chunks][NQ][ldz]
     int* flag = (int*)(part + cols * (size_t)kMaxChunks * NQ);
     int* colmap = flag + cols;
     int* src = colmap + cols;
@@ -1452,6 +1457,7 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     sp.tmom[0] = tmom;
     sp.tmom[1] = tmom + cols;
     sp.part = part;
+    sp.rst = rst;
     sp.flag = flag;
     const bool grouped = bt->gptr_dev != nullptr;
     const int gpb = grouped ? GPB : SG;  // groups per block iteration
@@ -1544,6 +1550,14 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     CUDA_OK(cudaMemcpyAsync(Bw, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemcpyAsync(Z, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     CUDA_OK(cudaMemsetAsync(GB, 0, state * sizeof(double), s));
+    // fused iteration (solver_kernels.cuh, prox_fused_kernel): the iterates W_t / W_{t-1} alternate between Bw and
+    // T, their Gram products between GZ and GB; Z is scratch.  One-way switch to the two-kernel state when the
+    // cluster kernels take over the tail.
+    bool fused = ctx->fused_prox && !small && !coop;
+    double* Bc[2] = {Bw, T};
+    double* GBc[2] = {GZ, GB};
+    int use_rst = 0;
+    if (fused) CUDA_OK(cudaMemcpyAsync(T, bt->B_dev, state * sizeof(double), cudaMemcpyDeviceToDevice, s));
     const dim3 zgrid((unsigned)(((long long)p * sp.nblk + 255) / 256), (unsigned)F);
     if (sparse) {
         CUDA_OK(cudaMemsetAsync(ctx->d_stat, 0, sizeof(unsigned long long), s));
@@ -1685,9 +1699,11 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         const bool probe = can_adapt && !check && !coop && !clus && (it == 1 || it == 3 || it == 6);
         const int cw_now = (wide && !check && !probe) ? cw_wide : cw;
-        int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, Z, GZ, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
+        const double* ap_in = fused ? Bc[par] : Z;  // fused: the Gram acts on the iterate itself
+        double* ap_out = fused ? GBc[par] : GZ;
+        int rc = sparse ? apply_rowsparse(ctx, sp, Kcur, ap_in, ap_out, cw_now, (int)((ldz + cw_now - 1) / cw_now), sidx,
                                           scount, s, algo)
-                        : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, Z, ldz, GZ, s, algo);
+                        : apply_batched(ctx, bt->G_dev, bt->g_stride, bt->pa, p, F, Kcur, ap_in, ldz, ap_out, s, algo);
         if (rc) return rc;
         if ((check || probe) && (can_adapt || (clus_thr > 0 && sparse && F * ncc <= kMaxScount)))
             CUDA_OK(cudaMemcpyAsync(ctx->h_scount, scount, sizeof(int) * (size_t)F * ncc, cudaMemcpyDeviceToHost, s));
@@ -1700,11 +1716,18 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             CUDA_OK(cudaMemsetAsync(ctx->d_ratio, 0, sizeof(unsigned long long), s));
             {
                 FamTimer tm(ctx, FAM_GAP, s, 0.0);
+                SolveDev spg = sp;
+                if (fused) {  // B = W_t, GZ = G W_t itself
+                    spg.B = Bc[par];
+                    spg.GZ = GBc[par];
+                    spg.direct = 1;
+                }
                 if (grouped)
-                    gap_partial_kernel<true><<<cgrid, ST, 0, s>>>(sp, par, 0);
+                    gap_partial_kernel<true><<<cgrid, ST, 0, s>>>(spg, par, 0);
                 else
-                    gap_partial_kernel<false><<<cgrid, ST, 0, s>>>(sp, par, 0);
-                gap_final_kernel<<<fgrid, 128, 0, s>>>(sp, it, 0);
+                    gap_partial_kernel<false><<<cgrid, ST, 0, s>>>(spg, par, 0);
+                gap_final_kernel<<<fgrid, 128, 0, s>>>(spg, it, 0);
+                if (fused) settle_done_kernel<<<mgrid, ST, 0, s>>>(sp, Bc[par], Bc[par ^ 1]);
             }
             LAUNCH_OK("gap kernels");
             ctx->launches++;
@@ -1778,7 +1801,30 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
         }
         {
             FamTimer tm(ctx, FAM_PROX, s, 0.0);
-            if (ctx->prox2) {
+            if (fused) {
+                FusedArgs fa;
+                fa.Bcur = Bc[par];
+                fa.Bnew = Bc[par ^ 1];
+                fa.GBcur = GBc[par];
+                fa.GBold = GBc[par ^ 1];
+                fa.stash = Z;
+                fa.it = it;
+                fa.use_rst = use_rst;
+                use_rst = 0;
+                // rows of the largest group per sub-lane (0: the caller did not say -> the widest instantiation;
+                // longer groups take the kernel's two-pass path)
+                const int rows_lane = bt->max_group > 0 ? (bt->max_group + SUB - 1) / SUB : 8;
+                if (!grouped)
+                    prox_fused_kernel<false, 1><<<cgrid, ST, 0, s>>>(sp, fa, par);
+                else if (rows_lane <= 2)
+                    prox_fused_kernel<true, 2><<<cgrid, ST, 0, s>>>(sp, fa, par);
+                else if (rows_lane <= 3)
+                    prox_fused_kernel<true, 3><<<cgrid, ST, 0, s>>>(sp, fa, par);
+                else if (rows_lane <= 5)
+                    prox_fused_kernel<true, 5><<<cgrid, ST, 0, s>>>(sp, fa, par);
+                else
+                    prox_fused_kernel<true, 8><<<cgrid, ST, 0, s>>>(sp, fa, par);
+            } else if (ctx->prox2) {
                 // one lane per column, 32 columns per block (solver_kernels.cuh, second mapping)
                 SolveDev s2 = sp;
                 s2.gpt = std::max(1, (Gn + PX_W * kMaxChunks - 1) / (PX_W * kMaxChunks));
@@ -1805,9 +1851,19 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             // converged columns leave the batch (after this iteration's epilogue, so that GZ of
             // the old layout is no longer needed): scatter their coefficients to the caller's
             // array, move the active columns of Z, B, GB to the front
+            SolveDev spc = sp;
+            if (fused) {
+                // live state after this iteration's prox: W_{t+1} (other buffer), W_t, G W_t; the restart dot of the
+                // iteration is reduced per column before the columns are renumbered
+                spc.Z = Bc[par ^ 1];
+                spc.B = Bc[par];
+                spc.GB = GBc[par];
+                restart_reduce_kernel<<<fgrid, 128, 0, s>>>(sp, par);
+                use_rst = 1;
+            }
             compact_plan_kernel<<<F, 32, 0, s>>>(sp, src, newK);
-            scatter_done_kernel<<<mgrid, ST, 0, s>>>(sp, 0);
-            compact_move_kernel<<<dim3((unsigned)((p + 127) / 128), 3, (unsigned)F), 128, 0, s>>>(sp, src, newK);
+            scatter_done_kernel<<<mgrid, ST, 0, s>>>(spc, 0);
+            compact_move_kernel<<<dim3((unsigned)((p + 127) / 128), 3, (unsigned)F), 128, 0, s>>>(spc, src, newK);
             compact_cols_kernel<<<F, 32, 0, s>>>(sp, src, newK, colmap);
             LAUNCH_OK("compaction kernels");
             ctx->launches += 3;
@@ -1819,6 +1875,18 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
             grids(Kmax, cgrid, mgrid, fgrid);
             do_compact = false;
             if (sparse) {  // the column blocks moved: support flags from scratch
+                zflags_kernel<<<zgrid, 256, 0, s>>>(sp, fused ? Bc[par ^ 1] : Z);
+                LAUNCH_OK("zflags_kernel");
+            }
+        }
+        if (fused && clus) {
+            // the cluster kernels take over from the next iteration: hand them the two-kernel state
+            const int pn = par ^ 1;
+            fused_to_classic_kernel<<<mgrid, ST, 0, s>>>(sp, Bc[pn], Bc[par], GBc[par], it + 1, pn, use_rst);
+            LAUNCH_OK("fused_to_classic_kernel");
+            use_rst = 0;
+            fused = false;
+            if (sparse) {
                 zflags_kernel<<<zgrid, 256, 0, s>>>(sp, Z);
                 LAUNCH_OK("zflags_kernel");
             }
@@ -1826,7 +1894,11 @@ int slm_solve_batch(slm_ctx* ctx, slm_batch* bt, void* stream) {
     }
     bt->iters_run = it;
     // coefficients still in the working array go back to the caller's layout
-    scatter_done_kernel<<<mgrid, ST, 0, s>>>(sp, 1);
+    {
+        SolveDev spe = sp;
+        if (fused) spe.B = Bc[it & 1];
+        scatter_done_kernel<<<mgrid, ST, 0, s>>>(spe, 1);
+    }
     LAUNCH_OK("scatter_done_kernel");
 
     // final certificate from an exact G*B, in the original column order

@@ -30,7 +30,8 @@ constexpr int SC = 8;              // grid columns per block
 constexpr int SG = 32;             // group lanes per block
 constexpr int ST = SC * SG;        // threads per block
 constexpr int kMaxChunks = 64;     // group chunks per column (partials per column)
-constexpr int NQ = 5;              // partial quantities per (chunk, column)
+constexpr int NQ = 7;              // partial quantities per (chunk, column): 0-4 gap pieces / restart dot of the
+                                   // two-kernel iteration, 5-6 restart dots of the fused iteration (by parity)
 constexpr int MOM_ROWS = 256;      // rows per block in the momentum kernel
 
 struct SolveDev {
@@ -48,6 +49,8 @@ struct SolveDev {
     double* theta[2];
     double* tmom[2];
     double* part;  // [F][n_chunks][NQ][ldz]
+    double* rst;   // [F][ldz] restart dot of the last iteration, reduced over the chunks (fused iteration, after a compaction)
+    int direct;    // gap kernels: GZ holds G*B itself (fused iteration), not G*Z of the momentum recurrence
     int* flag;     // 0 active, 1 converged/frozen, 3 skipped by the caller
     double *gap, *primal;
     int *n_iter, *status;
@@ -297,6 +300,291 @@ __global__ void __launch_bounds__(ST) prox_momentum_kernel(const __grid_constant
     }
 }
 
+
+// ---- K6 fused: one kernel per iteration, 40 bytes per coefficient -------------------------------
+// The two-kernel iteration above materialises the extrapolated point Z = W_t + th (W_t - W_{t-1}), applies
+// the Gram to it, and needs a second pass (prox_momentum) because the restart test of iteration t decides
+// the momentum of Z_{t+1}.  The Gram apply is linear, so it can just as well act on the iterate itself:
+//     G Z_t = (1 + th) G W_t - th G W_{t-1}.
+// With W_t, W_{t-1}, G W_t, G W_{t-1} resident (two buffers each, swapped by parity), z and G z are formed on
+// the fly at the START of iteration t -- when the restart test of iteration t-1 is already known -- and one
+// kernel does momentum, gradient step, soft-threshold, group shrink, ridge, restart dot and the support flags
+// of the new iterate: reads W_t, W_{t-1}, G W_t, G W_{t-1}, writes W_{t+1} over W_{t-1} (40 bytes per
+// coefficient instead of three passes over five arrays), no T / Z round trip, one launch less.  Same
+// iterates as the two-kernel form (same restart rule, same theta sequence); G W_t is exact instead of a
+// recurrence, and the apply contracts over the support of W_t, a subset of that of Z_t.
+struct FusedArgs {
+    const double* Bcur;   // W_t
+    double* Bnew;         // holds W_{t-1} on entry, W_{t+1} on exit
+    const double* GBcur;  // G W_t (this iteration's apply)
+    const double* GBold;  // G W_{t-1}
+    double* stash;        // [F][p][ldz] scratch for groups too long for registers
+    int it;               // iteration index (0: no momentum)
+    int use_rst;          // restart dot of iteration it-1 from sp.rst (after a compaction) instead of the partials
+};
+
+// momentum coefficient of iteration `it` for one column: th = (t_{k-1} - 1) / t_k unless the last iteration's
+// restart dot was positive.  tm = t_{k-1} (tmom of the other parity), returns th and the new t_k in tn.
+__device__ __forceinline__ double fused_theta(int it, double tm, double dsum, double* tn) {
+    if (it == 0) {
+        *tn = tm;
+        return 0.0;
+    }
+    double t = 0.5 * (1.0 + sqrt(1.0 + 4.0 * tm * tm));
+    double th = (tm - 1.0) / t;
+    if (dsum > 0.0) {  // gradient-scheme adaptive restart (O'Donoghue & Candes)
+        th = 0.0;
+        t = 1.0;
+    }
+    *tn = t;
+    return th;
+}
+
+// FZ_RC: rows per lane kept in registers across the group-norm reduction (the host picks the smallest
+// instantiation that covers the largest group: unused row slots still cost issue slots)
+template <bool GROUPED, int FZ_RC>
+__global__ void __launch_bounds__(ST, GROUPED ? (FZ_RC <= 5 ? 3 : 2) : SLM_PROX_MINB)
+    prox_fused_kernel(const __grid_constant__ SolveDev sp, const __grid_constant__ FusedArgs fa, int par) {
+    const int f = blockIdx.z, chunk = blockIdx.y;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, gl = threadIdx.x / SC;
+    const int k = k0 + c;
+    __shared__ double red[SG][SC];
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const bool active = (k < Kf) && sp.flag[colbase] == 0;
+    const int sub = GROUPED ? (gl % SUB) : (gl % 4);   // which byte of a warp ballot holds this lane's 8 columns
+    const int gsl = GROUPED ? (gl / SUB) : gl;         // group slot of this lane
+    const int gstep = GROUPED ? GPB : SG;              // groups per block iteration
+    const int rstep = GROUPED ? SUB : 1;
+    const int rsub = GROUPED ? sub : 0;
+    if (__syncthreads_and(!active)) {
+        // nothing iterates in this column block any more: the rows of this chunk's groups leave the support
+        if (sp.zflag && c == 0)
+            for (int i = 0; i < sp.gpt; ++i) {
+                const int g = (chunk * sp.gpt + i) * gstep + gsl;
+                if (g >= sp.Gn) break;
+                const int ja = sp.gptr ? sp.gptr[g] : g, jb = sp.gptr ? sp.gptr[g + 1] : g + 1;
+                for (int j = ja + rsub; j < jb; j += rstep) sp.zflag[((long long)f * sp.p + j) * sp.nblk + blockIdx.x] = 0;
+            }
+        return;
+    }
+    // restart dot of the previous iteration (every block of the column sums the same partials in the same order)
+    double dsum = 0.0;
+    if (fa.it > 0) {
+        if (fa.use_rst) {
+            dsum = active ? sp.rst[colbase] : 0.0;
+        } else {
+            const int slot_in = 5 + (par ^ 1);
+            double acc = 0.0;
+            if (active)
+                for (int ch = gl; ch < sp.n_chunks; ch += SG)
+                    acc += sp.part[(((long long)f * sp.n_chunks + ch) * NQ + slot_in) * ldz + k];
+            dsum = lanes_sum(acc, red, gl, c);
+        }
+    }
+    double tn;
+    const double th = fused_theta(fa.it, active ? sp.tmom[par ^ 1][colbase] : 1.0, dsum, &tn);
+    if (active && chunk == 0 && gl == 0) {
+        sp.theta[par][colbase] = th;
+        sp.tmom[par][colbase] = tn;
+    }
+    const double* __restrict__ cvec = sp.G + (long long)f * sp.g_stride + (long long)sp.p * sp.pa;
+    const double n = sp.n_obs[f], step = sp.lips_dev ? 1.0 / sp.lips_dev[f] : sp.step[f];
+    const double son = step / n;
+    const int ko = (active && sp.colmap) ? sp.colmap[colbase] : k;  // original column (penalty arrays)
+    const int kk = active ? k : 0;  // inactive lanes of a partly active block shadow column 0 (reads only)
+    const long long sbase = (long long)f * sp.p * ldz + kk;
+    const long long wbase = (long long)f * sp.p * ldz + (active ? ko : 0);
+    const long long gbase = (long long)f * sp.Gn * ldz + (active ? ko : 0);
+    const double lam1 = (active && sp.lam1) ? sp.lam1[(long long)f * ldz + ko] : 0.0;
+    const unsigned qmask = 0x01010101u << c;
+    const unsigned lane = threadIdx.x & 31u;
+    const double* __restrict__ Bcur = fa.Bcur;
+    const double* __restrict__ GBcur = fa.GBcur;
+    const double* __restrict__ GBold = fa.GBold;
+
+    double dot = 0.0;
+    for (int i = 0; i < sp.gpt; ++i) {
+        const int g = (chunk * sp.gpt + i) * gstep + gsl;
+        if (GROUPED && g >= sp.Gn) break;  // uniform over the warp (a warp owns one group)
+        const bool gv = g < sp.Gn;         // singleton groups: the lanes of a warp hold different rows
+        const int ja = gv ? (sp.gptr ? sp.gptr[g] : g) : 0;
+        const int jb = gv ? (sp.gptr ? sp.gptr[g + 1] : g + 1) : 0;
+        const double w2 = (gv && sp.W2) ? sp.W2[gbase + (long long)g * ldz] : 0.0;
+        const double d2 = (gv && sp.D2) ? sp.D2[gbase + (long long)g * ldz] : 0.0;
+        if (!GROUPED || jb - ja <= FZ_RC * rstep) {
+            // the group's rows of this lane stay in registers across the norm reduction: one pass
+            constexpr int RC = GROUPED ? FZ_RC : 1;
+            // four loads per row in flight for all RC rows, then the registers are recycled: bb = W_t, zz takes
+            // the place of W_{t-1}, u that of G W_t
+            double bb[RC], zz[RC], u[RC], gbo[RC];
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < RC; ++r) {
+                const int j = ja + rsub + r * rstep;
+                bb[r] = zz[r] = u[r] = gbo[r] = 0.0;
+                if (j < jb) {
+                    const long long e = sbase + (long long)j * ldz;
+                    bb[r] = Bcur[e];
+                    zz[r] = fa.Bnew[e];
+                    u[r] = GBcur[e];
+                    gbo[r] = GBold[e];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RC; ++r) {
+                const int j = ja + rsub + r * rstep;
+                if (j < jb) {
+                    const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
+                    const double z = bb[r] + th * (bb[r] - zz[r]);
+                    const double gz = u[r] + th * (u[r] - gbo[r]);
+                    const double v = z - son * (gz - cvec[j]);
+                    zz[r] = z;
+                    u[r] = softt(v, step * w1);
+                    ss += u[r] * u[r];
+                } else {
+                    u[r] = 0.0;
+                }
+            }
+            if (GROUPED) ss = sub_sum(qmask, ss);
+            const double nrm = sqrt(ss);
+            double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
+            scale = scale / (1.0 + step * d2);
+#pragma unroll
+            for (int r = 0; r < RC; ++r) {
+                const int j = ja + rsub + r * rstep;
+                const bool inb = j < jb;
+                bool nz = false;
+                if (inb && active) {
+                    const double bn = scale * u[r];
+                    fa.Bnew[sbase + (long long)j * ldz] = bn;
+                    dot += (zz[r] - bn) * (bn - bb[r]);
+                    nz = bn != 0.0;
+                }
+                if (sp.zflag) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (c == 0 && inb)
+                        sp.zflag[((long long)f * sp.p + j) * sp.nblk + blockIdx.x] =
+                            (unsigned char)(((bal >> (lane & 24u)) & 0xffu) != 0u);
+                }
+            }
+        } else {
+            // long group (GROUPED only): u goes through the stash array, two passes
+            double ss = 0.0;
+            for (int j = ja + rsub; j < jb; j += rstep) {
+                const long long e = sbase + (long long)j * ldz;
+                const double b = Bcur[e], bo = fa.Bnew[e], gbn = GBcur[e], gbo = GBold[e];
+                const double w1 = sp.W1 ? sp.W1[wbase + (long long)j * ldz] : lam1;
+                const double z = b + th * (b - bo);
+                const double gz = gbn + th * (gbn - gbo);
+                const double u = softt(z - son * (gz - cvec[j]), step * w1);
+                if (active) fa.stash[e] = u;
+                ss += u * u;
+            }
+            ss = sub_sum(qmask, ss);
+            const double nrm = sqrt(ss);
+            double scale = nrm > 0.0 ? fmax(0.0, 1.0 - step * w2 / nrm) : 0.0;
+            scale = scale / (1.0 + step * d2);
+            const int trips = (jb - ja + rstep - 1) / rstep;  // uniform over the warp: the ballot needs whole warps
+            for (int t = 0; t < trips; ++t) {
+                const int j = ja + rsub + t * rstep;
+                const bool inb = j < jb;
+                bool nz = false;
+                if (inb && active) {
+                    const long long e = sbase + (long long)j * ldz;
+                    const double b = Bcur[e], bo = fa.Bnew[e];
+                    const double bn = scale * fa.stash[e];
+                    const double z = b + th * (b - bo);
+                    fa.Bnew[e] = bn;
+                    dot += (z - bn) * (bn - b);
+                    nz = bn != 0.0;
+                }
+                if (sp.zflag) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (c == 0 && inb)
+                        sp.zflag[((long long)f * sp.p + j) * sp.nblk + blockIdx.x] =
+                            (unsigned char)(((bal >> (lane & 24u)) & 0xffu) != 0u);
+                }
+            }
+        }
+    }
+    dot = lanes_sum(active ? dot : 0.0, red, gl, c);
+    if (active && gl == 0)
+        sp.part[(((long long)f * sp.n_chunks + chunk) * NQ + 5 + par) * ldz + k] = dot;
+}
+
+// columns flagged at this convergence check: their final iterate goes into BOTH iterate buffers, so that
+// whichever buffer is "current" when they are collected (compaction, end of the solve) holds it
+__global__ void __launch_bounds__(ST) settle_done_kernel(const __grid_constant__ SolveDev sp, const double* __restrict__ src,
+                                                         double* __restrict__ dst) {
+    const int f = blockIdx.z;
+    const int Kf = sp.K[f];
+    const int k = blockIdx.x * SC + threadIdx.x % SC;
+    const int r = threadIdx.x / SC;
+    if (k >= Kf || sp.flag[(long long)f * sp.ldz + k] != 1) return;
+    const long long sb = (long long)f * sp.p * sp.ldz + k;
+    const int j0 = blockIdx.y * MOM_ROWS, j1 = min(j0 + MOM_ROWS, sp.p);
+    for (int j = j0 + r; j < j1; j += SG) dst[sb + (long long)j * sp.ldz] = src[sb + (long long)j * sp.ldz];
+}
+
+// restart dot of iteration `par` summed over the chunks into sp.rst (before a compaction renumbers the columns)
+__global__ void restart_reduce_kernel(const __grid_constant__ SolveDev sp, int par) {
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sp.K[f]) return;
+    double acc = 0.0;
+    for (int ch = 0; ch < sp.n_chunks; ++ch) acc += sp.part[(((long long)f * sp.n_chunks + ch) * NQ + 5 + par) * sp.ldz + k];
+    sp.rst[(long long)f * sp.ldz + k] = acc;
+}
+
+// fused -> two-kernel state at the start of iteration `it` (the cluster / cooperative kernels and the
+// two-kernel iteration work on Z, B, GB, theta): Z = W_t + th (W_t - W_{t-1}), B = W_t, GB = G W_{t-1},
+// theta[par] = th, tmom[par] = t_k.  Bcur / Bold / GBold may alias sp.B / sp.GB (element-wise, read before write).
+__global__ void __launch_bounds__(ST) fused_to_classic_kernel(const __grid_constant__ SolveDev sp, const double* Bcur,
+                                                              const double* Bold, const double* GBold, int it,
+                                                              int par, int use_rst) {
+    const int f = blockIdx.z;
+    const int Kf = sp.K[f];
+    const int k0 = blockIdx.x * SC;
+    if (k0 >= Kf) return;
+    const int c = threadIdx.x % SC, r = threadIdx.x / SC;
+    const int k = k0 + c;
+    __shared__ double red[SG][SC];
+    const long long ldz = sp.ldz;
+    const long long colbase = (long long)f * ldz + k;
+    const bool active = (k < Kf) && sp.flag[colbase] == 0;
+    double dsum = 0.0;
+    if (it > 0) {
+        if (use_rst) {
+            dsum = active ? sp.rst[colbase] : 0.0;
+        } else {
+            double acc = 0.0;
+            if (active)
+                for (int ch = r; ch < sp.n_chunks; ch += SG)
+                    acc += sp.part[(((long long)f * sp.n_chunks + ch) * NQ + 5 + (par ^ 1)) * ldz + k];
+            dsum = lanes_sum(acc, red, r, c);
+        }
+    }
+    double tn;
+    const double th = fused_theta(it, active ? sp.tmom[par ^ 1][colbase] : 1.0, dsum, &tn);
+    const long long sb = (long long)f * sp.p * ldz + k;
+    const int j0 = blockIdx.y * MOM_ROWS, j1 = min(j0 + MOM_ROWS, sp.p);
+    if (k < Kf && sp.flag[colbase] != 3)  // columns the caller froze never entered the iterate buffers
+        for (int j = j0 + r; j < j1; j += SG) {
+            const long long e = sb + (long long)j * ldz;
+            const double b = Bcur[e], bo = Bold[e], gbo = GBold[e];
+            sp.Z[e] = active ? b + th * (b - bo) : b;
+            sp.B[e] = b;
+            sp.GB[e] = gbo;
+        }
+    if (active && blockIdx.y == 0 && r == 0) {
+        sp.theta[par][colbase] = th;
+        sp.tmom[par][colbase] = tn;
+    }
+}
 
 // ---- K6 (second mapping): one lane per grid column --------------------------------------------
 // prox_main_kernel / prox_momentum_kernel above give a row of the state arrays to 8 threads (a
@@ -644,7 +932,7 @@ __global__ void __launch_bounds__(ST) gap_partial_kernel(const __grid_constant__
 
     auto gb_at = [&](long long e) {
         const double gz = sp.GZ[e];
-        return final_mode ? gz : (gz + theta * sp.GB[e]) * inv1pt;
+        return (final_mode || sp.direct) ? gz : (gz + theta * sp.GB[e]) * inv1pt;
     };
 
     double cb = 0.0, bgb = 0.0, pen = 0.0, ridge = 0.0, lbmax = 0.0;
@@ -887,6 +1175,7 @@ __global__ void compact_cols_kernel(const __grid_constant__ SolveDev sp, const i
             sp.theta[par][base + kc] = sp.theta[par][base + k];
             sp.tmom[par][base + kc] = sp.tmom[par][base + k];
         }
+        if (sp.rst) sp.rst[base + kc] = sp.rst[base + k];
         colmap[base + kc] = colmap[base + k];
         sp.flag[base + kc] = 0;
     }
