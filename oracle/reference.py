@@ -27,14 +27,18 @@ restatement of the *problem* (convex, so any exact solver agrees) by a cyclic
 block-coordinate descent in C (slm_oracle.c) that is certified by a duality gap
 computed from X and y.
 
-PARITY PINNING: Lasso is pinned by the reference's only numeric known-answer
-test (tests/test_lasso.py:29-61) and by sklearn's coordinate-descent Lasso on
-random problems (the source of that KAT).  For GroupLasso / OverlapGroupLasso /
-SparseGroupLasso / RidgedGroupLasso / Adaptive* coefficient VALUES the
-reference's tests hold no golden vectors: **parity unpinned** against the
-reference for those, pinned only by solver-independent optimality certificates
-(KKT, duality gap), closed forms on orthonormal designs and the reference's
-structural tests.
+PARITY PINNING: pinned by the reference's OWN problem-building code.  tests/golden/make_golden_reference.py
+installs a numeric stand-in for the cvxpy names the reference uses (tests/golden/cvxpy_shim.py), loads
+/root/reference/src/sparselm/model/_lasso.py, _adaptive_lasso.py and _base.py by path and calls the reference's
+_generate_params / _generate_auxiliaries / _generate_objective (_base.py:453-458) and _iterative_update
+(_adaptive_lasso.py:196-204, 364-374, 712-726).  The committed fixtures (tests/golden/golden_reference.json, 57
+cases over all ten estimators) hold the reference's objective values, its adaptive weight updates and a minimiser
+of the reference's objective with an independent KKT certificate; tests/test_reference_fixtures.py checks this
+module against them (objective to 1e-13, minimiser, weights).  In addition: the reference's only numeric
+known-answer test (tests/test_lasso.py:29-61), sklearn's coordinate-descent Lasso on random problems, third-party
+conic solutions (tests/golden/make_golden_nlp.py), closed forms on orthonormal designs and the reference's
+structural tests.  What cannot run here is the reference's solver (cvxpy + a conic backend): the solve is a
+restatement of the convex problem, certified by a duality gap computed from X and y.
 """
 
 from __future__ import annotations
