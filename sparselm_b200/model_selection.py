@@ -204,6 +204,13 @@ def batched_cv(engine, X, y, test_folds, ests, specs, opts, scoring, return_trai
     iters_run = 0
 
     fds = {} if fds is None else dict(fds)  # may arrive pre-populated (prepare started early)
+    if n_cand and _fold_key(ests[0], specs[0]) not in fds:
+        # enqueue the GPU side of the preparation (H2D, packing, Gram build) before the host-side grouping and
+        # ordering of the candidates below: that Python work then runs while the GPU is busy
+        x_dev = isinstance(X, torch.Tensor) and X.is_cuda
+        score_folds = set() if (sharded and cache is None and not x_dev) else None
+        fds[_fold_key(ests[0], specs[0])] = prepare_folds(engine, X, yv, test_folds, ests[0], specs[0], cache, cache_key,
+                                                         shard, sample_weight, score_folds)
     warm = _WarmStarts()  # candidate -> device view [pe] of its solution on some training fold (refit start)
     batches = {}
     for ci, s in enumerate(specs):
