@@ -155,6 +155,17 @@ class EngineRegressor(RegressorMixin, BaseEstimator, metaclass=ABCMeta):
 
     def _validate_hyperparams(self, X, y) -> None:
         """Reference: CVXRegressor._validate_params(X, y) (_base.py:229-245)."""
+        only = self.__dict__.get("_validate_only")
+        if only:
+            # a grid search re-parametrises ONE working estimator per candidate: every parameter was validated
+            # for the first candidate, only the grid's own parameters can have changed since
+            from sklearn.utils._param_validation import validate_parameter_constraints
+
+            cons = self._parameter_constraints
+            validate_parameter_constraints({k: cons[k] for k in only if k in cons},
+                                           {k: getattr(self, k) for k in only if k in cons},
+                                           caller_name=self.__class__.__name__)
+            return
         self._validate_params()  # sklearn: checks _parameter_constraints
 
     def _engine_options(self):

@@ -110,6 +110,8 @@ class GroupLasso(Lasso):
         cache = self.__dict__.get("_group_cache")
         if cache is None or cache[0] is not self.groups or cache[1] != n_features:
             return None
+        if self.__dict__.get("_groups_frozen"):
+            return cache  # inside one grid-search plan: `groups` cannot have been mutated since the last check
         if self.groups is not None and hash(np.asarray(self.groups).tobytes()) != cache[6]:
             return None
         return cache

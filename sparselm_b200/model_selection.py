@@ -485,6 +485,12 @@ class GridSearchCV(_SkGridSearchCV):
 
             for ci, c in enumerate(candidates):
                 work.set_params(**c)
+                if ci == 1:
+                    # from the second candidate on only the grid's own parameters are re-validated, and the
+                    # group structure memoised for the first candidate is reused without re-hashing `groups`
+                    # (the working estimator is private to this loop)
+                    work.__dict__["_validate_only"] = set().union(*[set(cc) for cc in candidates])
+                    work.__dict__["_groups_frozen"] = True
                 with _w.catch_warnings():
                     if ci > 0:  # structural warnings (e.g. groups=None) are emitted once
                         _w.simplefilter("ignore", UserWarning)
