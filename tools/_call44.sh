@@ -1,0 +1,2 @@
+set -x
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -5
