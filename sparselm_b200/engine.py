@@ -693,7 +693,7 @@ class Engine:
         """Solve grids[f] (a PenaltyGrid) on Gram G[f] for every f, as one batch.
 
         newton: pure group penalties only (no l1 term) -- columns that have not converged after a
-        first stretch of 500 iterations get a lock-step Newton phase on their active groups
+        first stretch of NEWTON_FIRST iterations get a lock-step Newton phase on their active groups
         (sparselm_b200/newton.py) between further stretches.  None (default) = on for
         160 < p <= 2048: below, the fused small-design kernel iterates at ~0.3 us per iteration;
         above, one p x p factorisation per column and step costs more than the iterations it saves

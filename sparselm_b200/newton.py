@@ -1,6 +1,6 @@
 """Second-order phase for slow columns of a batched solve: lock-step Newton on the active manifold.
 
-Why ("known weak spot"): accelerated proximal-gradient iterations need
+Why ("C4, the ill-conditioned case"): accelerated proximal-gradient iterations need
 ~sqrt(condition number) iterations.  A group-penalised problem whose penalty is nearly flat on its
 support (the adaptive passes weight an active group by alpha^2/||b_g||, reference
 _adaptive_lasso.py:364-374) on a Gram with exactly flat directions (the duplicated columns of the
@@ -16,8 +16,8 @@ factorisations.  The conic interior-point solvers behind the reference's cvxpy c
 
 What this module does: host-side orchestration, all slow columns in lock step.  On the GPU
 (``newton_phase_device``) every Newton step is ONE call into the engine (``slm_newton_step``,
-csrc/newton_kernels.cuh): Hessian assembly straight from the Gram, a batched blocked Cholesky whose
-trailing updates run on the FP64 tensor-core GEMM, blocked triangular solves and the Armijo line
+csrc/newton_kernels.cuh): Hessian assembly straight from the Gram on the active coordinates of every column, a
+batched blocked Cholesky whose trailing updates run on the TMA-fed FP64 tensor-core GEMM, blocked triangular solves and the Armijo line
 search -- no library factorisation, no ``[k, p, p]`` copies of the Gram, no host synchronisation
 inside a step.  ``newton_phase`` is the same iteration written with torch operations
 (``torch.linalg.cholesky_ex``); it runs on CPU tensors in ``tests/test_newton.py`` and is the model the
@@ -29,9 +29,10 @@ decreases phi (Armijo test on the *difference* of objective values, formed witho
 Scope: pure group penalties (no l1 term) with optional ridge: GroupLasso, OverlapGroupLasso,
 RidgedGroupLasso and their adaptive variants (also in whitened variables, standardize=True).
 On by default for 160 < p <= 2048 (engine.Engine.solve); ``solver_options={"newton": True / False}``
-forces it.  Measured on C4 (AdaptiveOverlapGroupLasso, 20 alphas x 5 folds x 3 passes, p_ext = 1961): 2.1 s per
-search against 12.4 s, 2100 iterations against 129 350, no column left on max_iter (6 before), scores
-equal to 3e-8 relative; 1109 factorisations per search, batched cuSOLVER potrf 0.39 ms each at n = 1961.
+forces it.  Measured on C4 (AdaptiveOverlapGroupLasso, 20 alphas x 5 folds x 3 passes, p_ext = 1961): 0.41 s per
+search against 12.4 s first-order only (round 1 with torch / cuSOLVER: 1.25 s), 1155 iterations against 129 350,
+no column left on max_iter (6 before), scores equal to 3e-8 relative; 1384 factorisations per search on the active
+coordinates of every column.
 """
 
 from __future__ import annotations
