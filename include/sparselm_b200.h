@@ -45,9 +45,11 @@ void slm_destroy(slm_ctx* ctx);
  * "dense_apply" (solver uses the dense Gram apply), "chunk_w" (columns per support chunk),
  * "tma" (bit mask of the kernel families fed by TMA + mbarrier instead of cp.async: 1 Gram build,
  * 2 dense Gram apply, 4 row-sparse Gram apply, 8 / 16 wide padded-pitch bands instead of 128-byte
- * swizzled boxes for the gather / tiled kernels; default 15), "prox2" (one-lane-per-column prox kernels,
- * default 0: measured slower than the 8-columns-per-row mapping), "force_apply_shape" / "force_sparse_shape" / "force_syrk_shape" (tile menu overrides of
- * tools/gemm_probe.py, -1 = automatic). */
+ * swizzled boxes for the gather / tiled kernels; default 15), "fused_prox" (default 1: one prox_fused_kernel per
+ * iteration on the iterate buffers, the Gram applied to the iterate itself; 0: the two-kernel iteration on a
+ * materialised extrapolated point), "prox2" (one-lane-per-column prox kernels of the two-kernel iteration,
+ * default 0: measured slower than the 8-columns-per-row mapping), "force_apply_shape" / "force_sparse_shape" /
+ * "force_syrk_shape" (tile menu overrides of tools/gemm_probe.py, -1 = automatic). */
 int slm_set_option(slm_ctx* ctx, const char* name, int value);
 const char* slm_last_error(const slm_ctx* ctx);
 int slm_sm_count(const slm_ctx* ctx);
