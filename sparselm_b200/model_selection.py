@@ -332,14 +332,13 @@ def _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, 
     rank's partial sums [n_splits, 2, K] (test rows) and the same for the training rows (or None)."""
     import ctypes
 
+    from .parallel import gather_layout, scoring_plan
+
     torch = engine.torch
     W = shard.world
-    # send layout: [p + 1][ldg], the columns this rank solved, fold after fold, every fold's group padded to a
-    # multiple of 8 columns (only what was solved travels: C3 on 8 ranks, 2.6 MB per rank)
-    kfr = np.array([[int((owner[f] == r).sum()) for f in range(n_splits)] for r in range(W)])  # [W, n_splits]
-    pad = (kfr + 7) // 8 * 8
-    off = np.concatenate([np.zeros((W, 1), dtype=np.int64), np.cumsum(pad, axis=1)], axis=1)  # [W, n_splits + 1]
-    ldg = max(8, int(off[:, -1].max()))
+    # send layout: [p + 1][ldg], the columns this rank solved, fold after fold (only what was solved travels: C3 on
+    # 8 ranks, 2.6 MB per rank)
+    kfr, pad, off, ldg = gather_layout(owner, W)
     send = torch.zeros((p + 1, ldg), dtype=torch.float64, device=engine.device)
     for f in range(n_splits):
         kf = len(mine[f])
@@ -355,34 +354,18 @@ def _sharded_residual_sums(engine, shard, fd, out, owner, mine, p, K, n_splits, 
                                                  send.numel(), engine.stream), "slm_gather_results")
     else:
         shard.all_gather_(send, recv)
-    rows = shard.fold_row_ranges(fd.row_ptr)
     # every (fold, solving rank) group against this rank's slice of the fold's rows -- and, for train scores,
     # against its slices of the other folds -- as ONE batched scoring launch
-    items, where = [], []
-    for f in range(n_splits):
-        for r in range(W):
-            kf = int(kfr[r, f])
-            if kf == 0:
-                continue
-            o = int(off[r, f])
-            Bfr = recv[r, :p, o:o + int(pad[r, f])]
-            icpt = recv[r, p, o:o + kf] if fd.fit_intercept else None
-            cols = np.flatnonzero(owner[f] == r)
-            lo, hi = rows[f]
-            if hi > lo:
-                items.append((lo, hi, Bfr, kf, icpt))
-                where.append((0, f, cols))
-            if want_train:
-                for f2 in range(n_splits):
-                    lo2, hi2 = rows[f2]
-                    if f2 != f and hi2 > lo2:
-                        items.append((lo2, hi2, Bfr, kf, icpt))
-                        where.append((1, f, cols))
+    plan = scoring_plan(owner, shard.fold_row_ranges(fd.row_ptr), W, want_train)
+    items = []
+    for lo, hi, r, f, kind, cols in plan:
+        o, kf = int(off[r, f]), len(cols)
+        items.append((lo, hi, recv[r, :p, o:o + int(pad[r, f])], kf, recv[r, p, o:o + kf] if fd.fit_intercept else None))
     part = np.zeros((n_splits, 2, K))
     tpart = np.zeros((n_splits, 2, K)) if want_train else None
     if items:
         res = engine.cv_score_many(fd.Xa, p, items, rows_scaled=wtd).cpu().numpy()  # one D2H
-        for i, (kind, f, cols) in enumerate(where):
+        for i, (lo, hi, r, f, kind, cols) in enumerate(plan):
             tgt = part if kind == 0 else tpart
             tgt[f][:, cols] += res[i][:, :len(cols)]
     return part, tpart

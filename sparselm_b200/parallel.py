@@ -19,7 +19,7 @@ import functools
 
 import numpy as np
 
-__all__ = ["GridShard", "assign_columns"]
+__all__ = ["GridShard", "assign_columns", "gather_layout", "scoring_plan"]
 
 
 @functools.lru_cache(maxsize=64)
@@ -56,6 +56,47 @@ def _assign_columns(n_folds: int, n_cols: int, world: int):
             owner[f, k] = r
             given[r] += 1
     return owner
+
+
+def gather_layout(owner, world: int):
+    """Layout of the coefficient exchange of a row-sharded scoring (model_selection._sharded_residual_sums).
+
+    Every rank sends ONE [p + 1][ldg] block: the columns it solved, fold after fold, every fold's group padded to
+    a multiple of 8 columns (the scoring GEMM reads a group through a 16-byte aligned pointer with row stride ldg).
+    Returns (kfr, pad, off, ldg): kfr[r][f] = columns rank r solved on fold f, pad = kfr rounded up to 8,
+    off[r][f] = first column of that group in rank r's block, ldg = common block width (>= 8, multiple of 8)."""
+    owner = np.asarray(owner)
+    n_splits = owner.shape[0]
+    kfr = np.array([[int((owner[f] == r).sum()) for f in range(n_splits)] for r in range(world)], dtype=np.int64)
+    pad = (kfr + 7) // 8 * 8
+    off = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(pad, axis=1)], axis=1)
+    ldg = max(8, int(off[:, -1].max()))
+    return kfr, pad, off, ldg
+
+
+def scoring_plan(owner, rows, world: int, want_train: bool = False):
+    """The scoring problems of ONE rank of a row-sharded scoring: rows[f] = (lo, hi) is the rank's slice of test fold
+    f's rows.  Every (fold f, solving rank r) group of columns is scored on the rank's slice of fold f (kind 0: test
+    residual sums) and, for train scores, on its slices of the other folds (kind 1).  Returns a list of
+    (lo, hi, r, f, kind, cols): cols = the grid columns of the group (owner[f] == r), in the order they were sent.
+    Summed over the ranks, kind 0 covers every (column, test row) pair exactly once."""
+    owner = np.asarray(owner)
+    n_splits = owner.shape[0]
+    plan = []
+    for f in range(n_splits):
+        for r in range(world):
+            cols = np.flatnonzero(owner[f] == r)
+            if len(cols) == 0:
+                continue
+            lo, hi = rows[f]
+            if hi > lo:
+                plan.append((int(lo), int(hi), r, f, 0, cols))
+            if want_train:
+                for f2 in range(n_splits):
+                    lo2, hi2 = rows[f2]
+                    if f2 != f and hi2 > lo2:
+                        plan.append((int(lo2), int(hi2), r, f, 1, cols))
+    return plan
 
 
 class GridShard:
@@ -102,7 +143,9 @@ class GridShard:
         """recv[r] = send of rank r (torch tensors; recv has a leading world dimension)."""
         import torch.distributed as dist
 
-        dist.all_gather_into_tensor(recv, send, group=self.group)
+        # concatenated form [world * d0, ...]: the one every backend accepts (gloo rejects the stacked shape)
+        flat = recv.view((recv.shape[0] * send.shape[0],) + tuple(send.shape[1:])) if send.dim() >= 1 else recv
+        dist.all_gather_into_tensor(flat, send.contiguous(), group=self.group)
         return recv
 
     def allreduce_sum_(self, tensor):
