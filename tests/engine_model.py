@@ -133,3 +133,60 @@ def solve(pb: BatchProblem, tol=1e-10, floor_rel=1e-14, max_iter=20000, check_ev
     GBx = pb.G @ B
     P, D, g = gap_terms(pb, B, GBx)
     return B, {"iters": iters, "gap": g, "primal": P, "done": done, "total_iters": it}
+
+
+def solve_fused(pb: BatchProblem, tol=1e-10, floor_rel=1e-14, max_iter=20000, check_every=10, B0=None):
+    """The fused iteration of csrc/solver_kernels.cuh (prox_fused_kernel) in numpy: the state is W_t, W_{t-1},
+    G W_t, G W_{t-1}; the Gram acts on the iterate, the extrapolated point and its product are formed on the fly at
+    the START of iteration t, when the restart test of iteration t-1 is known:
+
+        z_t = W_t + th_t (W_t - W_{t-1}),   G z_t = (1 + th_t) G W_t - th_t G W_{t-1},
+        th_t = (t_{k-1} - 1) / t_k  unless  dot_{t-1} = sum (z_{t-1} - W_t)(W_t - W_{t-1}) > 0  (then th_t = 0, t_k = 1).
+
+    Same restart rule and theta sequence as `solve` (the two-kernel form): the iterates agree up to rounding."""
+    p, K = pb.p, pb.K
+    W = np.zeros((p, K)) if B0 is None else B0.copy()
+    Wold = W.copy()
+    GWold = np.zeros((p, K))
+    tm = np.ones(K)                 # t_{k-1}
+    dot = np.zeros(K)               # restart dot of the previous iteration
+    done = np.zeros(K, bool)
+    iters = np.zeros(K, int)
+    floor = max(floor_rel, 4e-15 / tol) * pb.yty / (2 * pb.n)
+    step = 1.0 / pb.L
+    for it in range(max_iter):
+        GW = pb.G @ W               # exact product of the iterate (the kernel contracts over its support rows)
+        if it % check_every == 0:
+            P, D, g = gap_terms(pb, W, GW)
+            newly = (~done) & (g <= tol * np.maximum(np.abs(P), floor))
+            iters[newly] = it
+            done |= newly
+            if done.all():
+                break
+        if it == 0:
+            th, tn = np.zeros(K), tm.copy()
+        else:
+            tn = (1 + np.sqrt(1 + 4 * tm * tm)) / 2
+            th = (tm - 1) / tn
+            th = np.where(dot > 0, 0.0, th)
+            tn = np.where(dot > 0, 1.0, tn)
+        Z = W + th * (W - Wold)
+        GZ = GW + th * (GW - GWold)
+        V = Z - step * (GZ - pb.c[:, None]) / pb.n
+        U = soft(V, step * pb.W1)
+        ss = np.add.reduceat(U * U, pb.gptr[:-1], axis=0)
+        nrm = np.sqrt(ss)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sc = np.where(nrm > 0, np.maximum(0.0, 1.0 - step * pb.W2 / np.where(nrm > 0, nrm, 1)), 0.0)
+        sc = sc / (1.0 + step * pb.D2)
+        Wn = U * sc[pb.gid]
+        dot_new = ((Z - Wn) * (Wn - W)).sum(0)
+        # finished columns keep their state (settle_done_kernel: the final iterate sits in both buffers)
+        Wold = np.where(done, W, W)
+        GWold = np.where(done, GWold, GW)
+        W = np.where(done, W, Wn)
+        tm = np.where(done, tm, tn)
+        dot = np.where(done, dot, dot_new)
+    iters[~done] = max_iter
+    P, D, g = gap_terms(pb, W, pb.G @ W)
+    return W, {"iters": iters, "gap": g, "primal": P, "done": done, "total_iters": it}
