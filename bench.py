@@ -763,11 +763,12 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     dense_equiv = ap["flops"] / (ap["ms"] * 1e-3) / 1e12 if ap["ms"] > 0 else None
     # DRAM bytes per launch of the dominant kernel from an ncu --set full capture of THIS workload on one GPU
     # (profiles/): a constant of that capture, so it is only quoted for the configuration it was taken on
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_build = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if world == 1 and os.path.exists(tpath):
         ent = json.load(open(tpath)).get(args.workload, {})
         traffic, traffic_src = ent.get("gram_apply_dram_bytes_per_launch"), ent.get("source")
+        traffic_build = ent.get("gram_build_dram_bytes_per_launch")
     step_ms = {k: v["ms"] / args.steps for k, v in tim.items()}
     info = res["info"]
     gb = tim["gram_build"]
@@ -776,7 +777,9 @@ def finish(args, wl, res, engine, tim, exec_flops, dense_flops, ms, value, e2e, 
     roof_build = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel<SYM> (Gram build, TMA-fed FP64 DMMA, SYRK flop count)",
                   "achieved": build_tf, "peak": peak, "unit": "TFLOP/s", "frac": build_tf / peak if build_tf else None,
                   "peak_source": src, "avg_launch_ms": gb["ms"] / max(gb["launches"], 1),
-                  "launches_per_step": gb["launches"] / args.steps, "traffic": None}
+                  "launches_per_step": gb["launches"] / args.steps, "traffic": traffic_build,
+                  "traffic_source": None if traffic_build is None else "ncu --set full capture of this workload's build "
+                                    "launch on one GPU (profiles/r02z_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum"}
     roof_apply = {"bound": "tensor", "kernel": "gemm_f64_tma_kernel (row-sparse Gram apply, TMA gather4-fed FP64 DMMA)",
                   "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                   "peak_source": src, "dense_equivalent_tflops": dense_equiv,
